@@ -1,0 +1,162 @@
+/* tandem_b200 — C ABI of the B200-native replacement for TANDEM's libdr (dense per-frame hot path).
+ *
+ * One opaque handle per object, int return codes (0 = ok, <0 = error, text via tdm_last_error()),
+ * no exceptions and no C++/torch types across the boundary, all pointers caller-owned unless stated.
+ * Blocking / non-blocking behaviour mirrors the reference classes each group replaces:
+ *
+ *   tdm_mvsnet_*   <->  class DrMvsnet          tandem/libdr/dr_mvsnet/src/dr_mvsnet/dr_mvsnet.h:36-66
+ *   tdm_fusion_*   <->  class DrFusion          tandem/libdr/dr_fusion/src/dr_fusion/dr_fusion.h:44-73
+ *   tdm_tracker_*  <->  class CudaCoarseTracker tandem/libdr/cuda_coarse_tracker/include/public/cuda_coarse_tracker.h:9-82
+ *
+ * The header-compatible C++ shims over this ABI live in include/dr_mvsnet/, include/dr_fusion/ and
+ * include/cuda_coarse_tracker/ ; INTEGRATION.md shows how tandem/CMakeLists.txt:118-121 links them.
+ */
+#ifndef TANDEM_B200_H
+#define TANDEM_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TDM_OK 0
+#define TDM_ERR (-1)
+#define TDM_PRECISION_FP32 0
+#define TDM_PRECISION_MIXED16 1 /* fp16 activations, bf16 cost volume (range), fp32 accumulate */
+#define TDM_PRECISION_BF16 2    /* bf16 everywhere (accuracy study only: misses the 1e-3 Abs Rel budget) */
+
+/* Thread-local text of the last error raised by any tdm_* call on this thread. */
+const char* tdm_last_error(void);
+/* Library / build identification: "tandem_b200 <version> sm_100a". */
+const char* tdm_version(void);
+/* Number of CUDA devices visible (0 on a CPU-only box; never throws). */
+int tdm_device_count(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * CVA-MVSNet (replaces DrMvsnet; dr_mvsnet.h:36-66, implementation dr_mvsnet.cpp:125-331)
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct tdm_mvsnet tdm_mvsnet;
+
+/* weights_path: a .tdmw container, or the reference's ".../model.pt" path, in which case the sidecar
+ * ".../model.tdmw" next to it is loaded (DrMvsnet(char const* filename), dr_mvsnet.cpp:333).
+ * precision: activation storage type; accumulation is always fp32. device: CUDA ordinal. */
+int tdm_mvsnet_create(const char* weights_path, int precision, int device, tdm_mvsnet** out);
+void tdm_mvsnet_destroy(tdm_mvsnet* h);
+
+/* DrMvsnet::CallAsync (dr_mvsnet.h:43-53): "blocking for last input, non-blocking for this input".
+ * bgrs[i]: H*W*3 uint8 BGR interleaved, window order, reference view at ref_index; intrinsic: 3x3
+ * row-major full resolution (stage K's derived as rows0-1 * 0.25 / 0.5 / 1, dr_mvsnet.cpp:220-247);
+ * cam_to_worlds[i]: 4x4 row-major. All inputs are copied before the call returns. */
+int tdm_mvsnet_call_async(tdm_mvsnet* h, int height, int width, int view_num, int ref_index,
+                          unsigned char* const* bgrs, const float* intrinsic_matrix,
+                          float* const* cam_to_worlds, float depth_min, float depth_max,
+                          float discard_percentage);
+/* Same, with the three per-stage intrinsics given explicitly (9 floats each, stage1..stage3) — the
+ * entry the golden-vector tests use, because export_model.py's K's are centre-preserving
+ * (cva_mvsnet/models/datasets.py:144-174) while the C++ wrapper's are not. */
+int tdm_mvsnet_call_async_k(tdm_mvsnet* h, int height, int width, int view_num, int ref_index,
+                            unsigned char* const* bgrs, const float* intrinsics_stage123,
+                            float* const* cam_to_worlds, float depth_min, float depth_max,
+                            float discard_percentage);
+/* DrMvsnet::GetResult (blocking). Copies the stage-3 maps (H*W floats each; any pointer may be NULL)
+ * into caller memory: depth/confidence are edge-filtered, *_dense unfiltered (dr_mvsnet.cpp:296-329).
+ * Calling it twice without a new CallAsync is an error, as in the reference (dr_mvsnet.cpp:100-102). */
+int tdm_mvsnet_get_result(tdm_mvsnet* h, float* depth, float* confidence, float* depth_dense,
+                          float* confidence_dense);
+int tdm_mvsnet_ready(tdm_mvsnet* h); /* 1 ready, 0 busy  (DrMvsnet::Ready) */
+int tdm_mvsnet_wait(tdm_mvsnet* h);  /* DrMvsnet::Wait */
+
+/* Options (call before the first call_async): filter_all_stages=1 also edge-filters stages 1 and 2
+ * (the Python model does, cva_mvsnet.py:165-173; the C++ consumer only reads stage 3).
+ * keep_intermediates=1 keeps every layer output alive for tdm_mvsnet_debug_tensor. */
+int tdm_mvsnet_set_option(tdm_mvsnet* h, const char* key, int value);
+/* Stage outputs of the last finished call: which = "depth"|"confidence"|"depth_dense"|"confidence_dense"|"edge". */
+int tdm_mvsnet_stage_output(tdm_mvsnet* h, int stage /*1..3*/, const char* which, float* out, size_t capacity);
+/* Test hook: copy a named intermediate of the last call as planar fp32 [C][D][H][W]; dims4 receives C,D,H,W.
+ * Returns the number of floats written, or <0. */
+long long tdm_mvsnet_debug_tensor(tdm_mvsnet* h, const char* name, float* out, size_t capacity, int* dims4);
+
+/* Device-resident measurement: re-runs the forward of the last submitted window `iters` times on the
+ * handle's stream with inputs already in HBM (no H2D/D2H inside), timed with CUDA events on that stream.
+ * ms_total receives the elapsed milliseconds; launches (optional) the kernel launches per forward. */
+int tdm_mvsnet_run_resident(tdm_mvsnet* h, int iters, float* ms_total, int* launches);
+/* Per-kernel CUDA-event timing of one resident forward: writes lines "name ms algorithmic_bytes flops\n"
+ * into buf (NUL terminated). Returns bytes written or <0. */
+long long tdm_mvsnet_profile(tdm_mvsnet* h, char* buf, size_t capacity);
+
+/* ------------------------------------------------------------------------------------------------
+ * TSDF fusion (replaces DrFusion; dr_fusion.h:18-73, implementation dr_fusion/src/tsdfvh/tsdf_volume.cu)
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct tdm_fusion tdm_fusion;
+typedef struct tdm_fusion_options { /* field-for-field DrFusionOptions, dr_fusion.h:18-36 */
+  float voxel_size;
+  int num_buckets;
+  int bucket_size;
+  int num_blocks;
+  int block_size;
+  int max_sdf_weight;
+  float truncation_distance;
+  float max_sensor_depth;
+  float min_sensor_depth;
+  int num_render_streams;
+  float fx, fy, cx, cy;
+  int height, width;
+} tdm_fusion_options;
+
+int tdm_fusion_create(const tdm_fusion_options* opt, int device, tdm_fusion** out);
+void tdm_fusion_destroy(tdm_fusion* h);
+/* DrFusion::IntegrateScanAsync (dr_fusion.h:50): bgr H*W*3 u8, depth H*W f32 metric z-depth, pose 4x4
+ * row-major cam->world; inputs are copied into pinned staging before returning (tsdf_volume.cu:542-543). */
+int tdm_fusion_integrate_async(tdm_fusion* h, const unsigned char* bgr, const float* depth, const float* pose);
+/* DrFusion::RenderAsync (dr_fusion.h:52): n_poses must equal num_render_streams (tsdf_volume.cu:643-648). */
+int tdm_fusion_render_async(tdm_fusion* h, const float* const* camera_poses, int n_poses);
+/* DrFusion::GetRenderResult (dr_fusion.h:54): pointers into a pinned double buffer owned by the handle,
+ * valid until the next get_render_result (tsdf_volume.cu:710-732). bgr_out/depth_out: arrays of n_poses. */
+int tdm_fusion_get_render_result(tdm_fusion* h, unsigned char** bgr_out, float** depth_out, int n_poses);
+int tdm_fusion_synchronize(tdm_fusion* h);
+/* Mesh (DrFusion::ExtractMeshAsync/GetMeshSync/GetMesh, dr_fusion.h:56-68): vertices as xyz float triples,
+ * colours as rgb float triples, 3 vertices per triangle. Returns vertex count or <0. */
+long long tdm_fusion_extract_mesh(tdm_fusion* h, const float lower[3], const float upper[3],
+                                  float* vert, float* cols, size_t max_vertices);
+/* Introspection for parity tests and the roofline: counters of the last integrate / render. */
+typedef struct tdm_fusion_stats {
+  long long allocated_blocks;      /* total blocks in the map */
+  long long visible_blocks;        /* blocks integrated in the last scan */
+  long long dropped_blocks;        /* bucket overflows (never allocated), cumulative */
+  long long candidate_blocks;      /* distinct blocks touched by the last allocation pass */
+} tdm_fusion_stats;
+int tdm_fusion_get_stats(tdm_fusion* h, tdm_fusion_stats* out);
+/* Dump the block map: xyz int triples (sorted lexicographically) into coords (capacity in blocks) and,
+ * if voxels != NULL, 512 voxels per block as {float sdf; uint8 c0,c1,c2; uint8 weight} (8 B each). */
+long long tdm_fusion_dump_blocks(tdm_fusion* h, int* coords, void* voxels, size_t capacity_blocks);
+/* Device-resident measurement of integrate+render for the last submitted scan/pose. */
+int tdm_fusion_run_resident(tdm_fusion* h, int iters, float* ms_integrate, float* ms_render);
+
+/* ------------------------------------------------------------------------------------------------
+ * Coarse tracker, pyramid level 0 (replaces CudaCoarseTracker; cuda_coarse_tracker.h:9-82)
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct tdm_tracker tdm_tracker;
+int tdm_tracker_create(int w, int h, float setting_huberTH, float setting_coarseCutoffTH, int n_max,
+                       int device, tdm_tracker** out);
+void tdm_tracker_destroy(tdm_tracker* t);
+int tdm_tracker_set_k(tdm_tracker* t, int w, int h, float fx, float fy, float cx, float cy);
+int tdm_tracker_set_reference(tdm_tracker* t, int n, const float* pc_u, const float* pc_v,
+                              const float* pc_idepth, const float* pc_color, float ref_exposure,
+                              const double ref_aff_g2l[2]);
+int tdm_tracker_set_new(tdm_tracker* t, const float* dInew /* h*w*3: (I,dx,dy) interleaved */);
+/* calcRes: refToNew 4x4 row-major double; res6 = [E, numTermsInE, flowT, 0, flowRT, saturatedRatio]. */
+int tdm_tracker_calc_res(tdm_tracker* t, const double* refToNew, float new_exposure,
+                         const double aff_g2l[2], float cutoffTH, double res6[6]);
+/* calcG: H 8x8 row-major, b 8; uses the warped buffers of the last calc_res. */
+int tdm_tracker_calc_g(tdm_tracker* t, float new_exposure, const double aff_g2l[2], double H[64], double b[8]);
+/* Fused single-launch calcRes+calcG (no warped buffers), same outputs. */
+int tdm_tracker_calc_res_g(tdm_tracker* t, const double* refToNew, float new_exposure,
+                           const double aff_g2l[2], float cutoffTH, double res6[6], double H[64], double b[8]);
+int tdm_tracker_synchronize(tdm_tracker* t);
+int tdm_tracker_run_resident(tdm_tracker* t, int iters, float* ms_total);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TANDEM_B200_H */

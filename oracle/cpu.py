@@ -1,0 +1,143 @@
+"""ctypes bindings of the C oracles (oracle/tsdf_oracle.c, oracle/tracker_oracle.c).  TEST INFRASTRUCTURE ONLY:
+imported by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_BUILD = os.path.join(_HERE, "_build")
+
+
+def build():
+    subprocess.run(["make", "-s", "-C", _HERE], check=True)
+
+
+def _load(name):
+    path = os.path.join(_BUILD, name)
+    src = os.path.join(_HERE, name[3:].replace(".so", ".c"))
+    if not os.path.exists(path) or os.path.getmtime(path) < os.path.getmtime(src):
+        build()
+    return ctypes.CDLL(path)
+
+
+class _Options(ctypes.Structure):
+    _fields_ = [("voxel_size", ctypes.c_float), ("num_buckets", ctypes.c_int), ("bucket_size", ctypes.c_int),
+                ("num_blocks", ctypes.c_int), ("block_size", ctypes.c_int), ("max_sdf_weight", ctypes.c_int),
+                ("truncation_distance", ctypes.c_float), ("max_sensor_depth", ctypes.c_float),
+                ("min_sensor_depth", ctypes.c_float), ("num_render_streams", ctypes.c_int),
+                ("fx", ctypes.c_float), ("fy", ctypes.c_float), ("cx", ctypes.c_float), ("cy", ctypes.c_float),
+                ("height", ctypes.c_int), ("width", ctypes.c_int)]
+
+
+VOXEL_DTYPE = np.dtype([("sdf", "<f4"), ("color", "u1", (3,)), ("weight", "u1")])
+_fp = ctypes.POINTER(ctypes.c_float)
+_dp = ctypes.POINTER(ctypes.c_double)
+
+
+class TsdfOracle:
+    def __init__(self, options):
+        """options: any ctypes struct with DrFusionOptions' fields (e.g. tandem_b200._lib.FusionOptions)."""
+        self._l = _load("libtsdf_oracle.so")
+        self._l.tsdf_oracle_create.restype = ctypes.c_void_p
+        self._l.tsdf_oracle_dump.restype = ctypes.c_long
+        o = _Options()
+        for f, _ in _Options._fields_:
+            setattr(o, f, getattr(options, f))
+        self.o = o
+        self._h = ctypes.c_void_p(self._l.tsdf_oracle_create(ctypes.byref(o)))
+
+    def __del__(self):
+        try:
+            self._l.tsdf_oracle_destroy(self._h)
+        except Exception:
+            pass
+
+    def integrate(self, bgr, depth, pose):
+        bgr = np.ascontiguousarray(bgr, np.uint8)
+        depth = np.ascontiguousarray(depth, np.float32)
+        pose = np.ascontiguousarray(pose, np.float32)
+        rc = self._l.tsdf_oracle_integrate(self._h, ctypes.c_void_p(bgr.ctypes.data), depth.ctypes.data_as(_fp),
+                                           pose.ctypes.data_as(_fp))
+        assert rc == 0
+
+    def render(self, pose):
+        pose = np.ascontiguousarray(pose, np.float32)
+        bgr = np.zeros((self.o.height, self.o.width, 3), np.uint8)
+        depth = np.zeros((self.o.height, self.o.width), np.float32)
+        self._l.tsdf_oracle_render(self._h, pose.ctypes.data_as(_fp), ctypes.c_void_p(bgr.ctypes.data),
+                                   depth.ctypes.data_as(_fp))
+        return bgr, depth
+
+    def stats(self):
+        out = (ctypes.c_long * 5)()
+        self._l.tsdf_oracle_stats(self._h, out)
+        return dict(allocated_blocks=out[0], visible_blocks=out[1], dropped_blocks=out[2], candidate_blocks=out[3],
+                    render_distinct_voxels=out[4])
+
+    def dump_blocks(self):
+        n = self.stats()["allocated_blocks"]
+        coords = np.empty((n, 3), np.int32)
+        vox = np.empty((n, 512), VOXEL_DTYPE)
+        m = self._l.tsdf_oracle_dump(self._h, ctypes.c_void_p(coords.ctypes.data), ctypes.c_void_p(vox.ctypes.data),
+                                     ctypes.c_long(n))
+        assert m == n
+        return coords, vox
+
+
+class _TrkCfg(ctypes.Structure):
+    _fields_ = [("w", ctypes.c_int), ("h", ctypes.c_int), ("fx", ctypes.c_float), ("fy", ctypes.c_float),
+                ("cx", ctypes.c_float), ("cy", ctypes.c_float), ("huber", ctypes.c_float)]
+
+
+class TrackerOracle:
+    """Same call surface as tandem_b200.CudaCoarseTracker, evaluated by oracle/tracker_oracle.c."""
+
+    def __init__(self, w, h, setting_huberTH=9.0, setting_coarseCutoffTH=20.0):
+        self._l = _load("libtracker_oracle.so")
+        self.cfg = _TrkCfg(w, h, 0, 0, 0, 0, setting_huberTH)
+
+    def setK(self, w, h, fx, fy, cx, cy):
+        self.cfg.fx, self.cfg.fy, self.cfg.cx, self.cfg.cy = fx, fy, cx, cy
+
+    def setReference(self, n, pc_u, pc_v, pc_idepth, pc_color, ref_exposure, ref_aff_g2l):
+        f = lambda a: np.ascontiguousarray(a, np.float32)
+        self.n, self.u, self.v, self.idepth, self.color = n, f(pc_u), f(pc_v), f(pc_idepth), f(pc_color)
+        self.ref_exposure, self.ref_aff = float(ref_exposure), np.ascontiguousarray(ref_aff_g2l, np.float64)
+
+    def setNew(self, dInew):
+        self.dI = np.ascontiguousarray(dInew, np.float32)
+
+    def _aff(self, new_exposure, aff):
+        out = (ctypes.c_float * 2)()
+        aff = np.ascontiguousarray(aff, np.float64)
+        self._l.tracker_oracle_affll(ctypes.c_float(self.ref_exposure), ctypes.c_float(new_exposure),
+                                     self.ref_aff.ctypes.data_as(_dp), aff.ctypes.data_as(_dp), out)
+        return out
+
+    def calcRes(self, refToNew, new_exposure, aff_g2l, cutoffTH):
+        T = np.ascontiguousarray(refToNew, np.float64)
+        aff = self._aff(new_exposure, aff_g2l)
+        self.warped = np.zeros((7, self.n), np.float32)
+        out7 = np.zeros(7, np.float64)
+        self._l.tracker_oracle_calc_res(ctypes.byref(self.cfg), T.ctypes.data_as(_dp), aff, ctypes.c_float(cutoffTH),
+                                        self.n, self.u.ctypes.data_as(_fp), self.v.ctypes.data_as(_fp),
+                                        self.idepth.ctypes.data_as(_fp), self.color.ctypes.data_as(_fp),
+                                        self.dI.ctypes.data_as(_fp), self.warped.ctypes.data_as(_fp),
+                                        out7.ctypes.data_as(_dp))
+        self.out7 = out7
+        res6 = np.zeros(6, np.float64)
+        self._l.tracker_oracle_res6(out7.ctypes.data_as(_dp), res6.ctypes.data_as(_dp))
+        return res6
+
+    def calcG(self, new_exposure, aff_g2l):
+        aff = self._aff(new_exposure, aff_g2l)
+        acc = np.zeros(45, np.float64)
+        H = np.zeros((8, 8), np.float64)
+        b = np.zeros(8, np.float64)
+        self._l.tracker_oracle_calc_g(ctypes.byref(self.cfg), aff, ctypes.c_float(self.ref_aff[1]), self.n,
+                                      self.color.ctypes.data_as(_fp), self.warped.ctypes.data_as(_fp),
+                                      int(self.out7[2]), acc.ctypes.data_as(_dp), H.ctypes.data_as(_dp),
+                                      b.ctypes.data_as(_dp))
+        return H, b

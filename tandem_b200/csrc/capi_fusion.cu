@@ -1,0 +1,82 @@
+// extern "C" entry points for the TSDF fusion engine (include/tandem_b200.h).
+#include "../../include/tandem_b200.h"
+#include "capi_common.h"
+#include "common.cuh"
+#include "fusion.h"
+
+struct tdm_fusion {
+  tdm::FusionIface* impl;
+};
+
+extern "C" {
+
+int tdm_fusion_create(const tdm_fusion_options* opt, int device, tdm_fusion** out) {
+  TDM_API_BEGIN
+  TDM_CHECK(opt && out, "null argument");
+  *out = new tdm_fusion{tdm::make_fusion(*opt, device)};
+  return TDM_OK;
+  TDM_API_END
+}
+void tdm_fusion_destroy(tdm_fusion* h) {
+  if (!h) return;
+  try { delete h->impl; } catch (...) {}
+  delete h;
+}
+int tdm_fusion_integrate_async(tdm_fusion* h, const unsigned char* bgr, const float* depth, const float* pose) {
+  TDM_API_BEGIN
+  TDM_CHECK(h && bgr && depth && pose, "null argument");
+  h->impl->integrate_async(bgr, depth, pose);
+  return TDM_OK;
+  TDM_API_END
+}
+int tdm_fusion_render_async(tdm_fusion* h, const float* const* camera_poses, int n_poses) {
+  TDM_API_BEGIN
+  TDM_CHECK(h && (camera_poses || n_poses == 0), "null argument");
+  h->impl->render_async(camera_poses, n_poses);
+  return TDM_OK;
+  TDM_API_END
+}
+int tdm_fusion_get_render_result(tdm_fusion* h, unsigned char** bgr_out, float** depth_out, int n_poses) {
+  TDM_API_BEGIN
+  TDM_CHECK(h && ((bgr_out && depth_out) || n_poses == 0), "null argument");
+  h->impl->get_render_result(bgr_out, depth_out, n_poses);
+  return TDM_OK;
+  TDM_API_END
+}
+int tdm_fusion_synchronize(tdm_fusion* h) {
+  TDM_API_BEGIN
+  TDM_CHECK(h, "null handle");
+  h->impl->synchronize();
+  return TDM_OK;
+  TDM_API_END
+}
+long long tdm_fusion_extract_mesh(tdm_fusion* h, const float lower[3], const float upper[3], float* vert, float* cols,
+                                  size_t max_vertices) {
+  TDM_API_BEGIN
+  TDM_CHECK(h && lower && upper, "null argument");
+  (void)vert; (void)cols; (void)max_vertices;
+  throw tdm::Error("tdm_fusion_extract_mesh: marching cubes (SURVEY.md §8f row n4, viewer output only) is not built yet");
+  TDM_API_END
+}
+int tdm_fusion_get_stats(tdm_fusion* h, tdm_fusion_stats* out) {
+  TDM_API_BEGIN
+  TDM_CHECK(h && out, "null argument");
+  h->impl->get_stats(out);
+  return TDM_OK;
+  TDM_API_END
+}
+long long tdm_fusion_dump_blocks(tdm_fusion* h, int* coords, void* voxels, size_t capacity_blocks) {
+  TDM_API_BEGIN
+  TDM_CHECK(h, "null handle");
+  return h->impl->dump_blocks(coords, voxels, capacity_blocks);
+  TDM_API_END
+}
+int tdm_fusion_run_resident(tdm_fusion* h, int iters, float* ms_integrate, float* ms_render) {
+  TDM_API_BEGIN
+  TDM_CHECK(h && ms_integrate && ms_render, "null argument");
+  h->impl->run_resident(iters, ms_integrate, ms_render);
+  return TDM_OK;
+  TDM_API_END
+}
+
+}  // extern "C"

@@ -1,0 +1,519 @@
+// Voxel-hashed TSDF fusion behind the DrFusion call surface (dr_fusion.h:44-73).
+//
+// Reference being replaced:
+//   AllocateFromDepthKernel  tandem/libdr/dr_fusion/src/tsdfvh/tsdf_volume.cu:317-434 (+ hash_table.cu:80-115)
+//   IntegrateScanKernel      tsdf_volume.cu:436-513 (+ :303-315, voxel.h:29-53)
+//   GenerateRgbDepthKernel   tsdf_volume.cu:600-632 (+ GetInterpolatedVoxel :161-289)
+// B200 design (not a port):
+//   K5 allocate : one thread per depth PIXEL (the reference sizes its grid by the 10 M hash entries), lock-free
+//                 insert with a single 64-bit CAS on the packed block key (no lock state, no duplicate blocks),
+//                 every new block appended to a compact block list.
+//   K6 integrate: persistent CTAs stride over the compact block list (the reference scans all 10 M entries,
+//                 free ones included), 256 threads x 2 voxels, one 128-bit load + store per thread, no
+//                 per-voxel re-hash.
+//   K7 ray-cast : one thread per pixel in 16x16 tiles, sphere tracing with a per-thread last-block cache so the
+//                 9 lookups of a trilinear sample mostly skip the hash probe.
+// The hash function, bucket structure (full bucket -> block dropped), voxel record (8 B) and all geometry are
+// the reference's; geometry that decides integers uses __f*_rn intrinsics so it is bit-identical to the CPU
+// oracle (oracle/tsdf_oracle.c) which evaluates the same expressions without FMA contraction.
+#include <algorithm>
+#include <cstring>
+#include <vector>
+
+#include "fusion.h"
+#include "mat4.h"
+
+namespace tdm {
+
+namespace {
+
+constexpr unsigned long long kEmptyKey = ~0ull;
+constexpr int kKeyBias = 1 << 20;
+
+struct Mat4 { float m[16]; };
+
+struct FusionDev {
+  tdm_fusion_options o;
+  unsigned long long* keys;  // [num_buckets*bucket_size], kEmptyKey = free
+  int* ptrs;                 // block index per entry
+  uint2* voxels;             // [num_blocks*512] {sdf bits, c0|c1<<8|c2<<16|w<<24}
+  int4* list;                // compact list of allocated blocks (x,y,z,ptr)
+  int* counters;             // [0] #blocks allocated, [1] dropped, [2] visible (last scan), [3] new this scan
+};
+
+__device__ __forceinline__ float mul_(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float add_(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float sub_(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ float div_(float a, float b) { return __fdiv_rn(a, b); }
+
+__device__ __forceinline__ float3 xform(const Mat4& T, float3 v) {  // matrix_utils.h:914-921 (w == 1)
+  const float* m = T.m;
+  float3 r;
+  r.x = add_(add_(add_(mul_(m[0], v.x), mul_(m[1], v.y)), mul_(m[2], v.z)), mul_(m[3], 1.0f));
+  r.y = add_(add_(add_(mul_(m[4], v.x), mul_(m[5], v.y)), mul_(m[6], v.z)), mul_(m[7], 1.0f));
+  r.z = add_(add_(add_(mul_(m[8], v.x), mul_(m[9], v.y)), mul_(m[10], v.z)), mul_(m[11], 1.0f));
+  return r;
+}
+__device__ __forceinline__ float norm3(float3 v) {
+  return __fsqrt_rn(add_(add_(mul_(v.x, v.x), mul_(v.y, v.y)), mul_(v.z, v.z)));
+}
+__device__ __forceinline__ float3 get_point3d(const tdm_fusion_options& o, int i, float depth) {  // utils.h:93-101
+  const int v = i / o.width, u = i - o.width * v;
+  float3 p;
+  p.z = depth;
+  p.x = div_(mul_(sub_((float)u, o.cx), p.z), o.fx);
+  p.y = div_(mul_(sub_((float)v, o.cy), p.z), o.fy);
+  return p;
+}
+__device__ __forceinline__ int2 project(const tdm_fusion_options& o, float3 p) {  // utils.h:103-108
+  const float x = add_(div_(mul_(o.fx, p.x), p.z), o.cx);
+  const float y = add_(div_(mul_(o.fy, p.y), p.z), o.cy);
+  return make_int2(__float2int_rz(roundf(x)), __float2int_rz(roundf(y)));
+}
+__device__ __forceinline__ int sgn(float n) { return (n > 0) - (n < 0); }
+
+__device__ __forceinline__ unsigned long long pack_key(int x, int y, int z) {
+  return (unsigned long long)(unsigned)(x + kKeyBias) | ((unsigned long long)(unsigned)(y + kKeyBias) << 21) |
+         ((unsigned long long)(unsigned)(z + kKeyBias) << 42);
+}
+__device__ __forceinline__ long long hash_bucket(const tdm_fusion_options& o, int x, int y, int z) {  // hash_table.cu:157-168
+  const int a = (int)((unsigned)x * 73856093u), b = (int)((unsigned)y * 19349669u), c = (int)((unsigned)z * 83492791u);
+  int r = (a ^ b ^ c) % o.num_buckets;
+  if (r < 0) r += o.num_buckets;
+  return (long long)r * o.bucket_size;
+}
+
+__device__ void insert_block(const FusionDev& d, int x, int y, int z) {
+  if (x <= -kKeyBias || x >= kKeyBias || y <= -kKeyBias || y >= kKeyBias || z <= -kKeyBias || z >= kKeyBias) return;
+  const unsigned long long key = pack_key(x, y, z);
+  const long long b = hash_bucket(d.o, x, y, z);
+  for (int i = 0; i < d.o.bucket_size; ++i) {
+    unsigned long long cur = d.keys[b + i];
+    if (cur == key) return;
+    if (cur == kEmptyKey) {
+      cur = atomicCAS(&d.keys[b + i], kEmptyKey, key);
+      if (cur == key) return;           // somebody else inserted the same block
+      if (cur == kEmptyKey) {           // we own the slot: take a voxel block and publish it in the list
+        const int ptr = atomicAdd(&d.counters[0], 1);
+        if (ptr >= d.o.num_blocks) {    // heap exhausted (heap.cu:16-18 aborts; we drop and count)
+          atomicAdd(&d.counters[1], 1);
+          d.ptrs[b + i] = -1;
+          return;
+        }
+        d.ptrs[b + i] = ptr;
+        d.list[ptr] = make_int4(x, y, z, ptr);
+        atomicAdd(&d.counters[3], 1);
+        return;
+      }
+      // slot taken by a different block in the meantime: keep scanning
+    }
+  }
+  atomicAdd(&d.counters[1], 1);  // bucket full: block dropped (hash_table.cu:103-115 returns without allocating)
+}
+
+__device__ __forceinline__ int find_block(const FusionDev& d, int x, int y, int z) {  // hash_table.cu:141-155
+  if (x <= -kKeyBias || x >= kKeyBias || y <= -kKeyBias || y >= kKeyBias || z <= -kKeyBias || z >= kKeyBias) return -1;
+  const unsigned long long key = pack_key(x, y, z);
+  const long long b = hash_bucket(d.o, x, y, z);
+  for (int i = 0; i < d.o.bucket_size; ++i)
+    if (d.keys[b + i] == key) return d.ptrs[b + i];
+  return -1;
+}
+
+// ---------------------------------------------------------------------------------------------- K5
+__global__ void k_allocate(FusionDev d, const float* __restrict__ depth, Mat4 T) {
+  const tdm_fusion_options& o = d.o;
+  const int n = o.height * o.width;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float dz = depth[i];
+  if (dz < o.min_sensor_depth || dz > o.max_sensor_depth) return;
+  const float bs = mul_((float)o.block_size, o.voxel_size);
+  const float3 start = make_float3(T.m[3], T.m[7], T.m[11]);
+  const float3 p = xform(T, get_point3d(o, i, dz));
+  if (p.x == 0 && p.y == 0 && p.z == 0) return;
+  const float3 dd = make_float3(sub_(p.x, start.x), sub_(p.y, start.y), sub_(p.z, start.z));
+  const float dn = norm3(dd);
+  const float3 dir = make_float3(div_(dd.x, dn), div_(dd.y, dn), div_(dd.z, dn));
+  const float len = add_(dn, o.truncation_distance);
+  const float3 end = make_float3(add_(start.x, mul_(dir.x, len)), add_(start.y, mul_(dir.y, len)), add_(start.z, mul_(dir.z, len)));
+  int3 bp = make_int3((int)floorf(div_(start.x, bs)), (int)floorf(div_(start.y, bs)), (int)floorf(div_(start.z, bs)));
+  const int3 be = make_int3((int)floorf(div_(end.x, bs)), (int)floorf(div_(end.y, bs)), (int)floorf(div_(end.z, bs)));
+  const int3 step = make_int3(sgn(dir.x), sgn(dir.y), sgn(dir.z));
+  const float3 dt = make_float3(dir.x != 0 ? fabsf(div_(bs, dir.x)) : FLT_MAX, dir.y != 0 ? fabsf(div_(bs, dir.y)) : FLT_MAX,
+                                dir.z != 0 ? fabsf(div_(bs, dir.z)) : FLT_MAX);
+  const float3 bd = make_float3(mul_(add_((float)bp.x, (float)step.x), bs), mul_(add_((float)bp.y, (float)step.y), bs),
+                                mul_(add_((float)bp.z, (float)step.z), bs));
+  float3 mt = make_float3(dir.x != 0 ? div_(sub_(bd.x, start.x), dir.x) : FLT_MAX,
+                          dir.y != 0 ? div_(sub_(bd.y, start.y), dir.y) : FLT_MAX,
+                          dir.z != 0 ? div_(sub_(bd.z, start.z), dir.z) : FLT_MAX);
+  int3 diff = make_int3(0, 0, 0);
+  bool neg = false;
+  if (bp.x != be.x && dir.x < 0) { diff.x--; neg = true; }
+  if (bp.y != be.y && dir.y < 0) { diff.y--; neg = true; }
+  if (bp.z != be.z && dir.z < 0) { diff.z--; neg = true; }
+  insert_block(d, bp.x, bp.y, bp.z);
+  if (neg) { bp.x += diff.x; bp.y += diff.y; bp.z += diff.z; insert_block(d, bp.x, bp.y, bp.z); }
+  int guard = 0;
+  while ((bp.x != be.x || bp.y != be.y || bp.z != be.z) && guard++ < 100000) {
+    if (mt.x < mt.y) {
+      if (mt.x < mt.z) { bp.x += step.x; mt.x = add_(mt.x, dt.x); } else { bp.z += step.z; mt.z = add_(mt.z, dt.z); }
+    } else {
+      if (mt.y < mt.z) { bp.y += step.y; mt.y = add_(mt.y, dt.y); } else { bp.z += step.z; mt.z = add_(mt.z, dt.z); }
+    }
+    insert_block(d, bp.x, bp.y, bp.z);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- K6
+__device__ __forceinline__ uint2 combine(uint2 v, float nsdf, const unsigned char* col, int max_w) {  // voxel.h:29-53
+  const float w = (float)(v.y >> 24);
+  const float wn = add_(w, 1.0f);
+  unsigned out = 0;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const float cur = (float)((v.y >> (8 * c)) & 0xFF);
+    const float m = div_(add_(mul_(cur, w), mul_((float)col[c], 1.0f)), wn);
+    out |= ((unsigned)m & 0xFF) << (8 * c);
+  }
+  const float sdf = div_(add_(mul_(__uint_as_float(v.x), w), mul_(nsdf, 1.0f)), wn);
+  int nw = (int)(v.y >> 24) + 1;
+  if (nw > max_w) nw = max_w;
+  return make_uint2(__float_as_uint(sdf), out | ((unsigned)nw << 24));
+}
+
+__global__ void __launch_bounds__(256)
+k_integrate(FusionDev d, const unsigned char* __restrict__ bgr, const float* __restrict__ depth, Mat4 Ti) {
+  const tdm_fusion_options& o = d.o;
+  const int nblocks = min(d.counters[0], o.num_blocks);
+  const float vs = o.voxel_size, tau = o.truncation_distance;
+  const int B = 8;
+  for (int b = blockIdx.x; b < nblocks; b += gridDim.x) {
+    const int4 e = d.list[b];
+    const float3 pos = make_float3(mul_(mul_((float)e.x, vs), (float)B), mul_(mul_((float)e.y, vs), (float)B),
+                                   mul_(mul_((float)e.z, vs), (float)B));
+    const float3 pc = xform(Ti, pos);
+    if (pc.z < 0) continue;
+    const double half = 0.5 * (double)vs * (double)B;  // double as written in the reference (tsdf_volume.cu:460-463)
+    const float3 ctr = make_float3((float)((double)pc.x + half), (float)((double)pc.y + half), (float)((double)pc.z + half));
+    int2 px = project(o, ctr);
+    if (!(px.x >= 0 && px.y >= 0 && px.x < o.width && px.y < o.height)) continue;
+    if (threadIdx.x == 0) atomicAdd(&d.counters[2], 1);
+    // thread t owns voxels (bx,by,bz0) and (bx,by,bz0+1): adjacent in memory (index x*64+y*8+z)
+    const int t = threadIdx.x;
+    const int bx = t >> 5, by = (t >> 2) & 7, bz0 = (t & 3) * 2;
+    uint4* vp = reinterpret_cast<uint4*>(d.voxels + (size_t)e.w * 512 + bx * 64 + by * 8 + bz0);
+    uint4 raw = *vp;
+    uint2 vox[2] = {make_uint2(raw.x, raw.y), make_uint2(raw.z, raw.w)};
+    bool dirty = false;
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const float3 vw = make_float3(add_(pos.x, mul_((float)bx, vs)), add_(pos.y, mul_((float)by, vs)),
+                                    add_(pos.z, mul_((float)(bz0 + k), vs)));
+      const float3 vc = xform(Ti, vw);
+      if (vc.z == 0.0f) continue;
+      px = project(o, vc);
+      if (!(px.x >= 0 && px.y >= 0 && px.x < o.width && px.y < o.height)) continue;
+      const int idx = px.y * o.width + px.x;
+      const float dz = depth[idx];
+      if (dz <= 0 || dz < o.min_sensor_depth || dz > o.max_sensor_depth) continue;
+      const float sd = norm3(get_point3d(o, idx, dz)), vd = norm3(vc);
+      float nsdf;
+      if (vd > sub_(sd, tau) && vd < add_(sd, tau) && dz < o.max_sensor_depth) nsdf = sub_(sd, vd);
+      else if (vd < sub_(sd, tau)) nsdf = tau;
+      else continue;
+      vox[k] = combine(vox[k], nsdf, bgr + 3 * (size_t)idx, o.max_sdf_weight);
+      dirty = true;
+    }
+    if (dirty) *vp = make_uint4(vox[0].x, vox[0].y, vox[1].x, vox[1].y);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- K7
+struct BlockCache { int x, y, z, ptr; };
+
+__device__ __forceinline__ uint2 get_voxel(const FusionDev& d, float3 p, BlockCache& bc) {  // tsdf_volume.cu:109-159
+  const float s = d.o.voxel_size;
+  const int gx = (int)add_(div_(p.x, s), mul_((float)sgn(p.x), 0.5f));
+  const int gy = (int)add_(div_(p.y, s), mul_((float)sgn(p.y), 0.5f));
+  const int gz = (int)add_(div_(p.z, s), mul_((float)sgn(p.z), 0.5f));
+  const int bx = gx >> 3, by = gy >> 3, bz = gz >> 3;  // floor division by the block size 8
+  if (bx != bc.x || by != bc.y || bz != bc.z) {
+    bc.x = bx; bc.y = by; bc.z = bz;
+    bc.ptr = find_block(d, bx, by, bz);
+  }
+  if (bc.ptr < 0) return make_uint2(0u, 0u);
+  return __ldg(d.voxels + (size_t)bc.ptr * 512 + (gx & 7) * 64 + (gy & 7) * 8 + (gz & 7));
+}
+
+__device__ uint2 get_interpolated(const FusionDev& d, float3 p, BlockCache& bc) {  // tsdf_volume.cu:161-289
+  const uint2 v0 = get_voxel(d, p, bc);
+  if ((v0.y >> 24) == 0) return v0;
+  const float s = d.o.voxel_size;
+  const float hs = div_(s, 2.0f);
+  const float3 pd = make_float3(sub_(p.x, hs), sub_(p.y, hs), sub_(p.z, hs));
+  const float3 vp = make_float3(div_(p.x, s), div_(p.y, s), div_(p.z, s));
+  const float wx = sub_(vp.x, floorf(vp.x)), wy = sub_(vp.y, floorf(vp.y)), wz = sub_(vp.z, floorf(vp.z));
+  float dist = 0.f, cf[3] = {0.f, 0.f, 0.f};
+  // corner order of the reference: 000,100,010,001,110,011,101,111
+  const int ox[8] = {0, 1, 0, 0, 1, 0, 1, 1}, oy[8] = {0, 0, 1, 0, 1, 1, 0, 1}, oz[8] = {0, 0, 0, 1, 0, 1, 1, 1};
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const float3 q = make_float3(add_(pd.x, ox[k] ? s : 0.f), add_(pd.y, oy[k] ? s : 0.f), add_(pd.z, oz[k] ? s : 0.f));
+    uint2 v = get_voxel(d, q, bc);
+    if ((v.y >> 24) == 0) v = v0;
+    const float w = mul_(mul_(ox[k] ? wx : sub_(1.f, wx), oy[k] ? wy : sub_(1.f, wy)), oz[k] ? wz : sub_(1.f, wz));
+    dist = add_(dist, mul_(w, __uint_as_float(v.x)));
+#pragma unroll
+    for (int c = 0; c < 3; ++c) cf[c] = add_(cf[c], mul_(w, (float)((v.y >> (8 * c)) & 0xFF)));
+  }
+  unsigned col = 0;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) col |= ((unsigned)cf[c] & 0xFF) << (8 * c);
+  return make_uint2(__float_as_uint(dist), col | (v0.y & 0xFF000000u));
+}
+
+__global__ void __launch_bounds__(256)
+k_raycast(FusionDev d, Mat4 T, unsigned char* __restrict__ bgr_out, float* __restrict__ depth_out) {
+  const tdm_fusion_options& o = d.o;
+  const int x = blockIdx.x * 16 + (threadIdx.x & 15);
+  const int y = blockIdx.y * 16 + (threadIdx.x >> 4);
+  if (x >= o.width || y >= o.height) return;
+  const int i = y * o.width + x;
+  BlockCache bc = {INT_MIN, INT_MIN, INT_MIN, -1};
+  float cur = 0.f;
+  int guard = 0;
+  while (cur < o.max_sensor_depth && guard++ < 100000) {
+    const uint2 v = get_interpolated(d, xform(T, get_point3d(o, i, cur)), bc);
+    const unsigned w = v.y >> 24;
+    const float sdf = __uint_as_float(v.x);
+    cur = add_(cur, w == 0 ? o.truncation_distance : sdf);
+    if (w != 0 && sdf < o.voxel_size) break;
+  }
+  if (cur < o.max_sensor_depth) {
+    const uint2 v = get_interpolated(d, xform(T, get_point3d(o, i, cur)), bc);
+    bgr_out[3 * i] = v.y & 0xFF; bgr_out[3 * i + 1] = (v.y >> 8) & 0xFF; bgr_out[3 * i + 2] = (v.y >> 16) & 0xFF;
+    depth_out[i] = cur;
+  } else {
+    bgr_out[3 * i] = bgr_out[3 * i + 1] = bgr_out[3 * i + 2] = 0;
+    depth_out[i] = 0.f;
+  }
+}
+
+__global__ void k_fill_keys(unsigned long long* keys, int* ptrs, long long n) {
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i < n) { keys[i] = kEmptyKey; ptrs[i] = -1; }
+}
+
+}  // namespace
+
+// ================================================================================================
+class FusionImpl final : public FusionIface {
+ public:
+  FusionImpl(const tdm_fusion_options& o, int device) : device_(device) {
+    int nd = 0;
+    if (cudaGetDeviceCount(&nd) != cudaSuccess || nd == 0)
+      throw Error("tandem_b200: no CUDA device visible - this library has no CPU fallback");
+    TDM_CHECK(o.block_size == 8, "block_size must be 8 (the voxel block layout is 8x8x8 as in FullSystem.cpp:259-276)");
+    TDM_CHECK(o.num_buckets > 0 && o.bucket_size > 0 && o.num_blocks > 0, "bad hash table options");
+    TDM_CHECK(o.height > 0 && o.width > 0 && o.num_render_streams >= 0, "bad image options");
+    TDM_CHECK(o.max_sdf_weight > 0 && o.max_sdf_weight <= 255, "max_sdf_weight must fit the u8 voxel weight");
+    TDM_CUDA(cudaSetDevice(device_));
+    d_.o = o;
+    n_entries_ = (long long)o.num_buckets * o.bucket_size;
+    int lo, hi;
+    TDM_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    TDM_CUDA(cudaStreamCreateWithPriority(&stream_, cudaStreamNonBlocking, lo));  // low priority as tsdf_volume.cu:64-75
+    TDM_CUDA(cudaMalloc(&d_.keys, n_entries_ * 8));
+    TDM_CUDA(cudaMalloc(&d_.ptrs, n_entries_ * 4));
+    TDM_CUDA(cudaMalloc(&d_.voxels, (size_t)o.num_blocks * 512 * 8));
+    TDM_CUDA(cudaMalloc(&d_.list, (size_t)o.num_blocks * sizeof(int4)));
+    TDM_CUDA(cudaMalloc(&d_.counters, 8 * sizeof(int)));
+    TDM_CUDA(cudaMemsetAsync(d_.voxels, 0, (size_t)o.num_blocks * 512 * 8, stream_));
+    TDM_CUDA(cudaMemsetAsync(d_.counters, 0, 8 * sizeof(int), stream_));
+    k_fill_keys<<<cdiv(n_entries_, 256), 256, 0, stream_>>>(d_.keys, d_.ptrs, n_entries_);
+    TDM_CUDA(cudaGetLastError());
+    const size_t npx = (size_t)o.height * o.width;
+    TDM_CUDA(cudaMallocHost(&h_bgr_in_, npx * 3));
+    TDM_CUDA(cudaMallocHost(&h_depth_in_, npx * 4));
+    TDM_CUDA(cudaMalloc(&d_bgr_in_, npx * 3));
+    TDM_CUDA(cudaMalloc(&d_depth_in_, npx * 4));
+    const int ns = std::max(1, o.num_render_streams);
+    for (int half = 0; half < 2; ++half) {
+      TDM_CUDA(cudaMallocHost(&h_bgr_out_[half], npx * 3 * ns));
+      TDM_CUDA(cudaMallocHost(&h_depth_out_[half], npx * 4 * ns));
+    }
+    TDM_CUDA(cudaMalloc(&d_bgr_out_, npx * 3 * ns));
+    TDM_CUDA(cudaMalloc(&d_depth_out_, npx * 4 * ns));
+    TDM_CUDA(cudaMallocHost(&h_counters_, 8 * sizeof(int)));
+    TDM_CUDA(cudaEventCreateWithFlags(&ev_int_, cudaEventDisableTiming));
+    TDM_CUDA(cudaEventCreateWithFlags(&ev_render_, cudaEventDisableTiming));
+    TDM_CUDA(cudaStreamSynchronize(stream_));
+    render_poses_.resize(ns);
+  }
+
+  ~FusionImpl() override {
+    cudaSetDevice(device_);
+    cudaStreamSynchronize(stream_);
+    cudaFree(d_.keys); cudaFree(d_.ptrs); cudaFree(d_.voxels); cudaFree(d_.list); cudaFree(d_.counters);
+    cudaFreeHost(h_bgr_in_); cudaFreeHost(h_depth_in_); cudaFree(d_bgr_in_); cudaFree(d_depth_in_);
+    for (int half = 0; half < 2; ++half) { cudaFreeHost(h_bgr_out_[half]); cudaFreeHost(h_depth_out_[half]); }
+    cudaFree(d_bgr_out_); cudaFree(d_depth_out_); cudaFreeHost(h_counters_);
+    cudaEventDestroy(ev_int_); cudaEventDestroy(ev_render_);
+    cudaStreamDestroy(stream_);
+  }
+
+  // IntegrateScanAsync, tsdf_volume.cu:515-598
+  void integrate_async(const unsigned char* bgr, const float* depth, const float* pose) override {
+    if (next_ != kIntegrate)
+      throw Error("call order is IntegrateScanAsync -> RenderAsync -> GetRenderResult (tsdf_volume.cu:520-525)");
+    TDM_CUDA(cudaSetDevice(device_));
+    const size_t npx = (size_t)d_.o.height * d_.o.width;
+    TDM_CUDA(cudaEventSynchronize(ev_int_));  // previous scan has left the pinned staging buffers
+    std::memcpy(h_bgr_in_, bgr, npx * 3);
+    std::memcpy(h_depth_in_, depth, npx * 4);
+    std::memcpy(pose_.m, pose, 64);
+    if (!inv4_f32(pose_.m, pose_inv_.m)) throw Error("camera pose is singular");
+    TDM_CUDA(cudaMemcpyAsync(d_bgr_in_, h_bgr_in_, npx * 3, cudaMemcpyHostToDevice, stream_));
+    TDM_CUDA(cudaMemcpyAsync(d_depth_in_, h_depth_in_, npx * 4, cudaMemcpyHostToDevice, stream_));
+    launch_integrate();
+    TDM_CUDA(cudaEventRecord(ev_int_, stream_));
+    have_scan_ = true;
+    next_ = d_.o.num_render_streams > 0 ? kRender : kRender;
+  }
+
+  // RenderAsync, tsdf_volume.cu:634-700
+  void render_async(const float* const* poses, int n) override {
+    if (next_ != kRender) throw Error("call order is IntegrateScanAsync -> RenderAsync -> GetRenderResult (tsdf_volume.cu:635-640)");
+    if (n != d_.o.num_render_streams) throw Error("RenderAsync: number of poses must equal num_render_streams (tsdf_volume.cu:643-648)");
+    TDM_CUDA(cudaSetDevice(device_));
+    for (int i = 0; i < n; ++i) std::memcpy(render_poses_[i].m, poses[i], 64);
+    launch_render(n, true);
+    TDM_CUDA(cudaEventRecord(ev_render_, stream_));
+    n_rendered_ = n;
+    next_ = kGet;
+  }
+
+  // GetRenderResult, tsdf_volume.cu:702-737
+  void get_render_result(unsigned char** bgr, float** depth, int n) override {
+    if (next_ != kGet) throw Error("call order is IntegrateScanAsync -> RenderAsync -> GetRenderResult (tsdf_volume.cu:703-708)");
+    if (n != n_rendered_) throw Error("GetRenderResult: wrong number of outputs");
+    TDM_CUDA(cudaSetDevice(device_));
+    TDM_CUDA(cudaEventSynchronize(ev_render_));
+    const size_t npx = (size_t)d_.o.height * d_.o.width;
+    for (int i = 0; i < n; ++i) {
+      bgr[i] = h_bgr_out_[free_half_] + (size_t)i * npx * 3;
+      depth[i] = h_depth_out_[free_half_] + (size_t)i * npx;
+    }
+    free_half_ ^= 1;  // the returned half stays valid until the next GetRenderResult (tsdf_volume.cu:719-732)
+    next_ = kIntegrate;
+  }
+
+  void synchronize() override {
+    TDM_CUDA(cudaSetDevice(device_));
+    TDM_CUDA(cudaStreamSynchronize(stream_));
+  }
+
+  void get_stats(tdm_fusion_stats* s) override {
+    fetch_counters();
+    s->allocated_blocks = std::min(h_counters_[0], d_.o.num_blocks);
+    s->dropped_blocks = h_counters_[1];
+    s->visible_blocks = h_counters_[2];
+    s->candidate_blocks = h_counters_[3];
+  }
+
+  long long dump_blocks(int* coords, void* voxels, size_t cap) override {
+    fetch_counters();
+    const long long n = std::min(h_counters_[0], d_.o.num_blocks);
+    if (!coords) return n;
+    std::vector<int4> list((size_t)n);
+    TDM_CUDA(cudaMemcpy(list.data(), d_.list, (size_t)n * sizeof(int4), cudaMemcpyDeviceToHost));
+    std::sort(list.begin(), list.end(), [](const int4& a, const int4& b) {
+      if (a.x != b.x) return a.x < b.x;
+      if (a.y != b.y) return a.y < b.y;
+      return a.z < b.z;
+    });
+    const long long m = std::min<long long>(n, (long long)cap);
+    for (long long k = 0; k < m; ++k) {
+      coords[3 * k] = list[k].x; coords[3 * k + 1] = list[k].y; coords[3 * k + 2] = list[k].z;
+      if (voxels)
+        TDM_CUDA(cudaMemcpy((char*)voxels + (size_t)k * 4096, d_.voxels + (size_t)list[k].w * 512, 4096, cudaMemcpyDeviceToHost));
+    }
+    return n;
+  }
+
+  void run_resident(int iters, float* ms_int, float* ms_render) override {
+    TDM_CHECK(have_scan_, "run_resident: no scan submitted yet");
+    TDM_CUDA(cudaSetDevice(device_));
+    cudaEvent_t e0, e1, e2;
+    TDM_CUDA(cudaEventCreate(&e0)); TDM_CUDA(cudaEventCreate(&e1)); TDM_CUDA(cudaEventCreate(&e2));
+    float ti = 0, tr = 0;
+    const int n = std::max(1, d_.o.num_render_streams);
+    if (render_poses_.empty()) render_poses_.resize(1);
+    for (int it = 0; it < iters; ++it) {
+      TDM_CUDA(cudaEventRecord(e0, stream_));
+      launch_integrate();
+      TDM_CUDA(cudaEventRecord(e1, stream_));
+      launch_render(n, false);
+      TDM_CUDA(cudaEventRecord(e2, stream_));
+      TDM_CUDA(cudaEventSynchronize(e2));
+      float a, b;
+      TDM_CUDA(cudaEventElapsedTime(&a, e0, e1));
+      TDM_CUDA(cudaEventElapsedTime(&b, e1, e2));
+      ti += a; tr += b;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
+    *ms_int = ti; *ms_render = tr;
+  }
+
+ private:
+  void launch_integrate() {
+    const int npx = d_.o.height * d_.o.width;
+    TDM_CUDA(cudaMemsetAsync(d_.counters + 2, 0, 2 * sizeof(int), stream_));
+    k_allocate<<<cdiv(npx, 128), 128, 0, stream_>>>(d_, d_depth_in_, pose_);
+    TDM_CUDA(cudaGetLastError());
+    k_integrate<<<148 * 8, 256, 0, stream_>>>(d_, d_bgr_in_, d_depth_in_, pose_inv_);
+    TDM_CUDA(cudaGetLastError());
+  }
+  void launch_render(int n, bool copy_back) {
+    const size_t npx = (size_t)d_.o.height * d_.o.width;
+    dim3 grid(cdiv(d_.o.width, 16), cdiv(d_.o.height, 16));
+    for (int i = 0; i < n; ++i) {
+      k_raycast<<<grid, 256, 0, stream_>>>(d_, render_poses_[i], d_bgr_out_ + (size_t)i * npx * 3, d_depth_out_ + (size_t)i * npx);
+      TDM_CUDA(cudaGetLastError());
+    }
+    if (copy_back) {
+      TDM_CUDA(cudaMemcpyAsync(h_bgr_out_[free_half_], d_bgr_out_, npx * 3 * n, cudaMemcpyDeviceToHost, stream_));
+      TDM_CUDA(cudaMemcpyAsync(h_depth_out_[free_half_], d_depth_out_, npx * 4 * n, cudaMemcpyDeviceToHost, stream_));
+    }
+  }
+  void fetch_counters() {
+    TDM_CUDA(cudaSetDevice(device_));
+    TDM_CUDA(cudaMemcpyAsync(h_counters_, d_.counters, 8 * sizeof(int), cudaMemcpyDeviceToHost, stream_));
+    TDM_CUDA(cudaStreamSynchronize(stream_));
+  }
+
+  enum Next { kIntegrate, kRender, kGet };
+  int device_;
+  FusionDev d_{};
+  long long n_entries_ = 0;
+  cudaStream_t stream_ = nullptr;
+  cudaEvent_t ev_int_ = nullptr, ev_render_ = nullptr;
+  unsigned char *h_bgr_in_ = nullptr, *d_bgr_in_ = nullptr;
+  float *h_depth_in_ = nullptr, *d_depth_in_ = nullptr;
+  unsigned char* h_bgr_out_[2] = {nullptr, nullptr};
+  float* h_depth_out_[2] = {nullptr, nullptr};
+  unsigned char* d_bgr_out_ = nullptr;
+  float* d_depth_out_ = nullptr;
+  int* h_counters_ = nullptr;
+  int free_half_ = 0;
+  Mat4 pose_{}, pose_inv_{};
+  std::vector<Mat4> render_poses_;
+  int n_rendered_ = 0;
+  bool have_scan_ = false;
+  Next next_ = kIntegrate;
+};
+
+FusionIface* make_fusion(const tdm_fusion_options& o, int device) { return new FusionImpl(o, device); }
+
+}  // namespace tdm

@@ -1,0 +1,25 @@
+// Type-erased interface of the TSDF fusion engine (fusion.cu).
+#pragma once
+#include <cfloat>
+#include <climits>
+
+#include "../../include/tandem_b200.h"
+#include "common.cuh"
+
+namespace tdm {
+
+class FusionIface {
+ public:
+  virtual ~FusionIface() = default;
+  virtual void integrate_async(const unsigned char* bgr, const float* depth, const float* pose) = 0;
+  virtual void render_async(const float* const* poses, int n) = 0;
+  virtual void get_render_result(unsigned char** bgr, float** depth, int n) = 0;
+  virtual void synchronize() = 0;
+  virtual void get_stats(tdm_fusion_stats* s) = 0;
+  virtual long long dump_blocks(int* coords, void* voxels, size_t cap) = 0;
+  virtual void run_resident(int iters, float* ms_int, float* ms_render) = 0;
+};
+
+FusionIface* make_fusion(const tdm_fusion_options& o, int device);
+
+}  // namespace tdm

@@ -1,0 +1,682 @@
+// CVA-MVSNet engine: host orchestration of the device kernels behind the DrMvsnet call surface.
+//
+// Reference call path being replaced:
+//   DrMvsnetImpl::CallAsync      tandem/libdr/dr_mvsnet/src/dr_mvsnet.cpp:125-283  (copy + reorder + K's + H2D)
+//   DrMvsnetImpl::CallSequential dr_mvsnet.cpp:285-331                              (module.forward + D2H)
+//   CvaMVSNet.forward            cva_mvsnet/models/cva_mvsnet.py:98-184
+// Design: one worker thread + one CUDA stream per handle (as the reference), u8 images uploaded from pinned
+// memory (6.45 MB instead of 25.8 MB fp32), everything else stays on the device until the four output maps
+// are copied back in one pinned D2H.
+#include <algorithm>
+#include <atomic>
+#include <condition_variable>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <sstream>
+#include <thread>
+#include <vector>
+
+#include "mvsnet.h"
+#include "mvsnet_kernels.cuh"
+#include "weights.h"
+
+namespace tdm {
+
+namespace {
+
+// ---- small host linear algebra (double) --------------------------------------------------------
+void mat4_mul(const double* a, const double* b, double* c) {
+  for (int i = 0; i < 4; ++i)
+    for (int j = 0; j < 4; ++j) {
+      double s = 0;
+      for (int k = 0; k < 4; ++k) s += a[i * 4 + k] * b[k * 4 + j];
+      c[i * 4 + j] = s;
+    }
+}
+bool mat4_inv(const double* m, double* out) {
+  double a[4][8];
+  for (int i = 0; i < 4; ++i)
+    for (int j = 0; j < 4; ++j) { a[i][j] = m[i * 4 + j]; a[i][4 + j] = (i == j) ? 1.0 : 0.0; }
+  for (int c = 0; c < 4; ++c) {
+    int piv = c;
+    for (int r = c + 1; r < 4; ++r) if (std::fabs(a[r][c]) > std::fabs(a[piv][c])) piv = r;
+    if (std::fabs(a[piv][c]) < 1e-300) return false;
+    if (piv != c) for (int j = 0; j < 8; ++j) std::swap(a[piv][j], a[c][j]);
+    const double d = a[c][c];
+    for (int j = 0; j < 8; ++j) a[c][j] /= d;
+    for (int r = 0; r < 4; ++r) if (r != c) {
+      const double f = a[r][c];
+      if (f != 0) for (int j = 0; j < 8; ++j) a[r][j] -= f * a[c][j];
+    }
+  }
+  for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) out[i * 4 + j] = a[i][4 + j];
+  return true;
+}
+// world->pixel 4x4: rows 0..2 = K * W[:3,:4], row 3 = W[3,:]   (module.py:799-805)
+void world_to_pixel(const float* K, const float* c2w, double* P) {
+  double c[16], w[16];
+  for (int i = 0; i < 16; ++i) c[i] = c2w[i];
+  if (!mat4_inv(c, w)) throw Error("cam_to_world is singular");
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 4; ++j) {
+      double s = 0;
+      for (int k = 0; k < 3; ++k) s += (double)K[i * 3 + k] * w[k * 4 + j];
+      P[i * 4 + j] = s;
+    }
+  for (int j = 0; j < 4; ++j) P[12 + j] = w[12 + j];
+}
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+  int C = 0, D = 0, H = 0, W = 0;
+  int kind = 1;      // 0: fp32 (logits / maps), 1: activation type TA, 2: cost-volume type TV
+  bool f32 = false;  // kind == 0
+};
+
+struct DevConv {
+  int cin = 0, cout = 0, kd = 1, kh = 1, kw = 1;
+  bool transposed = false;
+  float* w = nullptr;
+  float* bias = nullptr;
+};
+
+struct LaunchRec {
+  std::string name;
+  double bytes = 0, flops = 0;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  float ms = 0;
+};
+
+}  // namespace
+
+// ================================================================================================
+template <typename TA, typename TV>
+class MvsnetEngine final : public MvsnetIface {
+ public:
+  MvsnetEngine(const std::string& path, int device) : device_(device) {
+    TDM_CUDA(cudaSetDevice(device_));
+    wf_ = load_tdmw(path);
+    for (int i = 0; i < 3; ++i) depth_num_[i] = wf_.depth_num[i];
+    va_ = wf_.view_aggregation;
+    int lo, hi;
+    TDM_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    TDM_CUDA(cudaStreamCreateWithPriority(&stream_, cudaStreamNonBlocking, lo));
+    upload_weights();
+    worker_ = std::thread([this] { this->loop(); });
+  }
+
+  ~MvsnetEngine() override {
+    {
+      std::unique_lock<std::mutex> lk(mu_);
+      cv_done_.wait(lk, [this] { return !busy_; });
+      stop_ = true;
+    }
+    cv_work_.notify_all();
+    if (worker_.joinable()) worker_.join();
+    cudaSetDevice(device_);
+    free_plan();
+    for (auto& kv : convs_) { cudaFree(kv.second.w); cudaFree(kv.second.bias); }
+    if (select_state_) cudaFree(select_state_);
+    if (stream_) cudaStreamDestroy(stream_);
+  }
+
+  void set_option(const std::string& key, int value) override {
+    if (key == "filter_all_stages") filter_all_ = value != 0;
+    else if (key == "keep_intermediates") keep_ = value != 0;
+    else throw Error("unknown option " + key);
+  }
+
+  // "Blocking for last input. Non-blocking for this input." (dr_mvsnet.h:42)
+  void call_async(int H, int W, int V, int ref_index, unsigned char* const* bgrs, const float* K3x3x3,
+                  float* const* c2ws, float dmin, float dmax, float discard) override {
+    TDM_CHECK(V >= 2 && V <= kMaxSrc + 1, "view_num out of range");
+    TDM_CHECK(ref_index >= 0 && ref_index < V, "ref_index out of range");
+    TDM_CHECK(H % 32 == 0 && W % 32 == 0, "height and width must be multiples of 32 (three stride-2 levels at 1/4 resolution)");
+    for (int i = 0; i < V - 1; ++i)
+      for (int j = i + 1; j < V; ++j)
+        if (bgrs[i] == bgrs[j] || c2ws[i] == c2ws[j])
+          throw Error("CallAsync: the same data passed for two views (dr_mvsnet.cpp:153-160)");
+    std::unique_lock<std::mutex> lk(mu_);
+    cv_done_.wait(lk, [this] { return !busy_; });
+    if (has_result_) throw Error("CallAsync while a result is un-fetched (dr_mvsnet.cpp:315-318)");
+    if (!worker_error_.empty()) { std::string e = worker_error_; worker_error_.clear(); throw Error(e); }
+    TDM_CUDA(cudaSetDevice(device_));
+    ensure_plan(V, H, W);
+    // copy inputs (owned by the caller only during this call); reference view first (dr_mvsnet.cpp:190-197)
+    const size_t img = (size_t)H * W * 3;
+    for (int vi = 0; vi < V; ++vi) {
+      const int view = vi == 0 ? ref_index : (vi <= ref_index ? vi - 1 : vi);
+      std::memcpy(h_bgr_ + (size_t)vi * img, bgrs[view], img);
+      std::memcpy(c2w_[vi], c2ws[view], 16 * sizeof(float));
+    }
+    std::memcpy(K_, K3x3x3, 27 * sizeof(float));
+    dmin_ = dmin; dmax_ = dmax; discard_ = discard;
+    busy_ = true;
+    have_inputs_ = true;
+    lk.unlock();
+    cv_work_.notify_all();
+  }
+
+  bool ready() override {
+    std::lock_guard<std::mutex> lk(mu_);
+    return !busy_;
+  }
+  void wait() override {
+    std::unique_lock<std::mutex> lk(mu_);
+    cv_done_.wait(lk, [this] { return !busy_; });
+  }
+
+  void get_result(float* depth, float* conf, float* depth_dense, float* conf_dense) override {
+    std::unique_lock<std::mutex> lk(mu_);
+    cv_done_.wait(lk, [this] { return !busy_; });
+    if (!worker_error_.empty()) { std::string e = worker_error_; worker_error_.clear(); throw Error(e); }
+    if (!has_result_) throw Error("GetResult without a pending result (dr_mvsnet.cpp:100-102)");
+    const size_t n = (size_t)H_ * W_;
+    if (depth) std::memcpy(depth, h_out_, n * 4);
+    if (conf) std::memcpy(conf, h_out_ + n, n * 4);
+    if (depth_dense) std::memcpy(depth_dense, h_out_ + 2 * n, n * 4);
+    if (conf_dense) std::memcpy(conf_dense, h_out_ + 3 * n, n * 4);
+    has_result_ = false;
+  }
+
+  void stage_output(int stage, const std::string& which, float* out, size_t cap) override {
+    wait();
+    TDM_CHECK(stage >= 1 && stage <= 3, "stage must be 1..3");
+    TDM_CUDA(cudaSetDevice(device_));
+    const std::string name = "s" + std::to_string(stage) + "." + which;
+    auto it = bufs_.find(name);
+    if (it == bufs_.end()) throw Error("no such stage output: " + name);
+    const size_t n = (size_t)it->second.H * it->second.W;
+    TDM_CHECK(cap >= n, "stage_output: capacity too small");
+    TDM_CUDA(cudaMemcpy(out, it->second.p, n * 4, cudaMemcpyDeviceToHost));
+  }
+
+  long long debug_tensor(const std::string& name, float* out, size_t cap, int* dims4) override {
+    wait();
+    TDM_CUDA(cudaSetDevice(device_));
+    auto it = bufs_.find(name);
+    if (it == bufs_.end()) throw Error("no such tensor: " + name);
+    const DevBuf& b = it->second;
+    const long long npos = (long long)b.D * b.H * b.W;
+    const long long n = npos * b.C;
+    if (dims4) { dims4[0] = b.C; dims4[1] = b.D; dims4[2] = b.H; dims4[3] = b.W; }
+    if (!out) return n;
+    TDM_CHECK((long long)cap >= n, "debug_tensor: capacity too small");
+    if (b.f32) {
+      TDM_CUDA(cudaMemcpy(out, b.p, n * 4, cudaMemcpyDeviceToHost));  // C==1 planar already
+      return n;
+    }
+    float* tmp = nullptr;
+    TDM_CUDA(cudaMalloc(&tmp, n * 4));
+    if (b.kind == 2) k_cl_to_planar_f32<TV><<<cdiv(n, 256), 256, 0, stream_>>>((const TV*)b.p, tmp, npos, b.C);
+    else k_cl_to_planar_f32<TA><<<cdiv(n, 256), 256, 0, stream_>>>((const TA*)b.p, tmp, npos, b.C);
+    TDM_CUDA(cudaGetLastError());
+    TDM_CUDA(cudaMemcpyAsync(out, tmp, n * 4, cudaMemcpyDeviceToHost, stream_));
+    TDM_CUDA(cudaStreamSynchronize(stream_));
+    cudaFree(tmp);
+    return n;
+  }
+
+  void run_resident(int iters, float* ms_total, int* launches) override {
+    wait();
+    TDM_CHECK(have_inputs_, "run_resident: no window submitted yet");
+    TDM_CUDA(cudaSetDevice(device_));
+    cudaEvent_t e0, e1;
+    TDM_CUDA(cudaEventCreate(&e0));
+    TDM_CUDA(cudaEventCreate(&e1));
+    TDM_CUDA(cudaEventRecord(e0, stream_));
+    for (int i = 0; i < iters; ++i) forward(false);
+    TDM_CUDA(cudaEventRecord(e1, stream_));
+    TDM_CUDA(cudaEventSynchronize(e1));
+    TDM_CUDA(cudaEventElapsedTime(ms_total, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    if (launches) *launches = launches_per_forward_;
+  }
+
+  std::string profile() override {
+    wait();
+    TDM_CHECK(have_inputs_, "profile: no window submitted yet");
+    TDM_CUDA(cudaSetDevice(device_));
+    forward(false);  // warm
+    recs_.clear();
+    forward(true);
+    TDM_CUDA(cudaStreamSynchronize(stream_));
+    std::ostringstream os;
+    for (auto& r : recs_) {
+      cudaEventElapsedTime(&r.ms, r.e0, r.e1);
+      cudaEventDestroy(r.e0);
+      cudaEventDestroy(r.e1);
+      os << r.name << " " << r.ms << " " << (long long)r.bytes << " " << (long long)r.flops << "\n";
+    }
+    recs_.clear();
+    return os.str();
+  }
+
+ private:
+  // ---------------------------------------------------------------- weights
+  void add_conv(const std::string& key, const FoldedConv& fc) {
+    DevConv dc;
+    dc.cin = fc.cin; dc.cout = fc.cout; dc.kd = fc.kd; dc.kh = fc.kh; dc.kw = fc.kw; dc.transposed = fc.transposed;
+    TDM_CUDA(cudaMalloc(&dc.w, fc.w.size() * 4));
+    TDM_CUDA(cudaMemcpy(dc.w, fc.w.data(), fc.w.size() * 4, cudaMemcpyHostToDevice));
+    if (!fc.bias.empty()) {
+      TDM_CUDA(cudaMalloc(&dc.bias, fc.bias.size() * 4));
+      TDM_CUDA(cudaMemcpy(dc.bias, fc.bias.data(), fc.bias.size() * 4, cudaMemcpyHostToDevice));
+    }
+    convs_[key] = dc;
+  }
+
+  void upload_weights() {
+    const std::string f = "feature_net.";
+    add_conv("f.conv0.0", fold_conv(wf_, f + "conv0.0.conv.weight", "", f + "conv0.0.bn", false, 4));
+    add_conv("f.conv0.1", fold_conv(wf_, f + "conv0.1.conv.weight", "", f + "conv0.1.bn", false));
+    for (int b = 1; b <= 2; ++b)
+      for (int i = 0; i < 3; ++i) {
+        const std::string n = "conv" + std::to_string(b) + "." + std::to_string(i);
+        add_conv("f." + n, fold_conv(wf_, f + n + ".conv.weight", "", f + n + ".bn", false));
+      }
+    add_conv("f.out1", fold_conv(wf_, f + "out.stage1.weight", "", "", false));
+    add_conv("f.out2", fold_conv(wf_, f + "out.stage2.weight", "", "", false));
+    add_conv("f.out3", fold_conv(wf_, f + "out.stage3.weight", "", "", false));
+    add_conv("f.skip2", fold_conv(wf_, f + "skip.stage2.weight", f + "skip.stage2.bias", "", false));
+    add_conv("f.skip3", fold_conv(wf_, f + "skip.stage3.weight", f + "skip.stage3.bias", "", false));
+    for (int s = 1; s <= 3; ++s) {
+      const std::string p = "cost_regularization_net.stage" + std::to_string(s) + ".";
+      const std::string k = "s" + std::to_string(s) + ".";
+      for (int i = 0; i <= 6; ++i) {
+        const std::string n = "conv" + std::to_string(i);
+        add_conv(k + n, fold_conv(wf_, p + n + ".conv.weight", "", p + n + ".bn", false));
+      }
+      for (int i : {7, 9, 11}) {
+        const std::string n = "conv" + std::to_string(i);
+        add_conv(k + n, fold_conv(wf_, p + n + ".conv.weight", "", p + n + ".bn", true));
+      }
+      add_conv(k + "prob", fold_conv(wf_, p + "prob.weight", "", "", false));
+      if (va_) {
+        // volume_gates (cva_mvsnet.py:76-83): conv(C->1)+b, BN, ReLU, conv(1->1)+b, BN, ReLU folded to scalars
+        const std::string g = "volume_gates.stage" + std::to_string(s) + ".";
+        auto bn = [&](const std::string& pre, double& sc, double& sh, double bias) {
+          const double ga = wf_.get(pre + ".weight").data[0], be = wf_.get(pre + ".bias").data[0];
+          const double mu = wf_.get(pre + ".running_mean").data[0], var = wf_.get(pre + ".running_var").data[0];
+          sc = ga / std::sqrt(var + 1e-5);
+          sh = (bias - mu) * sc + be;
+        };
+        double s1, b1, s2, b2;
+        bn(g + "1", s1, b1, wf_.get(g + "0.bias").data[0]);
+        bn(g + "4", s2, b2, wf_.get(g + "3.bias").data[0]);
+        const auto& w1 = wf_.get(g + "0.weight").data;
+        Gate& gt = gates_[s - 1];
+        gt.C = (int)w1.size();
+        for (int c = 0; c < gt.C; ++c) gt.w1[c] = (float)(w1[c] * s1);
+        gt.b1 = (float)b1;
+        gt.w2 = (float)(wf_.get(g + "3.weight").data[0] * s2);
+        gt.b2 = (float)b2;
+      }
+    }
+    TDM_CUDA(cudaMalloc(&select_state_, sizeof(SelectState)));
+  }
+
+  // ---------------------------------------------------------------- buffers
+  DevBuf& alloc(const std::string& name, int C, int D, int H, int W, bool f32 = false, bool vol = false) {
+    DevBuf b;
+    b.C = C; b.D = D; b.H = H; b.W = W; b.f32 = f32;
+    b.kind = f32 ? 0 : (vol ? 2 : 1);
+    b.bytes = (size_t)C * D * H * W * (f32 ? 4 : (vol ? sizeof(TV) : sizeof(TA)));
+    TDM_CUDA(cudaMalloc(&b.p, b.bytes));
+    bufs_[name] = b;
+    return bufs_[name];
+  }
+  void free_plan() {
+    for (auto& kv : bufs_) cudaFree(kv.second.p);
+    bufs_.clear();
+    if (h_bgr_) cudaFreeHost(h_bgr_);
+    if (h_out_) cudaFreeHost(h_out_);
+    if (d_bgr_) cudaFree(d_bgr_);
+    h_bgr_ = nullptr; h_out_ = nullptr; d_bgr_ = nullptr;
+  }
+  void ensure_plan(int V, int H, int W) {
+    if (V == V_ && H == H_ && W == W_) return;
+    free_plan();
+    V_ = V; H_ = H; W_ = W;
+    TDM_CUDA(cudaMallocHost(&h_bgr_, (size_t)V * H * W * 3));
+    TDM_CUDA(cudaMallocHost(&h_out_, (size_t)4 * H * W * sizeof(float)));
+    TDM_CUDA(cudaMalloc(&d_bgr_, (size_t)V * H * W * 3));
+    alloc("f.img", 4, V, H, W);
+    alloc("f.c0_0", 8, V, H, W);
+    alloc("f.c3", 8, V, H, W);
+    alloc("f.c1_0", 16, V, H / 2, W / 2);
+    alloc("f.c1_1", 16, V, H / 2, W / 2);
+    alloc("f.c2", 16, V, H / 2, W / 2);
+    alloc("f.c2_0", 32, V, H / 4, W / 4);
+    alloc("f.c2_1", 32, V, H / 4, W / 4);
+    alloc("f.c1", 32, V, H / 4, W / 4);
+    alloc("feat1", 32, V, H / 4, W / 4);
+    alloc("f.i2", 32, V, H / 2, W / 2);
+    alloc("feat2", 16, V, H / 2, W / 2);
+    alloc("f.i3", 32, V, H, W);
+    alloc("feat3", 8, V, H, W);
+    for (int s = 1; s <= 3; ++s) {
+      const std::string k = "s" + std::to_string(s) + ".";
+      const int sc = 1 << (3 - s);
+      const int Hs = H / sc, Ws = W / sc, D = depth_num_[s - 1];
+      const int C = 32 >> (s - 1);
+      const bool four = (D == 4);
+      TDM_CHECK(D % 2 == 0 && (four || D % 8 == 0), "depth_num must be 4 or a multiple of 8");
+      const int D1 = D / 2, D2 = D / 4, D3 = four ? D2 : D / 8;
+      alloc(k + "volume", C, D, Hs, Ws, false, true);
+      alloc(k + "c0", 8, D, Hs, Ws);
+      alloc(k + "c1", 16, D1, Hs / 2, Ws / 2);
+      alloc(k + "c2", 16, D1, Hs / 2, Ws / 2);
+      alloc(k + "c3", 32, D2, Hs / 4, Ws / 4);
+      alloc(k + "c4", 32, D2, Hs / 4, Ws / 4);
+      alloc(k + "c5", 64, D3, Hs / 8, Ws / 8);
+      alloc(k + "c6", 64, D3, Hs / 8, Ws / 8);
+      alloc(k + "x7", 32, D2, Hs / 4, Ws / 4);
+      alloc(k + "x9", 16, D1, Hs / 2, Ws / 2);
+      alloc(k + "x11", 8, D, Hs, Ws);
+      alloc(k + "logits", 1, D, Hs, Ws, true);
+      alloc(k + "dmin", 1, 1, Hs, Ws, true);
+      for (const char* n : {"depth_dense", "confidence_dense", "depth", "confidence", "edge"})
+        alloc(k + n, 1, 1, Hs, Ws, true);
+    }
+    alloc("thr", 1, 1, 1, 4, true);
+  }
+  TA* buf(const std::string& n) { return (TA*)bufs_.at(n).p; }
+  float* fbuf(const std::string& n) { return (float*)bufs_.at(n).p; }
+
+  // ---------------------------------------------------------------- launches
+  void rec_begin(const std::string& name, double bytes, double flops) {
+    ++launch_count_;
+    if (!profiling_) return;
+    LaunchRec r;
+    r.name = name; r.bytes = bytes; r.flops = flops;
+    cudaEventCreate(&r.e0);
+    cudaEventCreate(&r.e1);
+    cudaEventRecord(r.e0, stream_);
+    recs_.push_back(r);
+  }
+  void rec_end() {
+    if (!profiling_) return;
+    cudaEventRecord(recs_.back().e1, stream_);
+  }
+
+  template <typename TIn, typename TOut, int CIN, int COUT>
+  void conv_inst(const void* in, const DevConv& c, const void* res, void* out, const ConvGeom& g) {
+    const long long npos = (long long)g.Do * g.Ho * g.Wo;
+    k_conv_direct<TIn, TOut, CIN, COUT><<<cdiv(npos, 128), 128, 0, stream_>>>((const TIn*)in, c.w, c.bias, (const TOut*)res,
+                                                                            (TOut*)out, g);
+  }
+
+  // stride s* per axis; 2-D convs pass the view axis as D with kd=1.
+  void conv(const std::string& wkey, const std::string& in, const std::string& out, int sd, int sh, int sw,
+            bool relu, int res_mode = 0, const std::string& res = "") {
+    const DevConv& c = convs_.at(wkey);
+    const DevBuf& bi = bufs_.at(in);
+    const DevBuf& bo = bufs_.at(out);
+    TDM_CHECK(bi.C == c.cin && bo.C == c.cout, "conv channel mismatch at " + wkey);
+    ConvGeom g;
+    g.Di = bi.D; g.Hi = bi.H; g.Wi = bi.W;
+    g.Do = bo.D; g.Ho = bo.H; g.Wo = bo.W;
+    g.kd = c.kd; g.kh = c.kh; g.kw = c.kw;
+    g.sd = sd; g.sh = sh; g.sw = sw;
+    g.pd = c.kd / 2; g.ph = c.kh / 2; g.pw = c.kw / 2;
+    g.transposed = c.transposed ? 1 : 0;
+    g.relu = relu ? 1 : 0;
+    g.res_mode = res_mode;
+    const double taps = (double)c.kd * c.kh * c.kw;
+    const double opos = (double)bo.D * bo.H * bo.W;
+    const double macs = c.transposed ? (double)bi.D * bi.H * bi.W * taps * c.cin * c.cout : opos * taps * c.cin * c.cout;
+    const double bytes = (double)bi.bytes + (double)bo.bytes + (res_mode ? (double)bufs_.at(res).bytes : 0.0);
+    rec_begin(wkey, bytes, 2.0 * macs);
+    const void* ip = bi.p;
+    const void* rp = res_mode ? bufs_.at(res).p : nullptr;
+#define TDM_CONV_CASE(CI, CO)                                                        \
+  if (c.cin == CI && c.cout == CO) {                                                 \
+    conv_inst<TA, TA, CI, CO>(ip, c, rp, bo.p, g);                                   \
+  } else
+    if (bo.f32) {
+      TDM_CHECK(c.cin == 8 && c.cout == 1 && bi.kind == 1, "fp32 output only for the prob conv");
+      conv_inst<TA, float, 8, 1>(ip, c, nullptr, bo.p, g);
+    } else if (bi.kind == 2) {  // stage conv0 reads the cost volume (type TV)
+      TDM_CHECK(c.cout == 8 && !res_mode, "volume input only for conv0");
+      if (c.cin == 32) conv_inst<TV, TA, 32, 8>(ip, c, rp, bo.p, g);
+      else if (c.cin == 16) conv_inst<TV, TA, 16, 8>(ip, c, rp, bo.p, g);
+      else if (c.cin == 8) conv_inst<TV, TA, 8, 8>(ip, c, rp, bo.p, g);
+      else throw Error("no conv0 instantiation for " + wkey);
+    } else
+    TDM_CONV_CASE(4, 8) TDM_CONV_CASE(8, 8) TDM_CONV_CASE(8, 16) TDM_CONV_CASE(16, 16) TDM_CONV_CASE(16, 32)
+    TDM_CONV_CASE(32, 32) TDM_CONV_CASE(32, 16) TDM_CONV_CASE(32, 8) TDM_CONV_CASE(8, 32) TDM_CONV_CASE(32, 64)
+    TDM_CONV_CASE(64, 64) TDM_CONV_CASE(64, 32) TDM_CONV_CASE(16, 8)
+    { throw Error("no conv instantiation for " + wkey); }
+#undef TDM_CONV_CASE
+    TDM_CUDA(cudaGetLastError());
+    rec_end();
+  }
+
+  void cost_volume(int s) {
+    const std::string k = "s" + std::to_string(s) + ".";
+    const DevBuf& fb = bufs_.at("feat" + std::to_string(s));
+    const DevBuf& vb = bufs_.at(k + "volume");
+    CvParams p;
+    std::memset(&p, 0, sizeof(p));
+    p.nsrc = V_ - 1; p.D = vb.D; p.H = vb.H; p.W = vb.W;
+    const float* K = K_ + 9 * (s - 1);
+    double Pr[16], Pri[16];
+    world_to_pixel(K, c2w_[0], Pr);
+    if (!mat4_inv(Pr, Pri)) throw Error("reference projection is singular");
+    for (int v = 1; v < V_; ++v) {
+      double Ps[16], M[16];
+      world_to_pixel(K, c2w_[v], Ps);
+      mat4_mul(Ps, Pri, M);
+      for (int i = 0; i < 3; ++i) {
+        for (int j = 0; j < 3; ++j) p.rot[v - 1][i * 3 + j] = (float)M[i * 4 + j];
+        p.trans[v - 1][i] = (float)M[i * 4 + 3];
+      }
+    }
+    p.view_aggregation = va_ ? 1 : 0;
+    if (va_) {
+      const Gate& g = gates_[s - 1];
+      for (int c = 0; c < g.C; ++c) p.gw1[c] = g.w1[c];
+      p.gb1 = g.b1; p.gw2 = g.w2; p.gb2 = g.b2;
+    }
+    p.hyp = hyp_spec(s);
+    const long long n = (long long)vb.D * vb.H * vb.W;
+    rec_begin(k + "cost_volume", (double)fb.bytes + (double)vb.bytes + (s > 1 ? 4.0 * vb.H * vb.W : 0.0),
+              (double)n * p.nsrc * fb.C * 12.0);
+    const float* dm = s > 1 ? fbuf(k + "dmin") : nullptr;
+    if (fb.C == 32) k_cost_volume<TA, TV, 32><<<cdiv(n, 128), 128, 0, stream_>>>((const TA*)fb.p, dm, (TV*)vb.p, p);
+    else if (fb.C == 16) k_cost_volume<TA, TV, 16><<<cdiv(n, 128), 128, 0, stream_>>>((const TA*)fb.p, dm, (TV*)vb.p, p);
+    else if (fb.C == 8) k_cost_volume<TA, TV, 8><<<cdiv(n, 128), 128, 0, stream_>>>((const TA*)fb.p, dm, (TV*)vb.p, p);
+    else throw Error("unsupported feature channels");
+    TDM_CUDA(cudaGetLastError());
+    rec_end();
+  }
+
+  HypSpec hyp_spec(int s) const {
+    HypSpec h;
+    const float base = (dmax_ - dmin_) / (float)(depth_num_[0] - 1);
+    const float ratio = s == 1 ? 1.f : (s == 2 ? 0.5f : 0.25f);
+    h.adaptive = s > 1;
+    h.dmin = dmin_;
+    h.interval = ratio * base;
+    h.D = depth_num_[s - 1];
+    return h;
+  }
+
+  void filter(int s) {
+    const std::string k = "s" + std::to_string(s) + ".";
+    const DevBuf& d = bufs_.at(k + "depth_dense");
+    const int n = d.H * d.W;
+    // cutoff_index = trunc(H*W*(100-p)/100) in fp32, clamped (module.py:1347-1348)
+    const float cf = (float)n * (100.0f - discard_) / 100.0f;
+    long long cutoff = (long long)cf;
+    cutoff = std::max(0ll, std::min((long long)n - 1, cutoff));
+    rec_begin(k + "edge_metric", 8.0 * n, 0);
+    k_edge_metric<<<cdiv(n, 128), 128, 0, stream_>>>(fbuf(k + "depth_dense"), fbuf(k + "edge"), d.H, d.W);
+    rec_end();
+    rec_begin(k + "percentile", 12.0 * n, 0);
+    k_select_init<<<1, 256, 0, stream_>>>(select_state_, (unsigned)cutoff);
+    for (int pass = 0; pass < 3; ++pass) {
+      k_select_hist<<<std::min(cdiv(n, 256 * 8), 592), 256, 0, stream_>>>(fbuf(k + "edge"), n, select_state_, pass);
+      k_select_scan<<<1, 256, 0, stream_>>>(select_state_, pass, fbuf("thr") + (s - 1));
+    }
+    launch_count_ += 6;
+    rec_end();
+    rec_begin(k + "apply_mask", 20.0 * n, 0);
+    k_apply_edge_mask<<<cdiv(n, 256), 256, 0, stream_>>>(fbuf(k + "edge"), fbuf("thr") + (s - 1), fbuf(k + "depth_dense"),
+                                                       fbuf(k + "confidence_dense"), fbuf(k + "depth"),
+                                                       fbuf(k + "confidence"), n);
+    TDM_CUDA(cudaGetLastError());
+    rec_end();
+  }
+
+  // The whole graph of cva_mvsnet.py:98-184 on stream_, inputs already in d_bgr_.
+  void forward(bool profiling) {
+    profiling_ = profiling;
+    launch_count_ = 0;
+    const int V = V_, H = H_, W = W_;
+    {
+      ViewPtrs vp;
+      for (int v = 0; v < V; ++v) vp.v[v] = d_bgr_ + (size_t)v * H * W * 3;
+      const long long n = (long long)V * H * W;
+      rec_begin("preprocess", 3.0 * n + 4.0 * n * sizeof(TA), 0);
+      k_preprocess_bgr<TA><<<cdiv(n, 256), 256, 0, stream_>>>(vp, buf("f.img"), V, H * W);
+      TDM_CUDA(cudaGetLastError());
+      rec_end();
+    }
+    conv("f.conv0.0", "f.img", "f.c0_0", 1, 1, 1, true);
+    conv("f.conv0.1", "f.c0_0", "f.c3", 1, 1, 1, true);
+    conv("f.conv1.0", "f.c3", "f.c1_0", 1, 2, 2, true);
+    conv("f.conv1.1", "f.c1_0", "f.c1_1", 1, 1, 1, true);
+    conv("f.conv1.2", "f.c1_1", "f.c2", 1, 1, 1, true);
+    conv("f.conv2.0", "f.c2", "f.c2_0", 1, 2, 2, true);
+    conv("f.conv2.1", "f.c2_0", "f.c2_1", 1, 1, 1, true);
+    conv("f.conv2.2", "f.c2_1", "f.c1", 1, 1, 1, true);
+    conv("f.out1", "f.c1", "feat1", 1, 1, 1, false);
+    conv("f.skip2", "f.c2", "f.i2", 1, 1, 1, false, 2, "f.c1");
+    conv("f.out2", "f.i2", "feat2", 1, 1, 1, false);
+    conv("f.skip3", "f.c3", "f.i3", 1, 1, 1, false, 2, "f.i2");
+    conv("f.out3", "f.i3", "feat3", 1, 1, 1, false);
+
+    for (int s = 1; s <= 3; ++s) {
+      const std::string k = "s" + std::to_string(s) + ".";
+      const HypSpec hs = hyp_spec(s);
+      const DevBuf& dd = bufs_.at(k + "depth_dense");
+      if (s > 1) {
+        const DevBuf& pd = bufs_.at("s" + std::to_string(s - 1) + ".depth_dense");
+        rec_begin(k + "adaptive_dmin", 4.0 * (pd.H * pd.W + dd.H * dd.W), 0);
+        k_adaptive_dmin<<<cdiv(dd.H * dd.W, 256), 256, 0, stream_>>>((const float*)pd.p, pd.H, pd.W, fbuf(k + "dmin"),
+                                                                    ((float)hs.D / 2.f) * hs.interval);
+        TDM_CUDA(cudaGetLastError());
+        rec_end();
+      }
+      cost_volume(s);
+      const bool four = hs.D == 4;
+      const int s5 = four ? 1 : 2;
+      conv(k + "conv0", k + "volume", k + "c0", 1, 1, 1, true);
+      conv(k + "conv1", k + "c0", k + "c1", 2, 2, 2, true);
+      conv(k + "conv2", k + "c1", k + "c2", 1, 1, 1, true);
+      conv(k + "conv3", k + "c2", k + "c3", 2, 2, 2, true);
+      conv(k + "conv4", k + "c3", k + "c4", 1, 1, 1, true);
+      conv(k + "conv5", k + "c4", k + "c5", s5, 2, 2, true);
+      conv(k + "conv6", k + "c5", k + "c6", 1, 1, 1, true);
+      conv(k + "conv7", k + "c6", k + "x7", s5, 2, 2, true, 1, k + "c4");
+      conv(k + "conv9", k + "x7", k + "x9", 2, 2, 2, true, 1, k + "c2");
+      conv(k + "conv11", k + "x9", k + "x11", 2, 2, 2, true, 1, k + "c0");
+      conv(k + "prob", k + "x11", k + "logits", 1, 1, 1, false);
+      {
+        const int HW = dd.H * dd.W;
+        rec_begin(k + "regress", 4.0 * HW * (hs.D + 3), 0);
+        const float* dm = s > 1 ? fbuf(k + "dmin") : nullptr;
+        if (hs.D <= 8) k_regress<8><<<cdiv(HW, 128), 128, 0, stream_>>>(fbuf(k + "logits"), dm, fbuf(k + "depth_dense"), fbuf(k + "confidence_dense"), HW, hs);
+        else if (hs.D <= 32) k_regress<32><<<cdiv(HW, 128), 128, 0, stream_>>>(fbuf(k + "logits"), dm, fbuf(k + "depth_dense"), fbuf(k + "confidence_dense"), HW, hs);
+        else if (hs.D <= 64) k_regress<64><<<cdiv(HW, 128), 128, 0, stream_>>>(fbuf(k + "logits"), dm, fbuf(k + "depth_dense"), fbuf(k + "confidence_dense"), HW, hs);
+        else throw Error("depth_num > 64 unsupported");
+        TDM_CUDA(cudaGetLastError());
+        rec_end();
+      }
+    }
+    for (int s = filter_all_ ? 1 : 3; s <= 3; ++s) filter(s);
+    launches_per_forward_ = launch_count_;
+    profiling_ = false;
+  }
+
+  // ---------------------------------------------------------------- worker (DrMvsnetImpl::Loop, dr_mvsnet.cpp:83-93)
+  void loop() {
+    cudaSetDevice(device_);
+    for (;;) {
+      {
+        std::unique_lock<std::mutex> lk(mu_);
+        cv_work_.wait(lk, [this] { return stop_ || (busy_ && !started_); });
+        if (stop_) return;
+        started_ = true;
+      }
+      std::string err;
+      try {
+        const size_t n = (size_t)H_ * W_;
+        TDM_CUDA(cudaMemcpyAsync(d_bgr_, h_bgr_, (size_t)V_ * n * 3, cudaMemcpyHostToDevice, stream_));
+        forward(false);
+        TDM_CUDA(cudaMemcpyAsync(h_out_, fbuf("s3.depth"), n * 4, cudaMemcpyDeviceToHost, stream_));
+        TDM_CUDA(cudaMemcpyAsync(h_out_ + n, fbuf("s3.confidence"), n * 4, cudaMemcpyDeviceToHost, stream_));
+        TDM_CUDA(cudaMemcpyAsync(h_out_ + 2 * n, fbuf("s3.depth_dense"), n * 4, cudaMemcpyDeviceToHost, stream_));
+        TDM_CUDA(cudaMemcpyAsync(h_out_ + 3 * n, fbuf("s3.confidence_dense"), n * 4, cudaMemcpyDeviceToHost, stream_));
+        TDM_CUDA(cudaStreamSynchronize(stream_));
+      } catch (const std::exception& e) {
+        err = e.what();
+      }
+      {
+        std::lock_guard<std::mutex> lk(mu_);
+        worker_error_ = err;
+        has_result_ = err.empty();
+        busy_ = false;
+        started_ = false;
+      }
+      cv_done_.notify_all();
+    }
+  }
+
+  struct Gate { int C = 0; float w1[64]; float b1 = 0, w2 = 0, b2 = 0; };
+
+  int device_ = 0;
+  cudaStream_t stream_ = nullptr;
+  WeightFile wf_;
+  int depth_num_[3];
+  bool va_ = false;
+  std::map<std::string, DevConv> convs_;
+  Gate gates_[3];
+  std::map<std::string, DevBuf> bufs_;
+  SelectState* select_state_ = nullptr;
+  int V_ = 0, H_ = 0, W_ = 0;
+  unsigned char* h_bgr_ = nullptr;
+  unsigned char* d_bgr_ = nullptr;
+  float* h_out_ = nullptr;
+  float c2w_[kMaxSrc + 1][16];
+  float K_[27];
+  float dmin_ = 0, dmax_ = 0, discard_ = 0;
+  bool filter_all_ = false, keep_ = true;
+  bool profiling_ = false;
+  int launch_count_ = 0, launches_per_forward_ = 0;
+  std::vector<LaunchRec> recs_;
+
+  std::thread worker_;
+  std::mutex mu_;
+  std::condition_variable cv_work_, cv_done_;
+  bool busy_ = false, started_ = false, stop_ = false, has_result_ = false, have_inputs_ = false;
+  std::string worker_error_;
+};
+
+MvsnetIface* make_mvsnet(const std::string& path, int precision, int device) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0)
+    throw Error("tandem_b200: no CUDA device visible - this library has no CPU fallback");
+  if (precision == 0) return new MvsnetEngine<float, float>(path, device);
+  if (precision == 1) return new MvsnetEngine<__half, __nv_bfloat16>(path, device);       // mixed16
+  if (precision == 2) return new MvsnetEngine<__nv_bfloat16, __nv_bfloat16>(path, device);  // pure bf16
+  throw Error("unknown precision");
+}
+
+}  // namespace tdm

@@ -1,0 +1,421 @@
+// CVA-MVSNet device kernels, generation 1 ("direct" path): channels-last activations
+// ([V|D][H][W][C]), fp32 accumulation, one thread per output position.  These kernels are the
+// parity baseline for every layer; the tcgen05 implicit-GEMM kernels (conv_tc.cuh) replace the
+// convolutions layer by layer and are validated against these and against the CPU oracle.
+//
+// Reference semantics restated here (never the reference's code):
+//   FeatureNet / Conv2d+BN+ReLU      cva_mvsnet/models/module.py:496-531, 104-110
+//   homography warp + aggregation    module.py:764-908, 1068-1110 ; gates cva_mvsnet.py:76-83
+//   CostRegNet (Conv3d / Deconv3d)   module.py:577-600, 213-219, 272-278
+//   softmax / expectation / conf     module.py:1116-1133
+//   adaptive hypotheses              cva_mvsnet.py:143-147, module.py:1503-1565
+//   edge filter                      module.py:1320-1361
+#pragma once
+#include "common.cuh"
+
+namespace tdm {
+
+// ------------------------------------------------------------------------------------------------
+// a1: u8 BGR HWC (window order) -> T [V][H][W][4] RGB/255 (+ zero 4th channel), reference view first.
+// Replaces the scalar CPU loop + 25.8 MB pageable H2D of dr_mvsnet.cpp:190-217,260.
+// ------------------------------------------------------------------------------------------------
+struct ViewPtrs {
+  const unsigned char* v[16];
+};
+
+template <typename T>
+__global__ void k_preprocess_bgr(ViewPtrs src, T* __restrict__ out, int V, int HW) {
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= (long long)V * HW) return;
+  int v = (int)(i / HW);
+  int p = (int)(i - (long long)v * HW);
+  const unsigned char* s = src.v[v] + 3ll * p;
+  float o[4];
+  o[0] = __fdiv_rn((float)s[2], 255.0f);
+  o[1] = __fdiv_rn((float)s[1], 255.0f);
+  o[2] = __fdiv_rn((float)s[0], 255.0f);
+  o[3] = 0.f;
+  store_vec<T, 4>(out + 4 * i, o);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Generic direct convolution / transposed convolution, channels-last.
+// ------------------------------------------------------------------------------------------------
+struct ConvGeom {
+  int Di, Hi, Wi;
+  int Do, Ho, Wo;
+  int kd, kh, kw;
+  int sd, sh, sw;
+  int pd, ph, pw;
+  int transposed;  // 0: conv, 1: transposed conv evaluated as a gather over output positions
+  int relu;
+  int res_mode;    // 0 none; 1 same-shape residual added after the activation; 2 residual is the
+                   // nearest-neighbour x2 up-sampling (h,w) of a half-resolution tensor (FPN top-down)
+};
+
+template <typename TIn, typename TOut, int CIN, int COUT>
+__global__ void __launch_bounds__(128)
+k_conv_direct(const TIn* __restrict__ in, const float* __restrict__ wgt /*[taps][CIN][COUT]*/,
+              const float* __restrict__ bias /*[COUT] or null*/, const TOut* __restrict__ res,
+              TOut* __restrict__ out, ConvGeom g) {
+  constexpr int SLICE = CIN * COUT;
+  constexpr int TAPS_PER_STAGE = (SLICE >= 4096) ? 1 : (4096 / SLICE);
+  __shared__ __align__(16) float ws[TAPS_PER_STAGE * SLICE];
+
+  const long long npos = (long long)g.Do * g.Ho * g.Wo;
+  const long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const bool active = p < npos;
+  int ow = 0, oh = 0, od = 0;
+  if (active) {
+    ow = (int)(p % g.Wo);
+    long long t = p / g.Wo;
+    oh = (int)(t % g.Ho);
+    od = (int)(t / g.Ho);
+  }
+  float acc[COUT];
+#pragma unroll
+  for (int c = 0; c < COUT; ++c) acc[c] = 0.f;
+
+  const int ntaps = g.kd * g.kh * g.kw;
+  for (int t0 = 0; t0 < ntaps; t0 += TAPS_PER_STAGE) {
+    const int nt = min(TAPS_PER_STAGE, ntaps - t0);
+    __syncthreads();
+    for (int i = threadIdx.x; i < nt * SLICE; i += blockDim.x) ws[i] = wgt[(long long)t0 * SLICE + i];
+    __syncthreads();
+    if (!active) continue;
+    for (int tt = 0; tt < nt; ++tt) {
+      const int t = t0 + tt;
+      const int kw_ = t % g.kw;
+      const int kh_ = (t / g.kw) % g.kh;
+      const int kd_ = t / (g.kw * g.kh);
+      int id, ih, iw;
+      bool ok = true;
+      if (!g.transposed) {
+        id = od * g.sd - g.pd + kd_;
+        ih = oh * g.sh - g.ph + kh_;
+        iw = ow * g.sw - g.pw + kw_;
+      } else {
+        int nd = od + g.pd - kd_, nh = oh + g.ph - kh_, nw = ow + g.pw - kw_;
+        ok = (nd % g.sd == 0) && (nh % g.sh == 0) && (nw % g.sw == 0) && nd >= 0 && nh >= 0 && nw >= 0;
+        id = nd / g.sd; ih = nh / g.sh; iw = nw / g.sw;
+      }
+      ok = ok && id >= 0 && id < g.Di && ih >= 0 && ih < g.Hi && iw >= 0 && iw < g.Wi;
+      if (!ok) continue;
+      const TIn* ip = in + (((long long)id * g.Hi + ih) * g.Wi + iw) * CIN;
+      const float* wt = ws + tt * SLICE;
+      constexpr int CH = (CIN >= 8) ? 8 : CIN;
+#pragma unroll 1
+      for (int c0 = 0; c0 < CIN; c0 += CH) {
+        float x[CH];
+        load_vec<TIn, CH>(ip + c0, x);
+#pragma unroll
+        for (int ci = 0; ci < CH; ++ci) {
+          const float* wr = wt + (c0 + ci) * COUT;
+#pragma unroll
+          for (int co = 0; co < COUT; ++co) acc[co] = fmaf(x[ci], wr[co], acc[co]);
+        }
+      }
+    }
+  }
+  if (!active) return;
+#pragma unroll
+  for (int c = 0; c < COUT; ++c) {
+    float v = acc[c] + (bias ? bias[c] : 0.f);
+    if (g.relu) v = fmaxf(v, 0.f);
+    acc[c] = v;
+  }
+  if (g.res_mode == 1) {
+    float r[COUT];
+    load_vec<TOut, COUT>(res + p * COUT, r);
+#pragma unroll
+    for (int c = 0; c < COUT; ++c) acc[c] += r[c];
+  } else if (g.res_mode == 2) {
+    float r[COUT];
+    const long long rp = ((long long)od * (g.Ho / 2) + (oh >> 1)) * (g.Wo / 2) + (ow >> 1);
+    load_vec<TOut, COUT>(res + rp * COUT, r);
+#pragma unroll
+    for (int c = 0; c < COUT; ++c) acc[c] += r[c];
+  }
+  store_vec<TOut, COUT>(out + p * COUT, acc);
+}
+
+// ------------------------------------------------------------------------------------------------
+// a3/a4: depth hypotheses.  Stage 1: d_j = dmin + interval*j.  Later stages: per-pixel dmin map from
+// the bilinear (align_corners=False) x2 up-sampling of the previous stage's dense depth.
+// ------------------------------------------------------------------------------------------------
+struct HypSpec {
+  int adaptive;    // 0 uniform, 1 adaptive
+  float dmin;      // uniform
+  float interval;  // stage interval (ratio * base)
+  int D;
+};
+
+__device__ __forceinline__ float hyp_value(const HypSpec& h, float dmin_px, int j) {
+  if (!h.adaptive) return h.dmin + h.interval * (float)j;
+  const float dmax = dmin_px + (float)h.D * h.interval;
+  const float lin = (float)j / (float)h.D;  // torch.linspace(0,1,D+1)[j], exact for power-of-two D
+  return dmin_px + (dmax - dmin_px) * lin;
+}
+
+__global__ void k_adaptive_dmin(const float* __restrict__ prev /*[h][w]*/, int h, int w,
+                                float* __restrict__ dmin /*[2h][2w]*/, float half_range) {
+  const int H = 2 * h, W = 2 * w;
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= H * W) return;
+  const int y = i / W, x = i - y * W;
+  float sy = fmaxf(0.5f * ((float)y + 0.5f) - 0.5f, 0.f);
+  float sx = fmaxf(0.5f * ((float)x + 0.5f) - 0.5f, 0.f);
+  int y0 = (int)sy, x0 = (int)sx;
+  int y1 = min(y0 + 1, h - 1), x1 = min(x0 + 1, w - 1);
+  float ly = sy - (float)y0, lx = sx - (float)x0;
+  float hy = 1.f - ly, hx = 1.f - lx;
+  float up = hy * (hx * prev[y0 * w + x0] + lx * prev[y0 * w + x1]) +
+             ly * (hx * prev[y1 * w + x0] + lx * prev[y1 * w + x1]);
+  dmin[i] = fmaxf(up - half_range, 0.001f);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1 (a5+a6): fused plane-sweep cost volume with view aggregation.  One thread per (d,h,w) voxel,
+// w fastest: all sources are warped, differenced, gated and accumulated in registers and the final
+// volume is written exactly once; the per-view warped volumes of the reference never exist.
+// ------------------------------------------------------------------------------------------------
+constexpr int kMaxSrc = 15;
+struct CvParams {
+  int nsrc, D, H, W;
+  float rot[kMaxSrc][9];
+  float trans[kMaxSrc][3];
+  float gw1[64];       // folded gate layer 1 weights (per channel)
+  float gb1, gw2, gb2; // folded scalars
+  int view_aggregation;
+  HypSpec hyp;
+};
+
+template <typename T, typename TV, int C>
+__global__ void __launch_bounds__(128)
+k_cost_volume(const T* __restrict__ feats /*[V][H][W][C], ref first*/, const float* __restrict__ dmin_map,
+              TV* __restrict__ vol /*[D][H][W][C]*/, const __grid_constant__ CvParams p) {
+  const long long n = (long long)p.D * p.H * p.W;
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int x = (int)(i % p.W);
+  const int y = (int)((i / p.W) % p.H);
+  const int d = (int)(i / ((long long)p.W * p.H));
+  const long long HW = (long long)p.H * p.W;
+  const float depth = hyp_value(p.hyp, p.hyp.adaptive ? dmin_map[y * p.W + x] : 0.f, d);
+
+  float ref[C];
+  load_vec<T, C>(feats + ((long long)y * p.W + x) * C, ref);
+  float acc[C];
+#pragma unroll
+  for (int c = 0; c < C; ++c) acc[c] = 0.f;
+  float sum[C], sq[C];
+  if (!p.view_aggregation) {
+#pragma unroll
+    for (int c = 0; c < C; ++c) { sum[c] = ref[c]; sq[c] = ref[c] * ref[c]; }
+  }
+  const float fx = (float)x, fy = (float)y;
+  const float half_w = 0.5f * (float)(p.W - 1), half_h = 0.5f * (float)(p.H - 1);
+
+  for (int s = 0; s < p.nsrc; ++s) {
+    const float* R = p.rot[s];
+    const float* t = p.trans[s];
+    const float rx = R[0] * fx + R[1] * fy + R[2];
+    const float ry = R[3] * fx + R[4] * fy + R[5];
+    const float rz = R[6] * fx + R[7] * fy + R[8];
+    const float qx = rx * depth + t[0];
+    const float qy = ry * depth + t[1];
+    const float qz = rz * depth + t[2];
+    float warped[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) warped[c] = 0.f;
+    const float u = qx / qz, v = qy / qz;
+    // grid_sample(align_corners=True) round trip through normalised coordinates
+    const float gx = u / half_w - 1.f, gy = v / half_h - 1.f;
+    const float ix = ((gx + 1.f) * 0.5f) * (float)(p.W - 1);
+    const float iy = ((gy + 1.f) * 0.5f) * (float)(p.H - 1);
+    const bool finite = (ix == ix) && (iy == iy) && fabsf(ix) < 1e8f && fabsf(iy) < 1e8f;
+    if (finite && !(qz < 0.001f)) {
+      const float x0f = floorf(ix), y0f = floorf(iy);
+      const int x0 = (int)x0f, y0 = (int)y0f;
+      const float ax = ix - x0f, ay = iy - y0f;
+      const T* base = feats + (long long)(s + 1) * HW * C;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int xx = x0 + (k & 1), yy = y0 + (k >> 1);
+        const float wgt = ((k & 1) ? ax : 1.f - ax) * ((k >> 1) ? ay : 1.f - ay);
+        if (xx >= 0 && xx < p.W && yy >= 0 && yy < p.H) {
+          float f[C];
+          load_vec<T, C>(base + ((long long)yy * p.W + xx) * C, f);
+#pragma unroll
+          for (int c = 0; c < C; ++c) warped[c] = fmaf(f[c], wgt, warped[c]);
+        }
+      }
+    }
+    if (p.view_aggregation) {
+      float dot = 0.f;
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        const float df = warped[c] - ref[c];
+        warped[c] = df * df;
+        dot = fmaf(p.gw1[c], warped[c], dot);
+      }
+      const float h1 = fmaxf(dot + p.gb1, 0.f);
+      const float g = fmaxf(fmaf(p.gw2, h1, p.gb2), 0.f) + 1.f;
+#pragma unroll
+      for (int c = 0; c < C; ++c) acc[c] = fmaf(g, warped[c], acc[c]);
+    } else {
+#pragma unroll
+      for (int c = 0; c < C; ++c) { sum[c] += warped[c]; sq[c] = fmaf(warped[c], warped[c], sq[c]); }
+    }
+  }
+  if (p.view_aggregation) {
+    const float dv = (float)p.nsrc;
+#pragma unroll
+    for (int c = 0; c < C; ++c) acc[c] = acc[c] / dv;
+  } else {
+    const float nv = (float)(p.nsrc + 1);
+#pragma unroll
+    for (int c = 0; c < C; ++c) { const float m = sum[c] / nv; acc[c] = sq[c] / nv - m * m; }
+  }
+  store_vec<TV, C>(vol + i * C, acc);
+}
+
+// ------------------------------------------------------------------------------------------------
+// a8: softmax over D + soft-argmin depth + 4-neighbour confidence, one thread per pixel.
+// ------------------------------------------------------------------------------------------------
+template <int MAXD>
+__global__ void k_regress(const float* __restrict__ logits /*[D][H][W]*/, const float* __restrict__ dmin_map,
+                          float* __restrict__ depth, float* __restrict__ conf, int HW, HypSpec hyp) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= HW) return;
+  const int D = hyp.D;
+  float l[MAXD];
+  float m = -INFINITY;
+#pragma unroll
+  for (int j = 0; j < MAXD; ++j)
+    if (j < D) { l[j] = logits[(long long)j * HW + i]; m = fmaxf(m, l[j]); }
+  float s = 0.f;
+#pragma unroll
+  for (int j = 0; j < MAXD; ++j)
+    if (j < D) { l[j] = expf(l[j] - m); s += l[j]; }
+  const float dm = hyp.adaptive ? dmin_map[i] : 0.f;
+  float dsum = 0.f, isum = 0.f;
+#pragma unroll
+  for (int j = 0; j < MAXD; ++j)
+    if (j < D) {
+      l[j] = l[j] / s;
+      dsum = fmaf(l[j], hyp_value(hyp, dm, j), dsum);
+      isum = fmaf(l[j], (float)j, isum);
+    }
+  int idx = min(max((int)isum, 0), D - 1);
+  float c = 0.f;
+#pragma unroll
+  for (int j = 0; j < MAXD; ++j)
+    if (j < D && j >= idx - 1 && j <= idx + 2) c += l[j];
+  depth[i] = dsum;
+  conf[i] = c;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K4 (a9): edge filter.  (1) per-pixel 15-th smallest |window - centre| over a zero padded 5x5
+// window; (2) exact k-th order statistic of the H*W edge values by a 3-pass radix select on the
+// float bit patterns (all values >= 0 so the unsigned order equals the float order);
+// (3) zero depth/confidence where edge > threshold.
+// ------------------------------------------------------------------------------------------------
+__global__ void k_edge_metric(const float* __restrict__ depth, float* __restrict__ edge, int H, int W) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= H * W) return;
+  const int y = i / W, x = i - y * W;
+  const float c = depth[i];
+  float e[25];
+#pragma unroll
+  for (int dy = -2; dy <= 2; ++dy)
+#pragma unroll
+    for (int dx = -2; dx <= 2; ++dx) {
+      const int yy = y + dy, xx = x + dx;
+      const float v = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? depth[yy * W + xx] : 0.f;
+      e[(dy + 2) * 5 + dx + 2] = fabsf(v - c);
+    }
+  // partial selection: after pass k the k smallest are in e[0..k]
+#pragma unroll
+  for (int k = 0; k < 15; ++k) {
+#pragma unroll
+    for (int j = k + 1; j < 25; ++j) {
+      const float a = e[k], b = e[j];
+      e[k] = fminf(a, b);
+      e[j] = fmaxf(a, b);
+    }
+  }
+  edge[i] = e[14];
+}
+
+struct SelectState {
+  unsigned prefix;   // bits decided so far (high bits)
+  unsigned k;        // remaining rank inside the current prefix bucket
+  unsigned hist[2048];
+};
+
+__global__ void k_select_init(SelectState* st, unsigned k) {
+  for (int i = threadIdx.x; i < 2048; i += blockDim.x) st->hist[i] = 0;
+  if (threadIdx.x == 0) { st->prefix = 0; st->k = k; }
+}
+
+// pass p: 0 -> bits 31..21 (11), 1 -> bits 20..10 (11), 2 -> bits 9..0 (10)
+__global__ void k_select_hist(const float* __restrict__ v, int n, SelectState* st, int pass) {
+  __shared__ unsigned h[2048];
+  for (int i = threadIdx.x; i < 2048; i += blockDim.x) h[i] = 0;
+  __syncthreads();
+  const unsigned prefix = st->prefix;
+  const int shift = pass == 0 ? 21 : (pass == 1 ? 10 : 0);
+  const unsigned hi_mask = pass == 0 ? 0u : (pass == 1 ? 0xFFE00000u : 0xFFFFFC00u);
+  const unsigned bmask = pass == 2 ? 0x3FFu : 0x7FFu;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const unsigned b = __float_as_uint(v[i]);
+    if ((b & hi_mask) == prefix) atomicAdd(&h[(b >> shift) & bmask], 1u);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2048; i += blockDim.x)
+    if (h[i]) atomicAdd(&st->hist[i], h[i]);
+}
+
+__global__ void k_select_scan(SelectState* st, int pass, float* thr_out) {
+  // single thread: 2048 bins, negligible
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    const int shift = pass == 0 ? 21 : (pass == 1 ? 10 : 0);
+    const int nb = pass == 2 ? 1024 : 2048;
+    unsigned k = st->k, cum = 0;
+    int bin = nb - 1;
+    for (int i = 0; i < nb; ++i) {
+      const unsigned c = st->hist[i];
+      if (k < cum + c) { bin = i; break; }
+      cum += c;
+    }
+    st->k = k - cum;
+    st->prefix |= ((unsigned)bin) << shift;
+    if (pass == 2) *thr_out = __uint_as_float(st->prefix);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2048; i += blockDim.x) st->hist[i] = 0;
+}
+
+__global__ void k_apply_edge_mask(const float* __restrict__ edge, const float* __restrict__ thr,
+                                  const float* __restrict__ depth_dense, const float* __restrict__ conf_dense,
+                                  float* __restrict__ depth, float* __restrict__ conf, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const bool m = edge[i] > *thr;
+  depth[i] = m ? 0.f : depth_dense[i];
+  conf[i] = m ? 0.f : conf_dense[i];
+}
+
+// layout helper for tests: channels-last T -> planar fp32 [C][N]
+template <typename T>
+__global__ void k_cl_to_planar_f32(const T* __restrict__ in, float* __restrict__ out, long long npos, int C) {
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= npos * C) return;
+  const long long pos = i / C;
+  const int c = (int)(i - pos * C);
+  out[(long long)c * npos + pos] = to_f<T>(in[i]);
+}
+
+}  // namespace tdm

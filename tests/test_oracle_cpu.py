@@ -1,0 +1,103 @@
+"""CPU tests that pin the oracles (no GPU needed)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import mvsnet_oracle as O
+from oracle.cpu import TrackerOracle, TsdfOracle
+from tandem_b200 import DrFusionOptions, default_weights
+from tandem_b200.synthetic import RoomScene, look_at_pose, tracker_case
+from tandem_b200.weights_io import load_tdmw
+
+
+def _forward(g, weights):
+    w, dn, va = load_tdmw(default_weights(weights))
+    img, order = O.preprocess_bgr(g["bgr"], int(g["ref_index"]))
+    Ks = [torch.from_numpy(g[f"K{s}"]) for s in (1, 2, 3)]
+    with torch.no_grad():
+        return O.forward(w, dn, img, Ks, torch.from_numpy(g["c2w"][order]), float(g["depth_min"]), float(g["depth_max"]),
+                         float(g["discard"]), va)
+
+
+def test_mvsnet_oracle_reproduces_shipped_goldens(golden_small):
+    """tandem/exported/tandem_512x320/sample_inputs.pt outputs (abl04) - the reference's own known-answer data."""
+    outs = _forward(golden_small, "abl04_fewer_depth_planes")
+    for s in (1, 2, 3):
+        ed = np.abs(outs[s - 1]["depth"].numpy() - golden_small[f"abl04_stage{s}_depth"]).mean()
+        ec = np.abs(outs[s - 1]["confidence"].numpy() - golden_small[f"abl04_stage{s}_confidence"]).mean()
+        assert ed < 2e-5 and ec < 2e-5, (s, ed, ec)
+
+
+def test_mvsnet_oracle_matches_reference_abl03(golden_small):
+    outs = _forward(golden_small, "abl03_view_aggregation")
+    for s in (1, 2, 3):
+        ed = np.abs(outs[s - 1]["depth_dense"].numpy() - golden_small[f"abl03_stage{s}_depth_dense"]).mean()
+        assert ed < 2e-5, (s, ed)
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/cva_mvsnet"), reason="reference tree not present")
+def test_oracle_matches_reference_model_on_fresh_input():
+    """Build-container only: the restatement equals the imported reference model on a seeded synthetic window."""
+    import sys
+    import types
+    sys.path.insert(0, "/root/reference/cva_mvsnet")
+    pkg = types.ModuleType("models"); pkg.__path__ = ["/root/reference/cva_mvsnet/models"]; sys.modules["models"] = pkg
+    from models.cva_mvsnet import CvaMVSNet, StageTensor
+    ck = torch.load("/root/reference/cva_mvsnet/pretrained/ablation/abl03_view_aggregation.ckpt", map_location="cpu",
+                    weights_only=False)
+    net = CvaMVSNet(depth_num=ck["hparams"]["MODEL.DEPTH_NUM"], view_aggregation=True).eval()
+    net.load_state_dict({k[len("cva_mvsnet."):]: v for k, v in ck["state_dict"].items()})
+    torch.manual_seed(0)
+    V, H, W = 4, 64, 96
+    img = torch.rand(V, 3, H, W)
+    img = torch.nn.functional.avg_pool2d(img, 5, 1, 2)
+    K3 = torch.tensor([[100.0, 0, 47.5], [0, 100.0, 31.5], [0, 0, 1]])
+    Ks = [torch.cat([K3[:2] * s, K3[2:]]) for s in (0.25, 0.5, 1.0)]
+    c2w = torch.eye(4).repeat(V, 1, 1)
+    c2w[:, 0, 3] = torch.arange(V) * 0.05
+    with torch.no_grad():
+        ref = net(img[None], StageTensor(*[k[None] for k in Ks]), c2w[None], torch.tensor([0.5]), torch.tensor([5.0]),
+                  torch.tensor([10.0]))
+        w, dn, va = load_tdmw(default_weights("abl03_view_aggregation"))
+        ours = O.forward(w, dn, img, Ks, c2w, 0.5, 5.0, 10.0, va)
+    for s in range(3):
+        assert (ref[s].depth_dense[0] - ours[s]["depth_dense"]).abs().max() < 1e-4
+        assert (ref[s].depth[0] - ours[s]["depth"]).abs().max() < 1e-4
+        assert (ref[s].confidence[0] - ours[s]["confidence"]).abs().max() < 1e-4
+
+
+def test_tsdf_oracle_basic_properties():
+    H, W = 60, 80
+    opt = DrFusionOptions(height=H, width=W, fx=40.0, fy=40.0, cx=39.5, cy=29.5, num_buckets=50021, num_blocks=40000)
+    scene = RoomScene(half=1.0, spheres=((0.4, 0.0, 0.5, 0.25),))
+    pose = look_at_pose((0.0, 0.0, -0.2), (0.3, 0.05, 1.0))
+    bgr, depth = scene.render(pose, H, W, 40.0, 40.0, 39.5, 29.5)
+    o = TsdfOracle(opt)
+    o.integrate(bgr, depth, pose)
+    n1 = o.stats()["allocated_blocks"]
+    assert n1 > 100 and o.stats()["dropped_blocks"] == 0
+    o.integrate(bgr, depth, pose)
+    assert o.stats()["allocated_blocks"] == n1 and o.stats()["candidate_blocks"] == 0   # idempotent block set
+    coords, vox = o.dump_blocks()
+    assert vox["weight"].max() == 2
+    assert np.all(np.abs(vox["sdf"]) <= opt.truncation_distance + 1e-6)
+    rb, rd = o.render(pose)
+    ok = (rd > 0) & (depth > 0.1)
+    assert ok.mean() > 0.8 and np.median(np.abs(rd[ok] - depth[ok])) < 0.01
+    assert o.stats()["render_distinct_voxels"] > 0
+
+
+def test_tracker_oracle_gauss_newton_descends():
+    """The normal equations must point downhill: one damped GN step on the affine+pose parameters lowers E."""
+    c = tracker_case(H=120, W=160, fx=80.0, fy=80.0, cx=79.5, cy=59.5)
+    t = TrackerOracle(c["w"], c["h"])
+    t.setK(c["w"], c["h"], c["fx"], c["fy"], c["cx"], c["cy"])
+    t.setReference(c["n"], c["pc_u"], c["pc_v"], c["pc_idepth"], c["pc_color"], 1.0, np.zeros(2))
+    t.setNew(c["dInew"])
+    r0 = t.calcRes(np.eye(4), 1.0, np.zeros(2), 1e9)
+    r1 = t.calcRes(c["refToNew"], 1.0, np.zeros(2), 1e9)
+    assert r1[0] / r1[1] < r0[0] / r0[1], "true relative pose must explain the new image better than identity"
+    H, b = t.calcG(1.0, np.zeros(2))
+    assert np.allclose(H, H.T) and np.all(np.linalg.eigvalsh(H[:6, :6]) > -1e-6)
