@@ -1,0 +1,53 @@
+// Drop-in replacement header for tandem/libdr/cuda_coarse_tracker/include/public/cuda_coarse_tracker.h (:9-82)
+// implemented over the tandem_b200 C ABI.  Caller: tandem/src/FullSystem/CoarseTracker.cpp:103-106,144,732,777-795,
+// 861-887.  The class owns only an opaque handle; callers `new` it, so the layout is ours to define.
+#ifndef PBA_CUDA_COARSE_TRACKER_H
+#define PBA_CUDA_COARSE_TRACKER_H
+
+#include <Eigen/Dense>
+
+struct tdm_tracker;  // include/tandem_b200.h
+
+class CudaCoarseTracker {
+public:
+  CudaCoarseTracker(int w, int h, float setting_huberTH, float setting_coarseCutoffTH);
+
+  void setK(int w, int h, float fx, float fy, float cx, float cy);
+
+  ~CudaCoarseTracker();
+
+  void init(int n_max_in = 0);
+
+  void free();
+
+  void setReference(int n_in, float const *pc_u_in, float const *pc_v_in, float const *pc_idepth_in,
+                    float const *pc_color_in, float ref_exposure_in, Eigen::Vector2d const &ref_aff_g2l_in);
+
+  void setNew(float const *dInew_in);
+
+  Eigen::Matrix<double, 6, 1> calcRes(Eigen::Matrix<double, 4, 4> const &refToNew, float new_exposure,
+                                      Eigen::Vector2d const &aff_g2l, float cutoffTH);
+
+  void calcG(Eigen::Matrix<double, 8, 8> &H_out, Eigen::Matrix<double, 8, 1> &b_out, const float new_exposure,
+             const Eigen::Vector2d &aff_g2l);
+
+  // Extension (not in the reference): calcRes + calcG in ONE launch, no warped buffers.
+  Eigen::Matrix<double, 6, 1> calcResAndG(Eigen::Matrix<double, 4, 4> const &refToNew, float new_exposure,
+                                          Eigen::Vector2d const &aff_g2l, float cutoffTH,
+                                          Eigen::Matrix<double, 8, 8> &H_out, Eigen::Matrix<double, 8, 1> &b_out);
+
+  void synchronize();
+
+  void startTiming();
+
+  float endTimingMilliseconds();
+
+private:
+  tdm_tracker *handle_ = nullptr;
+  const int w = 0, h = 0;
+  const float setting_huberTH, setting_coarseCutoffTH;
+  bool timing_ = false;
+  double t_start_ = 0;
+};
+
+#endif  // PBA_CUDA_COARSE_TRACKER_H

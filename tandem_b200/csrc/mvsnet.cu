@@ -70,8 +70,10 @@ void world_to_pixel(const float* K, const float* c2w, double* P) {
 
 struct DevBuf {
   void* p = nullptr;
-  size_t bytes = 0;
+  size_t bytes = 0;       // allocation size (with halos)
+  size_t alg_bytes = 0;   // algorithmic size C*D*H*W*sizeof(element): what the roofline counts
   int C = 0, D = 0, H = 0, W = 0;
+  int pd = 0;             // halo along D (P8 layout, see mvsnet_kernels.cuh)
   int kind = 1;      // 0: fp32 (logits / maps), 1: activation type TA, 2: cost-volume type TV
   bool f32 = false;  // kind == 0
 };
@@ -211,8 +213,8 @@ class MvsnetEngine final : public MvsnetIface {
     }
     float* tmp = nullptr;
     TDM_CUDA(cudaMalloc(&tmp, n * 4));
-    if (b.kind == 2) k_cl_to_planar_f32<TV><<<cdiv(n, 256), 256, 0, stream_>>>((const TV*)b.p, tmp, npos, b.C);
-    else k_cl_to_planar_f32<TA><<<cdiv(n, 256), 256, 0, stream_>>>((const TA*)b.p, tmp, npos, b.C);
+    if (b.kind == 2) k_p8_to_planar_f32<TV><<<cdiv(n, 256), 256, 0, stream_>>>(p8<const TV>(b), tmp);
+    else k_p8_to_planar_f32<TA><<<cdiv(n, 256), 256, 0, stream_>>>(p8<const TA>(b), tmp);
     TDM_CUDA(cudaGetLastError());
     TDM_CUDA(cudaMemcpyAsync(out, tmp, n * 4, cudaMemcpyDeviceToHost, stream_));
     TDM_CUDA(cudaStreamSynchronize(stream_));
@@ -272,7 +274,7 @@ class MvsnetEngine final : public MvsnetIface {
 
   void upload_weights() {
     const std::string f = "feature_net.";
-    add_conv("f.conv0.0", fold_conv(wf_, f + "conv0.0.conv.weight", "", f + "conv0.0.bn", false, 4));
+    add_conv("f.conv0.0", fold_conv(wf_, f + "conv0.0.conv.weight", "", f + "conv0.0.bn", false, 8));
     add_conv("f.conv0.1", fold_conv(wf_, f + "conv0.1.conv.weight", "", f + "conv0.1.bn", false));
     for (int b = 1; b <= 2; ++b)
       for (int i = 0; i < 3; ++i) {
@@ -321,14 +323,34 @@ class MvsnetEngine final : public MvsnetIface {
   }
 
   // ---------------------------------------------------------------- buffers
-  DevBuf& alloc(const std::string& name, int C, int D, int H, int W, bool f32 = false, bool vol = false) {
+  // f32: plain fp32 [C][D][H][W] map (logits, depth maps).  Otherwise P8 layout with zero halos; pd3 = 3-D tensor
+  // (halo along D as well), vol = cost-volume element type.
+  DevBuf& alloc(const std::string& name, int C, int D, int H, int W, bool f32 = false, bool vol = false, bool pd3 = false) {
     DevBuf b;
     b.C = C; b.D = D; b.H = H; b.W = W; b.f32 = f32;
     b.kind = f32 ? 0 : (vol ? 2 : 1);
-    b.bytes = (size_t)C * D * H * W * (f32 ? 4 : (vol ? sizeof(TV) : sizeof(TA)));
+    const size_t es = f32 ? 4 : (vol ? sizeof(TV) : sizeof(TA));
+    b.alg_bytes = (size_t)C * D * H * W * es;
+    if (f32) {
+      b.bytes = b.alg_bytes;
+    } else {
+      TDM_CHECK(C % 8 == 0, "P8 layout needs a multiple of 8 channels");
+      b.pd = pd3 ? 1 : 0;
+      b.bytes = (size_t)(C / 8) * (D + 2 * b.pd) * (H + 2) * (W + 2) * 8 * es + 4096;  // + slack for tile over-reads
+    }
     TDM_CUDA(cudaMalloc(&b.p, b.bytes));
+    TDM_CUDA(cudaMemsetAsync(b.p, 0, b.bytes, stream_));  // halos stay zero forever: kernels only write the interior
     bufs_[name] = b;
     return bufs_[name];
+  }
+  template <typename T>
+  static P8<T> p8(const DevBuf& b) {
+    P8<T> t;
+    t.p = (T*)b.p;
+    t.C = b.C; t.D = b.D; t.H = b.H; t.W = b.W; t.pd = b.pd;
+    t.Hp = b.H + 2; t.Wp = b.W + 2;
+    t.gs = (long long)(b.D + 2 * b.pd) * t.Hp * t.Wp * 8;
+    return t;
   }
   void free_plan() {
     for (auto& kv : bufs_) cudaFree(kv.second.p);
@@ -345,7 +367,7 @@ class MvsnetEngine final : public MvsnetIface {
     TDM_CUDA(cudaMallocHost(&h_bgr_, (size_t)V * H * W * 3));
     TDM_CUDA(cudaMallocHost(&h_out_, (size_t)4 * H * W * sizeof(float)));
     TDM_CUDA(cudaMalloc(&d_bgr_, (size_t)V * H * W * 3));
-    alloc("f.img", 4, V, H, W);
+    alloc("f.img", 8, V, H, W);
     alloc("f.c0_0", 8, V, H, W);
     alloc("f.c3", 8, V, H, W);
     alloc("f.c1_0", 16, V, H / 2, W / 2);
@@ -367,17 +389,17 @@ class MvsnetEngine final : public MvsnetIface {
       const bool four = (D == 4);
       TDM_CHECK(D % 2 == 0 && (four || D % 8 == 0), "depth_num must be 4 or a multiple of 8");
       const int D1 = D / 2, D2 = D / 4, D3 = four ? D2 : D / 8;
-      alloc(k + "volume", C, D, Hs, Ws, false, true);
-      alloc(k + "c0", 8, D, Hs, Ws);
-      alloc(k + "c1", 16, D1, Hs / 2, Ws / 2);
-      alloc(k + "c2", 16, D1, Hs / 2, Ws / 2);
-      alloc(k + "c3", 32, D2, Hs / 4, Ws / 4);
-      alloc(k + "c4", 32, D2, Hs / 4, Ws / 4);
-      alloc(k + "c5", 64, D3, Hs / 8, Ws / 8);
-      alloc(k + "c6", 64, D3, Hs / 8, Ws / 8);
-      alloc(k + "x7", 32, D2, Hs / 4, Ws / 4);
-      alloc(k + "x9", 16, D1, Hs / 2, Ws / 2);
-      alloc(k + "x11", 8, D, Hs, Ws);
+      alloc(k + "volume", C, D, Hs, Ws, false, true, true);
+      alloc(k + "c0", 8, D, Hs, Ws, false, false, true);
+      alloc(k + "c1", 16, D1, Hs / 2, Ws / 2, false, false, true);
+      alloc(k + "c2", 16, D1, Hs / 2, Ws / 2, false, false, true);
+      alloc(k + "c3", 32, D2, Hs / 4, Ws / 4, false, false, true);
+      alloc(k + "c4", 32, D2, Hs / 4, Ws / 4, false, false, true);
+      alloc(k + "c5", 64, D3, Hs / 8, Ws / 8, false, false, true);
+      alloc(k + "c6", 64, D3, Hs / 8, Ws / 8, false, false, true);
+      alloc(k + "x7", 32, D2, Hs / 4, Ws / 4, false, false, true);
+      alloc(k + "x9", 16, D1, Hs / 2, Ws / 2, false, false, true);
+      alloc(k + "x11", 8, D, Hs, Ws, false, false, true);
       alloc(k + "logits", 1, D, Hs, Ws, true);
       alloc(k + "dmin", 1, 1, Hs, Ws, true);
       for (const char* n : {"depth_dense", "confidence_dense", "depth", "confidence", "edge"})
@@ -385,7 +407,6 @@ class MvsnetEngine final : public MvsnetIface {
     }
     alloc("thr", 1, 1, 1, 4, true);
   }
-  TA* buf(const std::string& n) { return (TA*)bufs_.at(n).p; }
   float* fbuf(const std::string& n) { return (float*)bufs_.at(n).p; }
 
   // ---------------------------------------------------------------- launches
@@ -405,10 +426,14 @@ class MvsnetEngine final : public MvsnetIface {
   }
 
   template <typename TIn, typename TOut, int CIN, int COUT>
-  void conv_inst(const void* in, const DevConv& c, const void* res, void* out, const ConvGeom& g) {
+  void conv_inst(const DevBuf& in, const DevConv& c, const DevBuf* res, const DevBuf& out, const ConvGeom& g) {
     const long long npos = (long long)g.Do * g.Ho * g.Wo;
-    k_conv_direct<TIn, TOut, CIN, COUT><<<cdiv(npos, 128), 128, 0, stream_>>>((const TIn*)in, c.w, c.bias, (const TOut*)res,
-                                                                            (TOut*)out, g);
+    P8<const TOut> r{};
+    if (res) r = p8<const TOut>(*res);
+    P8<TOut> o{};
+    float* plain = nullptr;
+    if constexpr (COUT == 1) plain = (float*)out.p; else o = p8<TOut>(out);
+    k_conv_direct<TIn, TOut, CIN, COUT><<<cdiv(npos, 128), 128, 0, stream_>>>(p8<const TIn>(in), c.w, c.bias, r, o, plain, g);
   }
 
   // stride s* per axis; 2-D convs pass the view axis as D with kd=1.
@@ -430,25 +455,24 @@ class MvsnetEngine final : public MvsnetIface {
     const double taps = (double)c.kd * c.kh * c.kw;
     const double opos = (double)bo.D * bo.H * bo.W;
     const double macs = c.transposed ? (double)bi.D * bi.H * bi.W * taps * c.cin * c.cout : opos * taps * c.cin * c.cout;
-    const double bytes = (double)bi.bytes + (double)bo.bytes + (res_mode ? (double)bufs_.at(res).bytes : 0.0);
+    const double bytes = (double)bi.alg_bytes + (double)bo.alg_bytes + (res_mode ? (double)bufs_.at(res).alg_bytes : 0.0);
     rec_begin(wkey, bytes, 2.0 * macs);
-    const void* ip = bi.p;
-    const void* rp = res_mode ? bufs_.at(res).p : nullptr;
+    const DevBuf* rp = res_mode ? &bufs_.at(res) : nullptr;
 #define TDM_CONV_CASE(CI, CO)                                                        \
   if (c.cin == CI && c.cout == CO) {                                                 \
-    conv_inst<TA, TA, CI, CO>(ip, c, rp, bo.p, g);                                   \
+    conv_inst<TA, TA, CI, CO>(bi, c, rp, bo, g);                                     \
   } else
     if (bo.f32) {
       TDM_CHECK(c.cin == 8 && c.cout == 1 && bi.kind == 1, "fp32 output only for the prob conv");
-      conv_inst<TA, float, 8, 1>(ip, c, nullptr, bo.p, g);
+      conv_inst<TA, float, 8, 1>(bi, c, nullptr, bo, g);
     } else if (bi.kind == 2) {  // stage conv0 reads the cost volume (type TV)
       TDM_CHECK(c.cout == 8 && !res_mode, "volume input only for conv0");
-      if (c.cin == 32) conv_inst<TV, TA, 32, 8>(ip, c, rp, bo.p, g);
-      else if (c.cin == 16) conv_inst<TV, TA, 16, 8>(ip, c, rp, bo.p, g);
-      else if (c.cin == 8) conv_inst<TV, TA, 8, 8>(ip, c, rp, bo.p, g);
+      if (c.cin == 32) conv_inst<TV, TA, 32, 8>(bi, c, rp, bo, g);
+      else if (c.cin == 16) conv_inst<TV, TA, 16, 8>(bi, c, rp, bo, g);
+      else if (c.cin == 8) conv_inst<TV, TA, 8, 8>(bi, c, rp, bo, g);
       else throw Error("no conv0 instantiation for " + wkey);
     } else
-    TDM_CONV_CASE(4, 8) TDM_CONV_CASE(8, 8) TDM_CONV_CASE(8, 16) TDM_CONV_CASE(16, 16) TDM_CONV_CASE(16, 32)
+    TDM_CONV_CASE(8, 8) TDM_CONV_CASE(8, 16) TDM_CONV_CASE(16, 16) TDM_CONV_CASE(16, 32)
     TDM_CONV_CASE(32, 32) TDM_CONV_CASE(32, 16) TDM_CONV_CASE(32, 8) TDM_CONV_CASE(8, 32) TDM_CONV_CASE(32, 64)
     TDM_CONV_CASE(64, 64) TDM_CONV_CASE(64, 32) TDM_CONV_CASE(16, 8)
     { throw Error("no conv instantiation for " + wkey); }
@@ -485,12 +509,12 @@ class MvsnetEngine final : public MvsnetIface {
     }
     p.hyp = hyp_spec(s);
     const long long n = (long long)vb.D * vb.H * vb.W;
-    rec_begin(k + "cost_volume", (double)fb.bytes + (double)vb.bytes + (s > 1 ? 4.0 * vb.H * vb.W : 0.0),
+    rec_begin(k + "cost_volume", (double)fb.alg_bytes + (double)vb.alg_bytes + (s > 1 ? 4.0 * vb.H * vb.W : 0.0),
               (double)n * p.nsrc * fb.C * 12.0);
     const float* dm = s > 1 ? fbuf(k + "dmin") : nullptr;
-    if (fb.C == 32) k_cost_volume<TA, TV, 32><<<cdiv(n, 128), 128, 0, stream_>>>((const TA*)fb.p, dm, (TV*)vb.p, p);
-    else if (fb.C == 16) k_cost_volume<TA, TV, 16><<<cdiv(n, 128), 128, 0, stream_>>>((const TA*)fb.p, dm, (TV*)vb.p, p);
-    else if (fb.C == 8) k_cost_volume<TA, TV, 8><<<cdiv(n, 128), 128, 0, stream_>>>((const TA*)fb.p, dm, (TV*)vb.p, p);
+    if (fb.C == 32) k_cost_volume<TA, TV, 32><<<cdiv(n, 128), 128, 0, stream_>>>(p8<const TA>(fb), dm, p8<TV>(vb), p);
+    else if (fb.C == 16) k_cost_volume<TA, TV, 16><<<cdiv(n, 128), 128, 0, stream_>>>(p8<const TA>(fb), dm, p8<TV>(vb), p);
+    else if (fb.C == 8) k_cost_volume<TA, TV, 8><<<cdiv(n, 128), 128, 0, stream_>>>(p8<const TA>(fb), dm, p8<TV>(vb), p);
     else throw Error("unsupported feature channels");
     TDM_CUDA(cudaGetLastError());
     rec_end();
@@ -543,8 +567,8 @@ class MvsnetEngine final : public MvsnetIface {
       ViewPtrs vp;
       for (int v = 0; v < V; ++v) vp.v[v] = d_bgr_ + (size_t)v * H * W * 3;
       const long long n = (long long)V * H * W;
-      rec_begin("preprocess", 3.0 * n + 4.0 * n * sizeof(TA), 0);
-      k_preprocess_bgr<TA><<<cdiv(n, 256), 256, 0, stream_>>>(vp, buf("f.img"), V, H * W);
+      rec_begin("preprocess", 3.0 * n + 8.0 * n * sizeof(TA), 0);
+      k_preprocess_bgr<TA><<<cdiv(n, 256), 256, 0, stream_>>>(vp, p8<TA>(bufs_.at("f.img")), V, H * W);
       TDM_CUDA(cudaGetLastError());
       rec_end();
     }

@@ -1,7 +1,13 @@
-// CVA-MVSNet device kernels, generation 1 ("direct" path): channels-last activations
-// ([V|D][H][W][C]), fp32 accumulation, one thread per output position.  These kernels are the
-// parity baseline for every layer; the tcgen05 implicit-GEMM kernels (conv_tc.cuh) replace the
-// convolutions layer by layer and are validated against these and against the CPU oracle.
+// CVA-MVSNet device kernels, generation 1 ("direct" path): fp32 accumulation, one thread per output
+// position.  These kernels are the parity baseline for every layer; the tcgen05 implicit-GEMM
+// kernels (conv_tc.cuh) replace the convolutions layer by layer and are validated against these and
+// against the CPU oracle.
+//
+// Activation layout "P8" (shared with the tcgen05 path): channel-group-planar with zero halos,
+//     [C/8][D+2*pd][H+2][W+2][8]          (pd = 1 for volumes, 0 for the view axis of 2-D maps)
+// so one position of one channel group is a 16-byte (16-bit types) vector, a row segment of a group
+// is contiguous (1-D TMA bulk copies), and every 3x3x3 tap is a constant address shift inside a
+// plane.  Halos are zeroed once at allocation; kernels only ever write the interior.
 //
 // Reference semantics restated here (never the reference's code):
 //   FeatureNet / Conv2d+BN+ReLU      cva_mvsnet/models/module.py:496-531, 104-110
@@ -15,6 +21,18 @@
 
 namespace tdm {
 
+template <typename T>
+struct P8 {
+  T* p;
+  int C, D, H, W;   // logical dims
+  int pd;           // halo along D (0 or 1); H and W always carry a halo of 1
+  int Hp, Wp;       // H+2, W+2
+  long long gs;     // elements between channel groups = (D+2pd)*Hp*Wp*8
+  __device__ __forceinline__ long long pos(int d, int h, int w) const {
+    return ((((long long)(d + pd)) * Hp + (h + 1)) * Wp + (w + 1)) * 8;
+  }
+};
+
 // ------------------------------------------------------------------------------------------------
 // a1: u8 BGR HWC (window order) -> T [V][H][W][4] RGB/255 (+ zero 4th channel), reference view first.
 // Replaces the scalar CPU loop + 25.8 MB pageable H2D of dr_mvsnet.cpp:190-217,260.
@@ -24,18 +42,17 @@ struct ViewPtrs {
 };
 
 template <typename T>
-__global__ void k_preprocess_bgr(ViewPtrs src, T* __restrict__ out, int V, int HW) {
+__global__ void k_preprocess_bgr(ViewPtrs src, P8<T> out, int V, int HW) {
   long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (i >= (long long)V * HW) return;
   int v = (int)(i / HW);
   int p = (int)(i - (long long)v * HW);
   const unsigned char* s = src.v[v] + 3ll * p;
-  float o[4];
+  float o[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   o[0] = __fdiv_rn((float)s[2], 255.0f);
   o[1] = __fdiv_rn((float)s[1], 255.0f);
   o[2] = __fdiv_rn((float)s[0], 255.0f);
-  o[3] = 0.f;
-  store_vec<T, 4>(out + 4 * i, o);
+  store_vec<T, 8>(out.p + out.pos(v, p / out.W, p % out.W), o);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -55,9 +72,9 @@ struct ConvGeom {
 
 template <typename TIn, typename TOut, int CIN, int COUT>
 __global__ void __launch_bounds__(128)
-k_conv_direct(const TIn* __restrict__ in, const float* __restrict__ wgt /*[taps][CIN][COUT]*/,
-              const float* __restrict__ bias /*[COUT] or null*/, const TOut* __restrict__ res,
-              TOut* __restrict__ out, ConvGeom g) {
+k_conv_direct(const P8<const TIn> in, const float* __restrict__ wgt /*[taps][CIN][COUT]*/,
+              const float* __restrict__ bias /*[COUT] or null*/, const P8<const TOut> res,
+              const P8<TOut> out, float* __restrict__ plain_out /*COUT==1: fp32 [D][H][W]*/, ConvGeom g) {
   constexpr int SLICE = CIN * COUT;
   constexpr int TAPS_PER_STAGE = (SLICE >= 4096) ? 1 : (4096 / SLICE);
   __shared__ __align__(16) float ws[TAPS_PER_STAGE * SLICE];
@@ -101,13 +118,14 @@ k_conv_direct(const TIn* __restrict__ in, const float* __restrict__ wgt /*[taps]
       }
       ok = ok && id >= 0 && id < g.Di && ih >= 0 && ih < g.Hi && iw >= 0 && iw < g.Wi;
       if (!ok) continue;
-      const TIn* ip = in + (((long long)id * g.Hi + ih) * g.Wi + iw) * CIN;
+      const TIn* ip = in.p + in.pos(id, ih, iw);
       const float* wt = ws + tt * SLICE;
-      constexpr int CH = (CIN >= 8) ? 8 : CIN;
+      constexpr int CH = 8;
+      static_assert(CIN % 8 == 0, "P8 layout: channel count must be a multiple of 8");
 #pragma unroll 1
       for (int c0 = 0; c0 < CIN; c0 += CH) {
         float x[CH];
-        load_vec<TIn, CH>(ip + c0, x);
+        load_vec<TIn, CH>(ip + (c0 >> 3) * in.gs, x);
 #pragma unroll
         for (int ci = 0; ci < CH; ++ci) {
           const float* wr = wt + (c0 + ci) * COUT;
@@ -124,19 +142,28 @@ k_conv_direct(const TIn* __restrict__ in, const float* __restrict__ wgt /*[taps]
     if (g.relu) v = fmaxf(v, 0.f);
     acc[c] = v;
   }
-  if (g.res_mode == 1) {
-    float r[COUT];
-    load_vec<TOut, COUT>(res + p * COUT, r);
+  if constexpr (COUT == 1) {
+    plain_out[p] = acc[0];
+  } else {
+    if (g.res_mode != 0) {
+      const long long rp = g.res_mode == 1 ? res.pos(od, oh, ow) : res.pos(od, oh >> 1, ow >> 1);
 #pragma unroll
-    for (int c = 0; c < COUT; ++c) acc[c] += r[c];
-  } else if (g.res_mode == 2) {
-    float r[COUT];
-    const long long rp = ((long long)od * (g.Ho / 2) + (oh >> 1)) * (g.Wo / 2) + (ow >> 1);
-    load_vec<TOut, COUT>(res + rp * COUT, r);
+      for (int c0 = 0; c0 < COUT; c0 += 8) {
+        float r[8];
+        load_vec<TOut, 8>(res.p + rp + (c0 >> 3) * res.gs, r);
 #pragma unroll
-    for (int c = 0; c < COUT; ++c) acc[c] += r[c];
+        for (int c = 0; c < 8; ++c) acc[c0 + c] += r[c];
+      }
+    }
+    const long long op = out.pos(od, oh, ow);
+#pragma unroll
+    for (int c0 = 0; c0 < COUT; c0 += 8) {
+      float o8[8];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) o8[c] = acc[c0 + c];
+      store_vec<TOut, 8>(out.p + op + (c0 >> 3) * out.gs, o8);
+    }
   }
-  store_vec<TOut, COUT>(out + p * COUT, acc);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -192,19 +219,27 @@ struct CvParams {
 
 template <typename T, typename TV, int C>
 __global__ void __launch_bounds__(128)
-k_cost_volume(const T* __restrict__ feats /*[V][H][W][C], ref first*/, const float* __restrict__ dmin_map,
-              TV* __restrict__ vol /*[D][H][W][C]*/, const __grid_constant__ CvParams p) {
+k_cost_volume(const P8<const T> feats /*views on the D axis, ref first*/, const float* __restrict__ dmin_map,
+              const P8<TV> vol, const __grid_constant__ CvParams p) {
   const long long n = (long long)p.D * p.H * p.W;
   const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (i >= n) return;
   const int x = (int)(i % p.W);
   const int y = (int)((i / p.W) % p.H);
   const int d = (int)(i / ((long long)p.W * p.H));
-  const long long HW = (long long)p.H * p.W;
   const float depth = hyp_value(p.hyp, p.hyp.adaptive ? dmin_map[y * p.W + x] : 0.f, d);
 
   float ref[C];
-  load_vec<T, C>(feats + ((long long)y * p.W + x) * C, ref);
+  {
+    const T* rp = feats.p + feats.pos(0, y, x);
+#pragma unroll
+    for (int c0 = 0; c0 < C; c0 += 8) {
+      float t8[8];
+      load_vec<T, 8>(rp + (c0 >> 3) * feats.gs, t8);
+#pragma unroll
+      for (int c = 0; c < 8; ++c) ref[c0 + c] = t8[c];
+    }
+  }
   float acc[C];
 #pragma unroll
   for (int c = 0; c < C; ++c) acc[c] = 0.f;
@@ -238,16 +273,19 @@ k_cost_volume(const T* __restrict__ feats /*[V][H][W][C], ref first*/, const flo
       const float x0f = floorf(ix), y0f = floorf(iy);
       const int x0 = (int)x0f, y0 = (int)y0f;
       const float ax = ix - x0f, ay = iy - y0f;
-      const T* base = feats + (long long)(s + 1) * HW * C;
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const int xx = x0 + (k & 1), yy = y0 + (k >> 1);
         const float wgt = ((k & 1) ? ax : 1.f - ax) * ((k >> 1) ? ay : 1.f - ay);
         if (xx >= 0 && xx < p.W && yy >= 0 && yy < p.H) {
-          float f[C];
-          load_vec<T, C>(base + ((long long)yy * p.W + xx) * C, f);
+          const T* tp = feats.p + feats.pos(s + 1, yy, xx);
 #pragma unroll
-          for (int c = 0; c < C; ++c) warped[c] = fmaf(f[c], wgt, warped[c]);
+          for (int c0 = 0; c0 < C; c0 += 8) {
+            float f[8];
+            load_vec<T, 8>(tp + (c0 >> 3) * feats.gs, f);
+#pragma unroll
+            for (int c = 0; c < 8; ++c) warped[c0 + c] = fmaf(f[c], wgt, warped[c0 + c]);
+          }
         }
       }
     }
@@ -277,7 +315,16 @@ k_cost_volume(const T* __restrict__ feats /*[V][H][W][C], ref first*/, const flo
 #pragma unroll
     for (int c = 0; c < C; ++c) { const float m = sum[c] / nv; acc[c] = sq[c] / nv - m * m; }
   }
-  store_vec<TV, C>(vol + i * C, acc);
+  {
+    const long long op = vol.pos(d, y, x);
+#pragma unroll
+    for (int c0 = 0; c0 < C; c0 += 8) {
+      float o8[8];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) o8[c] = acc[c0 + c];
+      store_vec<TV, 8>(vol.p + op + (c0 >> 3) * vol.gs, o8);
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -410,12 +457,17 @@ __global__ void k_apply_edge_mask(const float* __restrict__ edge, const float* _
 
 // layout helper for tests: channels-last T -> planar fp32 [C][N]
 template <typename T>
-__global__ void k_cl_to_planar_f32(const T* __restrict__ in, float* __restrict__ out, long long npos, int C) {
+__global__ void k_p8_to_planar_f32(const P8<const T> in, float* __restrict__ out) {
+  const long long npos = (long long)in.D * in.H * in.W;
   long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  if (i >= npos * C) return;
-  const long long pos = i / C;
-  const int c = (int)(i - pos * C);
-  out[(long long)c * npos + pos] = to_f<T>(in[i]);
+  if (i >= npos * in.C) return;
+  const int c = (int)(i / npos);
+  long long pos = i - (long long)c * npos;
+  const int w = (int)(pos % in.W);
+  pos /= in.W;
+  const int h = (int)(pos % in.H);
+  const int d = (int)(pos / in.H);
+  out[i] = to_f<T>(in.p[in.pos(d, h, w) + (c >> 3) * in.gs + (c & 7)]);
 }
 
 }  // namespace tdm

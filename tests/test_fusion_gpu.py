@@ -15,15 +15,22 @@ INTR = dict(fx=80.0, fy=80.0, cx=79.5, cy=59.5)
 
 
 def _opts(**kw):
-    return DrFusionOptions(height=H, width=W, num_buckets=200003, bucket_size=10, num_blocks=120000, **INTR, **kw)
+    base = dict(height=H, width=W, num_buckets=200003, bucket_size=10, num_blocks=120000, **INTR)
+    base.update(kw)
+    return DrFusionOptions(**base)
 
 
-def _scene_frames(n, half=1.2, seed=0):
-    scene = RoomScene(half=half, spheres=((0.5, 0.1, 0.4, 0.3), (-0.4, -0.2, 0.6, 0.25), (0.1, 0.4, -0.6, 0.3)))
+SCENE = RoomScene(half=1.2, spheres=((0.5, 0.1, 0.4, 0.3), (-0.4, -0.2, 0.6, 0.25), (0.1, 0.4, -0.6, 0.3)))
+
+
+def _render(poses, seed=0):
+    return [SCENE.render(p, H, W, INTR["fx"], INTR["fy"], INTR["cx"], INTR["cy"], noise_sigma=0.002, dropout=0.02,
+                         seed=seed + k) for k, p in enumerate(poses)]
+
+
+def _scene_frames(n, seed=0):
     poses = circle_trajectory(n, radius=0.3)
-    frames = [scene.render(p, H, W, INTR["fx"], INTR["fy"], INTR["cx"], INTR["cy"], noise_sigma=0.002, dropout=0.02,
-                           seed=seed + k) for k, p in enumerate(poses)]
-    return poses, frames
+    return poses, _render(poses, seed)
 
 
 def _compare_maps(f, o):
@@ -39,14 +46,19 @@ def _compare_maps(f, o):
 
 def test_integrate_and_render_match_oracle():
     poses, frames = _scene_frames(4)
+    poses = [poses[0], poses[0].copy(), poses[1], poses[1].copy()]
+    poses[1][:3, 3] += np.float32(0.03)
+    poses[3][:3, 3] -= np.float32(0.02)
+    frames = _render(poses)
     f = DrFusion(_opts())
     o = TsdfOracle(_opts())
     for k, (pose, (bgr, depth)) in enumerate(zip(poses, frames)):
         f.IntegrateScanAsync(bgr, depth, pose)
         o.integrate(bgr, depth, pose)
-        f.RenderAsync([poses[(k + 1) % len(poses)]])
+        rp = poses[max(k - 1, 0)] if k % 2 else pose   # alternate: the view just integrated / the previous one
+        f.RenderAsync([rp])
         (rb,), (rd,) = f.GetRenderResult()
-        ob, od = o.render(poses[(k + 1) % len(poses)])
+        ob, od = o.render(rp)
         sg, so = f.stats(), o.stats()
         assert sg["allocated_blocks"] == so["allocated_blocks"]
         assert sg["visible_blocks"] == so["visible_blocks"]
