@@ -166,6 +166,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default="mixed16", choices=["mixed16", "fp32", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--tc", type=int, default=-1, help="1/0: force the tcgen05 conv path on/off (default: engine default)")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3) if a.impl == "ours" else a.warmup
 
@@ -193,6 +194,8 @@ def main():
     from tandem_b200 import DrMvsnet, default_weights
     win = load_window(rank)
     m = DrMvsnet(default_weights(WEIGHTS), precision=a.precision, device=local)
+    if a.tc >= 0:
+        m.set_option("use_tc", a.tc)
 
     def call():
         m.CallAsync(win["H"], win["W"], win["V"], win["ref_index"], win["bgrs"], win["K"], win["c2ws"], win["dmin"],
@@ -228,10 +231,8 @@ def main():
     barrier()
     clocks = sampler.stop() if sampler else None
 
-    if dist is not None:
-        t = torch.tensor([ms_dev, ms_e2e], device=f"cuda:{local}", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_dev, ms_e2e = float(t[0]), float(t[1])
+    from tandem_b200.parallel import reduce_max
+    ms_dev, ms_e2e = reduce_max(dist, [ms_dev, ms_e2e], device=f"cuda:{local}")   # slowest rank defines the step time
 
     if rank == 0:
         value = world * a.steps / (ms_dev / 1e3)

@@ -16,9 +16,15 @@
 // Accumulators live in TMEM, double-buffered per output plane, so the epilogue (tcgen05.ld -> bias/ReLU/skip ->
 // 16-byte stores) of plane d overlaps the MMAs of plane d+1.
 //
-// Warp roles (192 threads): warp 0 = TMA producer (one lane), warp 1 = MMA issuer (one lane) + TMEM allocator,
-// warps 2..5 = epilogue (TMEM lane quarter = warp_id % 4).
+// Warp roles (256 threads): warp 0 = TMA producer (one lane); warps 1,6,7 = MMA issuers (warp-uniform code, one elected
+// lane issues; chunk c of a plane belongs to issuer c mod 3 - a single issuing thread needs ~60 cycles of descriptor
+// arithmetic per tcgen05.mma, more than the ~36 cycles the tensor core needs to stream the 4.5 KB of operands, so the
+// issue work is spread over three warps); warp 1 also owns the TMEM allocation; warps 2..5 = epilogue (TMEM lane
+// quarter = warp_id % 4).
 #pragma once
+#include <cmath>
+#include <vector>
+
 #include "common.cuh"
 #include "mvsnet_kernels.cuh"
 
@@ -38,6 +44,7 @@ struct Geom {
   int relu, has_res;
   int cout;               // real output channels (<= NPAD)
   int S;                  // ring slots
+  int oHp, oWp, opd;      // padded dims / D halo of the OUTPUT tensor (differs from the input in deconv mode)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -98,19 +105,23 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-constexpr int kThreads = 192;
+constexpr int kThreads = 256;   // warp 0 TMA, warp 1 MMA (+TMEM alloc), warps 2..5 epilogue, warps 6,7 MMA
+constexpr int kMmaWarps = 3;
 
 // blocks of B per kd plane: one block = one K=16 MMA step = NPAD x 16 elements in canonical order
-template <int CIN> constexpr int blocks_per_kd() { return CIN >= 16 ? 9 * (CIN / 16) : 5; }
+// MODE 0: 3x3 stencil per plane (9 taps).  MODE 1: transposed conv k3 s2 p1 op1 as a GEMM over the INPUT grid: 2x2 taps
+// per plane at offsets {0,1}^2 (stencil positions (1..2,1..2)), 2 planes, N = 8 output parity classes x COUT.
+template <int CIN, int MODE = 0> constexpr int blocks_per_kd() { return MODE == 1 ? 4 * (CIN / 16) : (CIN >= 16 ? 9 * (CIN / 16) : 5); }
 
 // AFMT: 0 = f16, 1 = bf16 (a_format/b_format of the instruction descriptor).  OUT_PLAIN: fp32 [D][H][W] (prob conv).
-template <typename TIn, typename TOut, int CIN, int NPAD, int KD, bool OUT_PLAIN>
+template <typename TIn, typename TOut, int CIN, int NPAD, int KD, bool OUT_PLAIN, int MODE = 0>
 __global__ void __launch_bounds__(kThreads, 1)
 k_conv_tc(const TIn* __restrict__ in, const TIn* __restrict__ bimg /*host-arranged B image*/, const float* __restrict__ bias,
           const TOut* __restrict__ res, TOut* __restrict__ out, float* __restrict__ plain_out, const __grid_constant__ Geom g) {
   constexpr int CG = CIN / 8;
-  constexpr int NBLK = blocks_per_kd<CIN>();
+  constexpr int NBLK = blocks_per_kd<CIN, MODE>();
   constexpr int B_BYTES = KD * NBLK * NPAD * 32;
+  constexpr int PLANE0 = MODE == 1 ? 1 : 0;   // deconv reads input planes d and d+1 (padded indices d+1, d+2)
   constexpr uint32_t AFMT = std::is_same<TIn, __nv_bfloat16>::value ? 1u : 0u;
   constexpr uint32_t IDESC = (1u << 4) | (AFMT << 7) | (AFMT << 10) | ((uint32_t)(NPAD >> 3) << 17) | ((128u >> 4) << 24);
 
@@ -127,7 +138,8 @@ k_conv_tc(const TIn* __restrict__ in, const TIn* __restrict__ bimg /*host-arrang
   uint64_t* b_full = bars + 20;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 21);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // provably warp-uniform (uniform datapath)
+  const int lane = threadIdx.x & 31;
   int tile = blockIdx.x;
   const int tw = tile % g.tiles_w; tile /= g.tiles_w;
   const int th = tile % g.tiles_h; tile /= g.tiles_h;
@@ -140,8 +152,8 @@ k_conv_tc(const TIn* __restrict__ in, const TIn* __restrict__ bimg /*host-arrang
   while (tmem_cols < 2 * acc_cols) tmem_cols <<= 1;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < g.S; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 4); }
+    for (int s = 0; s < g.S; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], kMmaWarps); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], kMmaWarps); mbar_init(&acc_empty[b], 4); }
     mbar_init(b_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -152,7 +164,7 @@ k_conv_tc(const TIn* __restrict__ in, const TIn* __restrict__ bimg /*host-arrang
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -166,7 +178,7 @@ k_conv_tc(const TIn* __restrict__ in, const TIn* __restrict__ bimg /*host-arrang
         const int slot = rp % g.S;
         if (rp >= g.S) mbar_wait(&empty[slot], ((rp / g.S) - 1) & 1);
         mbar_expect_tx(&full[slot], row_bytes * (uint32_t)nrows * CG);
-        const int pp = d0 + rp;  // padded plane index (pd == 1: plane d-1+kd+1; pd == 0: plane d)
+        const int pp = d0 + rp + PLANE0;  // padded plane index (pd == 1: plane d-1+kd+1; pd == 0: plane d)
 #pragma unroll 1
         for (int cg = 0; cg < CG; ++cg) {
           const TIn* src = in + cg * g.in_gs + pp * plane_elems + ((long long)h0 * g.Wp + w0) * 8;
@@ -176,12 +188,38 @@ k_conv_tc(const TIn* __restrict__ in, const TIn* __restrict__ bimg /*host-arrang
         }
       }
     }
-  } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
+  } else if (warp == 1 || warp >= 6) {
+    // ===================== MMA issuers (warp-uniform; one elected lane issues) =====================
+    const int issuer = warp == 1 ? 0 : warp - 5;   // 0,1,2
+    const bool leader = lane == 0;
+    {
+      // Descriptor deltas are loop invariants: a K=16 step b of any plane / chunk reads A at (slot + chunk + a_off[b])
+      // and B at block (kd*NBLK + b).  Everything below is in the descriptor's 16-byte units.
+      uint32_t a_off[NBLK], a_lbo[NBLK];
+#pragma unroll
+      for (int b = 0; b < NBLK; ++b) {
+        if constexpr (MODE == 1) {
+          const int t = b / (CIN / 16), j = b % (CIN / 16);
+          a_off[b] = (uint32_t)(2 * j) * (cg_bytes >> 4) + (uint32_t)((1 + t / 2) * g.P + (1 + t % 2));
+          a_lbo[b] = cg_bytes >> 4;
+        } else if constexpr (CIN >= 16) {
+          const int t = b / (CIN / 16), j = b % (CIN / 16);
+          a_off[b] = (uint32_t)(2 * j) * (cg_bytes >> 4) + (uint32_t)((t / 3) * g.P + (t % 3));
+          a_lbo[b] = cg_bytes >> 4;
+        } else {
+          // taps are paired (0,1)(2,3)(4,5)(6,7)(7*,8): the 5th block re-reads tap 7 against zero weights so that no
+          // K slice ever touches shared memory outside the copied tile
+          const int t0 = b < 4 ? 2 * b : 7, t1 = b < 4 ? 2 * b + 1 : 8;
+          const int o0 = (t0 / 3) * g.P + (t0 % 3), o1 = (t1 / 3) * g.P + (t1 % 3);
+          a_off[b] = (uint32_t)o0;
+          a_lbo[b] = (uint32_t)(o1 - o0);
+        }
+      }
+      const uint32_t desc_hi = (128u >> 4) | (1u << 14);            // SBO = 128 B, version = 1 (bits 46..47 of the desc)
+      const uint32_t sB16 = (smem_u32(sB) & 0x3FFFFu) >> 4, sA16 = (smem_u32(sA) & 0x3FFFFu) >> 4;
+      const uint32_t b_lo_base = sB16 | ((uint32_t)(NPAD * 16 >> 4) << 16);
       mbar_wait(b_full, 0);
       int next_wait = 0;
-      const uint32_t sB_addr = smem_u32(sB), sA_addr = smem_u32(sA);
       for (int od = 0; od < ndo; ++od) {
         const int buf = od & 1;
         if (od >= 2) mbar_wait(&acc_empty[buf], ((od >> 1) - 1) & 1);
@@ -190,37 +228,27 @@ k_conv_tc(const TIn* __restrict__ in, const TIn* __restrict__ bimg /*host-arrang
           ++next_wait;
         }
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        for (int c = 0; c < g.nch; ++c) {
+        uint32_t slot16[KD];
+#pragma unroll
+        for (int kd = 0; kd < KD; ++kd) slot16[kd] = sA16 + (uint32_t)((od + kd) % g.S) * (slot_bytes >> 4);
+        for (int c = issuer; c < g.nch; c += kMmaWarps) {
           const uint32_t d_tmem = tmem_base + (uint32_t)(buf * acc_cols + c * NPAD);
-          uint32_t accum = 0;
-#pragma unroll 1
+#pragma unroll
           for (int kd = 0; kd < KD; ++kd) {
-            const uint32_t a_slot = sA_addr + (uint32_t)((od + kd) % g.S) * slot_bytes + (uint32_t)c * 128u * 16u;
-#pragma unroll 1
+            const uint32_t a16 = slot16[kd] + (uint32_t)c * 128u;
+#pragma unroll
             for (int b = 0; b < NBLK; ++b) {
-              uint32_t a_start, a_lbo;
-              if constexpr (CIN >= 16) {
-                const int t = b / (CIN / 16), j = b % (CIN / 16);
-                a_start = a_slot + (uint32_t)(2 * j) * cg_bytes + (uint32_t)((t / 3) * g.P + (t % 3)) * 16u;
-                a_lbo = cg_bytes;
-              } else {
-                // taps are paired (0,1)(2,3)(4,5)(6,7)(7*,8): the 5th block re-reads tap 7 against zero weights so
-                // that no K slice ever touches shared memory outside the copied tile
-                const int t0 = b < 4 ? 2 * b : 7, t1 = b < 4 ? 2 * b + 1 : 8;
-                const int o0 = (t0 / 3) * g.P + (t0 % 3);
-                const int o1 = (t1 / 3) * g.P + (t1 % 3);
-                a_start = a_slot + (uint32_t)o0 * 16u;
-                a_lbo = (uint32_t)(o1 - o0) * 16u;
-              }
-              const uint64_t ad = make_desc(a_start, a_lbo, 128u);
-              const uint64_t bd = make_desc(sB_addr + (uint32_t)((kd * NBLK + b) * NPAD * 32), (uint32_t)NPAD * 16u, 128u);
-              mma_f16(d_tmem, ad, bd, IDESC, accum);
-              accum = 1;
+              const uint64_t ad = ((uint64_t)desc_hi << 32) | (uint64_t)((a16 + a_off[b]) | (a_lbo[b] << 16));
+              const uint64_t bd = ((uint64_t)desc_hi << 32) | (uint64_t)(b_lo_base + (uint32_t)((kd * NBLK + b) * NPAD * 2));
+              if (leader) mma_f16(d_tmem, ad, bd, IDESC, (kd | b) != 0 ? 1u : 0u);
             }
           }
         }
-        mma_commit(&acc_full[buf]);           // accumulators of plane od complete -> epilogue
-        mma_commit(&empty[od % g.S]);         // oldest input plane no longer needed -> producer may refill
+        if (leader) {
+          mma_commit(&acc_full[buf]);         // this issuer's share of plane od complete -> epilogue (3 arrivals)
+          mma_commit(&empty[od % g.S]);       // oldest input plane no longer needed by this issuer -> producer may refill
+        }
+        __syncwarp();
       }
     }
   } else {
@@ -232,39 +260,74 @@ k_conv_tc(const TIn* __restrict__ in, const TIn* __restrict__ bimg /*host-arrang
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const int d = d0 + od;
       for (int c = 0; c < g.nch; ++c) {
-        uint32_t v[16];
-        float acc[NPAD];
-#pragma unroll
-        for (int n0 = 0; n0 < NPAD; n0 += 16) {
-          tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * acc_cols + c * NPAD + n0), v);
-#pragma unroll
-          for (int i = 0; i < 16; ++i) acc[n0 + i] = __uint_as_float(v[i]);
-        }
         const int l = c * 128 + q * 32 + lane;
         const int hh = l / g.P, ww = l - hh * g.P;
         const int h = h0 + hh, w = w0 + ww;
-        if (hh < g.R && ww < g.TW && h < g.H && w < g.W) {
-          if constexpr (OUT_PLAIN) {
-            plain_out[((long long)d * g.H + h) * g.W + w] = acc[0] + (bias ? bias[0] : 0.f);
-          } else {
-            const long long pos = ((((long long)(d + g.pd)) * g.Hp + (h + 1)) * g.Wp + (w + 1)) * 8;
+        const bool valid = hh < g.R && ww < g.TW && h < g.H && w < g.W;
+        const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * acc_cols + c * NPAD);
+        if constexpr (MODE == 1) {
+          // N = 8 parity classes x COUT: class (pd,ph,pw) of input position (d,h,w) is output (2d+pd, 2h+ph, 2w+pw)
+          constexpr int COUT = NPAD / 8;
+#pragma unroll 1
+          for (int n0 = 0; n0 < NPAD; n0 += 16) {
+            uint32_t v[16];
+            tmem_ld16(t_row + (uint32_t)n0, v);
+            if (valid) {
 #pragma unroll
-            for (int c0 = 0; c0 < NPAD; c0 += 8) {
-              if (c0 < g.cout) {
+              for (int k0 = 0; k0 < 16; k0 += 8) {
+                const int n = n0 + k0;
+                const int cls = n / COUT, co = n % COUT;
+                const int od2 = 2 * d + (cls >> 2), oh2 = 2 * h + ((cls >> 1) & 1), ow2 = 2 * w + (cls & 1);
+                const long long pos = ((((long long)(od2 + g.opd)) * g.oHp + (oh2 + 1)) * g.oWp + (ow2 + 1)) * 8;
                 float o8[8];
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
-                  float x = acc[c0 + i] + (bias ? bias[c0 + i] : 0.f);
+                  float x = __uint_as_float(v[k0 + i]) + (bias ? bias[co + i] : 0.f);
                   if (g.relu) x = fmaxf(x, 0.f);
                   o8[i] = x;
                 }
                 if (g.has_res) {
                   float r8[8];
-                  load_vec<TOut, 8>(res + pos + (c0 >> 3) * g.res_gs, r8);
+                  load_vec<TOut, 8>(res + pos + (co >> 3) * g.res_gs, r8);
 #pragma unroll
                   for (int i = 0; i < 8; ++i) o8[i] += r8[i];
                 }
-                store_vec<TOut, 8>(out + pos + (c0 >> 3) * g.out_gs, o8);
+                store_vec<TOut, 8>(out + pos + (co >> 3) * g.out_gs, o8);
+              }
+            }
+          }
+        } else {
+          uint32_t v[16];
+          float acc[NPAD];
+#pragma unroll
+          for (int n0 = 0; n0 < NPAD; n0 += 16) {
+            tmem_ld16(t_row + (uint32_t)n0, v);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) acc[n0 + i] = __uint_as_float(v[i]);
+          }
+          if (valid) {
+            if constexpr (OUT_PLAIN) {
+              plain_out[((long long)d * g.H + h) * g.W + w] = acc[0] + (bias ? bias[0] : 0.f);
+            } else {
+              const long long pos = ((((long long)(d + g.pd)) * g.Hp + (h + 1)) * g.Wp + (w + 1)) * 8;
+#pragma unroll
+              for (int c0 = 0; c0 < NPAD; c0 += 8) {
+                if (c0 < g.cout) {
+                  float o8[8];
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) {
+                    float x = acc[c0 + i] + (bias ? bias[c0 + i] : 0.f);
+                    if (g.relu) x = fmaxf(x, 0.f);
+                    o8[i] = x;
+                  }
+                  if (g.has_res) {
+                    float r8[8];
+                    load_vec<TOut, 8>(res + pos + (c0 >> 3) * g.res_gs, r8);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) o8[i] += r8[i];
+                  }
+                  store_vec<TOut, 8>(out + pos + (c0 >> 3) * g.out_gs, o8);
+                }
               }
             }
           }
@@ -308,46 +371,88 @@ inline void build_b_image(const float* w, int cin, int cout, int npad, int kd_n,
           }
 }
 
+// Transposed conv (k3 s2 p1 op1) B image: w is the gather-form folded weight [tap27][cin][cout] (tap index = kernel index
+// of the ConvTranspose3d).  Per axis, output parity p and input offset t (0 = same index, 1 = next index) select the
+// kernel index: p=0:t=0 -> k=1 ; p=1:t=0 -> k=2, t=1 -> k=0 ; (p=0,t=1) contributes nothing.
+template <typename T, int CIN>
+inline void build_b_image_deconv(const float* w, int cin, int cout, std::vector<T>& img, T (*cvt)(float)) {
+  constexpr int NBLK = blocks_per_kd<CIN, 1>();
+  const int npad = 8 * cout;
+  img.assign((size_t)2 * NBLK * npad * 16, cvt(0.f));
+  auto kidx = [](int p, int t) { return p == 0 ? (t == 0 ? 1 : -1) : (t == 0 ? 2 : 0); };
+  for (int td = 0; td < 2; ++td)
+    for (int b = 0; b < NBLK; ++b)
+      for (int half = 0; half < 2; ++half)
+        for (int cls = 0; cls < 8; ++cls)
+          for (int co = 0; co < cout; ++co)
+            for (int e = 0; e < 8; ++e) {
+              const int t = b / (CIN / 16), j = b % (CIN / 16);
+              const int ci = j * 16 + half * 8 + e;
+              const int th = t / 2, tw = t % 2;
+              const int kd = kidx(cls >> 2, td), kh = kidx((cls >> 1) & 1, th), kw = kidx(cls & 1, tw);
+              if (kd < 0 || kh < 0 || kw < 0 || ci >= cin) continue;
+              const int n = cls * cout + co;
+              const float val = w[((size_t)((kd * 3 + kh) * 3 + kw) * cin + ci) * cout + co];
+              img[(((size_t)(td * NBLK + b) * 2 + half) * (npad / 8) + n / 8) * 64 + (n % 8) * 8 + e] = cvt(val);
+            }
+}
+
 struct Plan {
   Geom g;
   int grid;
   size_t smem;
 };
 
-inline Plan make_plan(int cin, int npad, int kd, int D, int H, int W, int pd, size_t smem_limit = 200 * 1024) {
+inline Plan make_plan(int cin, int npad, int kd, int D, int H, int W, int pd, int mode = 0, size_t smem_limit = 225 * 1024) {
   Plan p{};
   Geom& g = p.g;
   g.D = D; g.H = H; g.W = W; g.Hp = H + 2; g.Wp = W + 2; g.pd = pd;
   const int cg = cin / 8;
-  const int nblk = cin >= 16 ? 9 * (cin / 16) : 5;
+  const int nblk = mode == 1 ? 4 * (cin / 16) : (cin >= 16 ? 9 * (cin / 16) : 5);
   const size_t bbytes = (((size_t)kd * nblk * npad * 32) + 127) / 128 * 128;
-  g.S = kd == 3 ? 4 : 2;
-  // choose TW (<= 320 so wide rows split), then the largest R that fits shared memory and TMEM (2*nch*npad <= 512)
-  int tiles_w = 1;
-  while ((W + tiles_w - 1) / tiles_w > 320) ++tiles_w;
-  g.TW = (W + tiles_w - 1) / tiles_w;
-  g.P = g.TW + 2;
-  int bestR = 0;
-  for (int R = 1; R <= 16 && R <= H; ++R) {
-    const int nch = (R * g.P + 127) / 128;
-    const int slot_pos = std::max((R + 2) * g.P, nch * 128 + 2 * g.P + 2) + 8;
-    const size_t smem = bbytes + (size_t)g.S * cg * slot_pos * 16 + 256;
-    if (smem <= smem_limit && 2 * nch * npad <= 512) bestR = R;
+  // Search (ring depth, tile width, tile rows, planes per tile) for the cheapest feasible tiling.
+  // cost = L2 bytes per useful output position (halo re-reads in h, w and d)
+  //        x MMA rows issued per useful position (pad columns, partial last chunk; weighted 1/4: MMA is not the limiter)
+  //        x wave quantisation on 148 SMs (one CTA per SM: time ~ ceil(T/148) tile-times for T tiles)
+  double best_cost = 1e30;
+  int bestR = 0, bestTW = 0, bestS = 0, bestDR = 0;
+  const int s_hi = kd == 3 ? 4 : 3, s_lo = kd == 3 ? 3 : 2;   // kd == 2 (deconv): 3 slots = 2 live + 1 prefetch
+  for (int S = s_hi; S >= s_lo; --S) {
+    for (int tiles_w = 1; tiles_w <= 20; ++tiles_w) {
+      const int TW = (W + tiles_w - 1) / tiles_w;
+      if (TW > 512) continue;
+      if (tiles_w > 1 && TW < 30) break;
+      const int tw_n = (W + TW - 1) / TW;
+      const int P = TW + 2;
+      for (int R = 1; R <= 32 && R <= H; ++R) {
+        const int nch = (R * P + 127) / 128;
+        const int slot_pos = std::max((R + 2) * P, nch * 128 + 2 * P + 2) + 8;
+        const size_t smem = bbytes + (size_t)S * cg * slot_pos * 16 + 256;
+        if (smem > smem_limit || 2 * nch * npad > 512) break;
+        const int th_n = (H + R - 1) / R;
+        for (int dsplit = 1; dsplit <= D; ++dsplit) {
+          const int DR = (D + dsplit - 1) / dsplit;
+          if (kd >= 2 && DR < 2 && D >= 2) break;
+          const int td_n = (D + DR - 1) / DR;
+          const double T = (double)tw_n * th_n * td_n;
+          const double amp = (double)(R + 2) / R * (double)P / TW * (kd == 3 ? (double)(DR + 2) / DR : (kd == 2 ? (double)(DR + 1) / DR : 1.0));
+          const double waste = (double)nch * 128 / ((double)R * TW);
+          const double quant = std::ceil(T / 148.0) / (T / 148.0);
+          const double tma = P * 16 >= 2048 ? 1.0 : 1.0 + 0.3 * (2048.0 - P * 16) / 2048.0;  // short bulk copies are inefficient
+          const double cost = amp * (0.75 + 0.25 * waste) * quant * tma * (S == s_hi ? 1.0 : 1.1);
+          if (cost < best_cost - 1e-9) { best_cost = cost; bestR = R; bestTW = TW; bestS = S; bestDR = DR; }
+          if (T > 4000) break;
+        }
+      }
+    }
+    if (bestR > 0 && S == s_hi) break;
   }
   TDM_CHECK(bestR > 0, "conv_tc: no tile fits shared memory");
-  g.R = bestR;
+  g.S = bestS; g.R = bestR; g.TW = bestTW; g.P = bestTW + 2; g.DR = bestDR;
   g.nch = (g.R * g.P + 127) / 128;
   g.slot_pos = std::max((g.R + 2) * g.P, g.nch * 128 + 2 * g.P + 2) + 8;
-  g.tiles_w = tiles_w;
+  g.tiles_w = (W + g.TW - 1) / g.TW;
   g.tiles_h = (H + g.R - 1) / g.R;
-  // planes per tile: keep >= ~2 waves of CTAs on 148 SMs when the tensor allows it
-  g.DR = D;
-  if (kd == 3) {
-    while (g.DR > 4 && (long long)g.tiles_w * g.tiles_h * ((D + g.DR - 1) / g.DR) < 296) g.DR = (g.DR + 1) / 2;
-  } else {
-    g.DR = 1;
-    while (g.DR < D && (long long)g.tiles_w * g.tiles_h * ((D + g.DR) / (g.DR + 1)) >= 592) ++g.DR;
-  }
   g.tiles_d = (D + g.DR - 1) / g.DR;
   p.grid = g.tiles_w * g.tiles_h * g.tiles_d;
   p.smem = bbytes + (size_t)g.S * cg * g.slot_pos * 16 + 256;

@@ -20,6 +20,7 @@
 
 #include "mvsnet.h"
 #include "mvsnet_kernels.cuh"
+#include "conv_tc.cuh"
 #include "weights.h"
 
 namespace tdm {
@@ -83,6 +84,11 @@ struct DevConv {
   bool transposed = false;
   float* w = nullptr;
   float* bias = nullptr;
+  // tcgen05 path (conv_tc.cuh): weights pre-arranged as the canonical K-major B image in the input's 16-bit type
+  void* bimg = nullptr;
+  int npad = 0;
+  bool tc_ok = false;
+  bool tc_deconv = false;  // transposed conv evaluated as a GEMM over the input grid (N = 8 parity classes x cout)
 };
 
 struct LaunchRec {
@@ -120,7 +126,7 @@ class MvsnetEngine final : public MvsnetIface {
     if (worker_.joinable()) worker_.join();
     cudaSetDevice(device_);
     free_plan();
-    for (auto& kv : convs_) { cudaFree(kv.second.w); cudaFree(kv.second.bias); }
+    for (auto& kv : convs_) { cudaFree(kv.second.w); cudaFree(kv.second.bias); cudaFree(kv.second.bimg); }
     if (select_state_) cudaFree(select_state_);
     if (stream_) cudaStreamDestroy(stream_);
   }
@@ -128,6 +134,7 @@ class MvsnetEngine final : public MvsnetIface {
   void set_option(const std::string& key, int value) override {
     if (key == "filter_all_stages") filter_all_ = value != 0;
     else if (key == "keep_intermediates") keep_ = value != 0;
+    else if (key == "use_tc") use_tc_ = value != 0;
     else throw Error("unknown option " + key);
   }
 
@@ -269,8 +276,43 @@ class MvsnetEngine final : public MvsnetIface {
       TDM_CUDA(cudaMalloc(&dc.bias, fc.bias.size() * 4));
       TDM_CUDA(cudaMemcpy(dc.bias, fc.bias.data(), fc.bias.size() * 4, cudaMemcpyHostToDevice));
     }
+    if constexpr (sizeof(TA) == 2) {
+      const bool vol_in = key.size() > 6 && key.compare(key.size() - 6, 6, ".conv0") == 0 && key[0] == 's';
+      const bool shape_ok = !fc.transposed && fc.kh == 3 && fc.kw == 3 && (fc.kd == 1 || fc.kd == 3) &&
+                            (fc.cin == 8 || fc.cin == 16 || fc.cin == 32) &&
+                            (fc.cout == 1 || fc.cout == 8 || fc.cout == 16 || fc.cout == 32);
+      if (shape_ok) {
+        dc.npad = fc.cout < 16 ? 16 : fc.cout;
+        dc.tc_ok = true;
+        if (vol_in) upload_bimg<TV>(fc, dc); else upload_bimg<TA>(fc, dc);
+      }
+      const bool deconv_ok = fc.transposed && fc.kd == 3 && fc.kh == 3 && fc.kw == 3 &&
+                             ((fc.cin == 16 && fc.cout == 8) || (fc.cin == 32 && fc.cout == 16));
+      if (deconv_ok) {
+        dc.npad = 8 * fc.cout;
+        dc.tc_ok = dc.tc_deconv = true;
+        std::vector<TA> img;
+        auto cvt = [](float v) -> TA { return from_host<TA>(v); };
+        if (fc.cin == 16) tc::build_b_image_deconv<TA, 16>(fc.w.data(), fc.cin, fc.cout, img, +cvt);
+        else tc::build_b_image_deconv<TA, 32>(fc.w.data(), fc.cin, fc.cout, img, +cvt);
+        TDM_CUDA(cudaMalloc(&dc.bimg, img.size() * sizeof(TA)));
+        TDM_CUDA(cudaMemcpy(dc.bimg, img.data(), img.size() * sizeof(TA), cudaMemcpyHostToDevice));
+      }
+    }
     convs_[key] = dc;
   }
+
+  template <typename TB>
+  void upload_bimg(const FoldedConv& fc, DevConv& dc) {
+    std::vector<TB> img;
+    auto cvt = [](float v) -> TB { return from_host<TB>(v); };
+    if (fc.cin == 8) tc::build_b_image<TB, 8>(fc.w.data(), fc.cin, fc.cout, dc.npad, fc.kd, img, +cvt);
+    else if (fc.cin == 16) tc::build_b_image<TB, 16>(fc.w.data(), fc.cin, fc.cout, dc.npad, fc.kd, img, +cvt);
+    else tc::build_b_image<TB, 32>(fc.w.data(), fc.cin, fc.cout, dc.npad, fc.kd, img, +cvt);
+    TDM_CUDA(cudaMalloc(&dc.bimg, img.size() * sizeof(TB)));
+    TDM_CUDA(cudaMemcpy(dc.bimg, img.data(), img.size() * sizeof(TB), cudaMemcpyHostToDevice));
+  }
+  template <typename TB> static TB from_host(float v);
 
   void upload_weights() {
     const std::string f = "feature_net.";
@@ -424,6 +466,13 @@ class MvsnetEngine final : public MvsnetIface {
     if (!profiling_) return;
     cudaEventRecord(recs_.back().e1, stream_);
   }
+  void rec_cancel() {
+    --launch_count_;
+    if (!profiling_) return;
+    cudaEventDestroy(recs_.back().e0);
+    cudaEventDestroy(recs_.back().e1);
+    recs_.pop_back();
+  }
 
   template <typename TIn, typename TOut, int CIN, int COUT>
   void conv_inst(const DevBuf& in, const DevConv& c, const DevBuf* res, const DevBuf& out, const ConvGeom& g) {
@@ -433,7 +482,77 @@ class MvsnetEngine final : public MvsnetIface {
     P8<TOut> o{};
     float* plain = nullptr;
     if constexpr (COUT == 1) plain = (float*)out.p; else o = p8<TOut>(out);
+    if constexpr (COUT >= 16) {
+      if (npos < 128ll * 592) {  // too few positions to fill the chip: split the output channels over blockIdx.y
+        dim3 grid(cdiv(npos, 128), COUT / 8);
+        k_conv_direct<TIn, TOut, CIN, COUT, 8><<<grid, 128, 0, stream_>>>(p8<const TIn>(in), c.w, c.bias, r, o, plain, g);
+        return;
+      }
+    }
     k_conv_direct<TIn, TOut, CIN, COUT><<<cdiv(npos, 128), 128, 0, stream_>>>(p8<const TIn>(in), c.w, c.bias, r, o, plain, g);
+  }
+
+  template <typename TIn, typename TOut, int CIN, int NPAD, int KD, bool PLAIN, int MODE = 0>
+  void tc_inst(const DevBuf& in, const DevConv& c, const DevBuf* res, const DevBuf& out, bool relu) {
+    tc::Plan pl = tc::make_plan(CIN, NPAD, KD, in.D, in.H, in.W, in.pd, MODE);   // tiles live on the INPUT grid
+    tc::Geom& g = pl.g;
+    g.oHp = out.H + 2; g.oWp = out.W + 2; g.opd = out.pd;
+    const P8<const TIn> pi = p8<const TIn>(in);
+    g.in_gs = pi.gs;
+    g.relu = relu ? 1 : 0;
+    g.has_res = res ? 1 : 0;
+    g.cout = c.cout;
+    TOut* op = nullptr;
+    float* plain = nullptr;
+    const TOut* rp = nullptr;
+    if constexpr (PLAIN) {
+      plain = (float*)out.p;
+    } else {
+      const P8<TOut> po = p8<TOut>(out);
+      g.out_gs = po.gs;
+      op = po.p;
+      if (res) { const P8<const TOut> pr = p8<const TOut>(*res); g.res_gs = pr.gs; rp = pr.p; }
+    }
+    auto kern = tc::k_conv_tc<TIn, TOut, CIN, NPAD, KD, PLAIN, MODE>;
+    static bool attr_set = false;
+    if (!attr_set) {
+      TDM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      attr_set = true;
+    }
+    kern<<<pl.grid, tc::kThreads, pl.smem, stream_>>>(pi.p, (const TIn*)c.bimg, c.bias, rp, op, plain, g);
+  }
+
+  // returns true if the tcgen05 kernel was launched
+  bool conv_tc_dispatch(const DevBuf& bi, const DevConv& c, const DevBuf* rp, const DevBuf& bo, bool relu) {
+    if constexpr (sizeof(TA) != 2) {
+      return false;
+    } else {
+      const bool is3d = c.kd == 3;
+      if (is3d != (bi.pd == 1)) return false;
+      if (c.tc_deconv) {
+        if (bo.D != 2 * bi.D || bo.H != 2 * bi.H || bo.W != 2 * bi.W || bi.kind != 1) return false;
+        if (c.cin == 16) { tc_inst<TA, TA, 16, 64, 2, false, 1>(bi, c, rp, bo, relu); return true; }
+        if (c.cin == 32) { tc_inst<TA, TA, 32, 128, 2, false, 1>(bi, c, rp, bo, relu); return true; }
+        return false;
+      }
+#define TDM_TC(TI, CI, NP, KDV)                                                            \
+  if (c.cin == CI && c.npad == NP && c.kd == KDV) {                                        \
+    tc_inst<TI, TA, CI, NP, KDV, false>(bi, c, rp, bo, relu);                              \
+    return true;                                                                           \
+  }
+      if (bo.f32) {
+        if (c.cin == 8 && c.cout == 1 && c.kd == 3 && bi.kind == 1) { tc_inst<TA, TA, 8, 16, 3, true>(bi, c, nullptr, bo, false); return true; }
+        return false;
+      }
+      if (bi.kind == 2) {
+        TDM_TC(TV, 32, 16, 3) TDM_TC(TV, 16, 16, 3) TDM_TC(TV, 8, 16, 3)
+        return false;
+      }
+      TDM_TC(TA, 8, 16, 1) TDM_TC(TA, 16, 16, 1) TDM_TC(TA, 32, 32, 1) TDM_TC(TA, 32, 16, 1)
+      TDM_TC(TA, 16, 16, 3) TDM_TC(TA, 32, 32, 3)
+#undef TDM_TC
+      return false;
+    }
   }
 
   // stride s* per axis; 2-D convs pass the view axis as D with kd=1.
@@ -456,8 +575,17 @@ class MvsnetEngine final : public MvsnetIface {
     const double opos = (double)bo.D * bo.H * bo.W;
     const double macs = c.transposed ? (double)bi.D * bi.H * bi.W * taps * c.cin * c.cout : opos * taps * c.cin * c.cout;
     const double bytes = (double)bi.alg_bytes + (double)bo.alg_bytes + (res_mode ? (double)bufs_.at(res).alg_bytes : 0.0);
-    rec_begin(wkey, bytes, 2.0 * macs);
     const DevBuf* rp = res_mode ? &bufs_.at(res) : nullptr;
+    if (use_tc_ && c.tc_ok && res_mode != 2 && (c.tc_deconv ? (sd == 2 && sh == 2 && sw == 2) : (sd == 1 && sh == 1 && sw == 1))) {
+      rec_begin(wkey + "[tc]", bytes, 2.0 * macs);
+      if (conv_tc_dispatch(bi, c, rp, bo, relu)) {
+        TDM_CUDA(cudaGetLastError());
+        rec_end();
+        return;
+      }
+      rec_cancel();
+    }
+    rec_begin(wkey, bytes, 2.0 * macs);
 #define TDM_CONV_CASE(CI, CO)                                                        \
   if (c.cin == CI && c.cout == CO) {                                                 \
     conv_inst<TA, TA, CI, CO>(bi, c, rp, bo, g);                                     \
@@ -681,7 +809,7 @@ class MvsnetEngine final : public MvsnetIface {
   float c2w_[kMaxSrc + 1][16];
   float K_[27];
   float dmin_ = 0, dmax_ = 0, discard_ = 0;
-  bool filter_all_ = false, keep_ = true;
+  bool filter_all_ = false, keep_ = true, use_tc_ = false;
   bool profiling_ = false;
   int launch_count_ = 0, launches_per_forward_ = 0;
   std::vector<LaunchRec> recs_;
@@ -692,6 +820,11 @@ class MvsnetEngine final : public MvsnetIface {
   bool busy_ = false, started_ = false, stop_ = false, has_result_ = false, have_inputs_ = false;
   std::string worker_error_;
 };
+
+template <> template <> float MvsnetEngine<float, float>::from_host<float>(float v) { return v; }
+template <> template <> __half MvsnetEngine<__half, __nv_bfloat16>::from_host<__half>(float v) { return __float2half_rn(v); }
+template <> template <> __nv_bfloat16 MvsnetEngine<__half, __nv_bfloat16>::from_host<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+template <> template <> __nv_bfloat16 MvsnetEngine<__nv_bfloat16, __nv_bfloat16>::from_host<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
 
 MvsnetIface* make_mvsnet(const std::string& path, int precision, int device) {
   int n = 0;

@@ -70,14 +70,17 @@ struct ConvGeom {
                    // nearest-neighbour x2 up-sampling (h,w) of a half-resolution tensor (FPN top-down)
 };
 
-template <typename TIn, typename TOut, int CIN, int COUT>
+// COUT_T output channels per thread (COUT_T == COUT: one thread owns a position; COUT_T == 8: blockIdx.y selects the
+// 8-channel group, used for the small low-resolution layers where positions alone cannot fill 148 SMs).
+template <typename TIn, typename TOut, int CIN, int COUT, int COUT_T = COUT>
 __global__ void __launch_bounds__(128)
 k_conv_direct(const P8<const TIn> in, const float* __restrict__ wgt /*[taps][CIN][COUT]*/,
               const float* __restrict__ bias /*[COUT] or null*/, const P8<const TOut> res,
               const P8<TOut> out, float* __restrict__ plain_out /*COUT==1: fp32 [D][H][W]*/, ConvGeom g) {
-  constexpr int SLICE = CIN * COUT;
+  constexpr int SLICE = CIN * COUT_T;
   constexpr int TAPS_PER_STAGE = (SLICE >= 4096) ? 1 : (4096 / SLICE);
   __shared__ __align__(16) float ws[TAPS_PER_STAGE * SLICE];
+  const int co0 = blockIdx.y * COUT_T;
 
   const long long npos = (long long)g.Do * g.Ho * g.Wo;
   const long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x;
@@ -89,15 +92,20 @@ k_conv_direct(const P8<const TIn> in, const float* __restrict__ wgt /*[taps][CIN
     oh = (int)(t % g.Ho);
     od = (int)(t / g.Ho);
   }
-  float acc[COUT];
+  float acc[COUT_T];
 #pragma unroll
-  for (int c = 0; c < COUT; ++c) acc[c] = 0.f;
+  for (int c = 0; c < COUT_T; ++c) acc[c] = 0.f;
 
   const int ntaps = g.kd * g.kh * g.kw;
   for (int t0 = 0; t0 < ntaps; t0 += TAPS_PER_STAGE) {
     const int nt = min(TAPS_PER_STAGE, ntaps - t0);
     __syncthreads();
-    for (int i = threadIdx.x; i < nt * SLICE; i += blockDim.x) ws[i] = wgt[(long long)t0 * SLICE + i];
+    if constexpr (COUT_T == COUT) {
+      for (int i = threadIdx.x; i < nt * SLICE; i += blockDim.x) ws[i] = wgt[(long long)t0 * SLICE + i];
+    } else {
+      for (int i = threadIdx.x; i < nt * SLICE; i += blockDim.x)
+        ws[i] = wgt[((long long)t0 * CIN + i / COUT_T) * COUT + co0 + (i % COUT_T)];
+    }
     __syncthreads();
     if (!active) continue;
     for (int tt = 0; tt < nt; ++tt) {
@@ -128,17 +136,17 @@ k_conv_direct(const P8<const TIn> in, const float* __restrict__ wgt /*[taps][CIN
         load_vec<TIn, CH>(ip + (c0 >> 3) * in.gs, x);
 #pragma unroll
         for (int ci = 0; ci < CH; ++ci) {
-          const float* wr = wt + (c0 + ci) * COUT;
+          const float* wr = wt + (c0 + ci) * COUT_T;
 #pragma unroll
-          for (int co = 0; co < COUT; ++co) acc[co] = fmaf(x[ci], wr[co], acc[co]);
+          for (int co = 0; co < COUT_T; ++co) acc[co] = fmaf(x[ci], wr[co], acc[co]);
         }
       }
     }
   }
   if (!active) return;
 #pragma unroll
-  for (int c = 0; c < COUT; ++c) {
-    float v = acc[c] + (bias ? bias[c] : 0.f);
+  for (int c = 0; c < COUT_T; ++c) {
+    float v = acc[c] + (bias ? bias[co0 + c] : 0.f);
     if (g.relu) v = fmaxf(v, 0.f);
     acc[c] = v;
   }
@@ -148,20 +156,20 @@ k_conv_direct(const P8<const TIn> in, const float* __restrict__ wgt /*[taps][CIN
     if (g.res_mode != 0) {
       const long long rp = g.res_mode == 1 ? res.pos(od, oh, ow) : res.pos(od, oh >> 1, ow >> 1);
 #pragma unroll
-      for (int c0 = 0; c0 < COUT; c0 += 8) {
+      for (int c0 = 0; c0 < COUT_T; c0 += 8) {
         float r[8];
-        load_vec<TOut, 8>(res.p + rp + (c0 >> 3) * res.gs, r);
+        load_vec<TOut, 8>(res.p + rp + ((co0 + c0) >> 3) * res.gs, r);
 #pragma unroll
         for (int c = 0; c < 8; ++c) acc[c0 + c] += r[c];
       }
     }
     const long long op = out.pos(od, oh, ow);
 #pragma unroll
-    for (int c0 = 0; c0 < COUT; c0 += 8) {
+    for (int c0 = 0; c0 < COUT_T; c0 += 8) {
       float o8[8];
 #pragma unroll
       for (int c = 0; c < 8; ++c) o8[c] = acc[c0 + c];
-      store_vec<TOut, 8>(out.p + op + (c0 >> 3) * out.gs, o8);
+      store_vec<TOut, 8>(out.p + op + ((co0 + c0) >> 3) * out.gs, o8);
     }
   }
 }

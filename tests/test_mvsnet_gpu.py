@@ -144,3 +144,50 @@ def test_cpp_shims_known_answer(tmp_path):
     r = subprocess.run([exe, default_weights("abl04_fewer_depth_planes"), binf], capture_output=True, text=True, timeout=300)
     print(r.stdout[-1500:], r.stderr[-500:])
     assert r.returncode == 0 and "test_dr_mvsnet: PASS" in r.stdout
+
+
+def _run_opts(g, weights, precision, **opts):
+    V, H, W, bgrs, c2ws, Ks = _inputs(g)
+    m = DrMvsnet(default_weights(weights), precision=precision)
+    for k, v in opts.items():
+        m.set_option(k, v)
+    m.CallAsyncStageK(H, W, V, int(g["ref_index"]), bgrs, Ks, c2ws, float(g["depth_min"]), float(g["depth_max"]),
+                      float(g["discard"]))
+    return m, m.GetResult()
+
+
+TC_LAYERS = ["f.c0_0", "f.c3", "f.c1_1", "f.c2", "f.c2_1", "f.c1", "feat2", "feat3"] + \
+    [f"s{s}.{n}" for s in (1, 2, 3) for n in ("c0", "c2", "c4", "x9", "x11", "logits")]
+
+
+@pytest.mark.parametrize("weights", ["abl03_view_aggregation", "abl04_fewer_depth_planes"])
+def test_tcgen05_convs_match_direct_kernels(golden_small, weights):
+    """Every layer computed by the tcgen05 implicit-GEMM kernel (conv_tc.cuh) against the direct kernel on the same
+    16-bit inputs (weights are additionally rounded to 16 bit on the tensor-core path)."""
+    md, od = _run_opts(golden_small, weights, "mixed16", use_tc=0)
+    mt, ot = _run_opts(golden_small, weights, "mixed16", use_tc=1)
+    prof = [r[0] for r in mt.profile()]
+    assert sum(n.endswith("[tc]") for n in prof) >= 20, prof
+    for name in TC_LAYERS:
+        a, b = mt.debug_tensor(name), md.debug_tensor(name)
+        scale = max(float(np.abs(b).max()), 1e-6)
+        e = np.abs(a - b)
+        print(f"{name:12s} max|d| {e.max():.3e} (scale {scale:.3e}) mean|d| {e.mean():.3e} mean|ref| {np.abs(b).mean():.3e}")
+        assert np.isfinite(a).all(), name
+        # layers are chained, so the tolerance covers the accumulated drift of up to ~12 fp16-weight layers; from
+        # stage 2 on the two engines also see slightly different hypotheses (they depend on the stage-1 depth), so
+        # isolated outliers at depth discontinuities are expected there and only robust statistics are compared
+        if name.startswith(("f.", "feat", "s1.")):
+            assert e.max() <= 6e-2 * scale, name
+        else:
+            assert np.quantile(e, 0.999) <= 6e-2 * scale, name
+        assert e.mean() <= 1e-2 * max(float(np.abs(b).mean()), 1e-6) + 1e-6, name
+    assert _absrel(od.depth_dense, ot.depth_dense) < 3e-4
+
+
+def test_tcgen05_benchmark_config_abs_rel(golden_full):
+    g = golden_full
+    m, out = _run_opts(g, "abl03_view_aggregation", "mixed16", use_tc=1)
+    ar = _absrel(g["abl03_stage3_depth_dense"], out.depth_dense)
+    print(f"C2 mixed16+tcgen05: Abs Rel {ar:.3e}")
+    assert ar < 5e-4
