@@ -114,16 +114,21 @@ constexpr int kMmaWarps = 3;
 template <int CIN, int MODE = 0> constexpr int blocks_per_kd() { return MODE == 1 ? 4 * (CIN / 16) : (CIN >= 16 ? 9 * (CIN / 16) : 5); }
 
 // AFMT: 0 = f16, 1 = bf16 (a_format/b_format of the instruction descriptor).  OUT_PLAIN: fp32 [D][H][W] (prob conv).
-template <typename TIn, typename TOut, int CIN, int NPAD, int KD, bool OUT_PLAIN, int MODE = 0>
+// HILO: the B image carries every weight twice, as W_hi = round16(W) in columns [0,NPAD) and W_lo = round16(W - W_hi)
+// in columns [NPAD, 2*NPAD); the MMA runs with N = 2*NPAD and the epilogue adds the two halves, which restores ~fp32
+// weight precision.  It is free here: at N <= 64 the instruction is bound by streaming the 4 KB A operand, not by N.
+template <typename TIn, typename TOut, int CIN, int NPAD, int KD, bool OUT_PLAIN, int MODE = 0, bool HILO = false>
 __global__ void __launch_bounds__(kThreads, 1)
 k_conv_tc(const TIn* __restrict__ in, const TIn* __restrict__ bimg /*host-arranged B image*/, const float* __restrict__ bias,
           const TOut* __restrict__ res, TOut* __restrict__ out, float* __restrict__ plain_out, const __grid_constant__ Geom g) {
   constexpr int CG = CIN / 8;
   constexpr int NBLK = blocks_per_kd<CIN, MODE>();
-  constexpr int B_BYTES = KD * NBLK * NPAD * 32;
+  constexpr int NMMA = HILO ? 2 * NPAD : NPAD;   // instruction N and TMEM columns per chunk
+  static_assert(!(HILO && MODE == 1), "hi/lo weights are only wired for the plain convolution epilogue");
+  constexpr int B_BYTES = KD * NBLK * NMMA * 32;
   constexpr int PLANE0 = MODE == 1 ? 1 : 0;   // deconv reads input planes d and d+1 (padded indices d+1, d+2)
   constexpr uint32_t AFMT = std::is_same<TIn, __nv_bfloat16>::value ? 1u : 0u;
-  constexpr uint32_t IDESC = (1u << 4) | (AFMT << 7) | (AFMT << 10) | ((uint32_t)(NPAD >> 3) << 17) | ((128u >> 4) << 24);
+  constexpr uint32_t IDESC = (1u << 4) | (AFMT << 7) | (AFMT << 10) | ((uint32_t)(NMMA >> 3) << 17) | ((128u >> 4) << 24);
 
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t* sB = smem;
@@ -138,6 +143,10 @@ k_conv_tc(const TIn* __restrict__ in, const TIn* __restrict__ bimg /*host-arrang
   uint64_t* b_full = bars + 20;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 21);
 
+  // N-slicing (blockIdx.y): wide outputs (CIN = 64 layers, whose full B image would not fit shared memory) are split into
+  // slices of NPAD columns, each with its own contiguous B image; slice ns produces output columns [ns*NPAD, (ns+1)*NPAD).
+  const int ns = blockIdx.y;
+  bimg += (size_t)ns * (B_BYTES / sizeof(TIn));
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // provably warp-uniform (uniform datapath)
   const int lane = threadIdx.x & 31;
   int tile = blockIdx.x;
@@ -147,7 +156,7 @@ k_conv_tc(const TIn* __restrict__ in, const TIn* __restrict__ bimg /*host-arrang
   const int w0 = tw * g.TW, h0 = th * g.R, d0 = td * g.DR;
   const int ndo = min(g.DR, g.D - d0);             // output planes of this tile
   const int nin = ndo + KD - 1;                    // input planes to stream
-  const uint32_t acc_cols = (uint32_t)g.nch * NPAD;  // TMEM columns per accumulator buffer
+  const uint32_t acc_cols = (uint32_t)g.nch * NMMA;  // TMEM columns per accumulator buffer
   uint32_t tmem_cols = 32;
   while (tmem_cols < 2 * acc_cols) tmem_cols <<= 1;
 
@@ -217,7 +226,7 @@ k_conv_tc(const TIn* __restrict__ in, const TIn* __restrict__ bimg /*host-arrang
       }
       const uint32_t desc_hi = (128u >> 4) | (1u << 14);            // SBO = 128 B, version = 1 (bits 46..47 of the desc)
       const uint32_t sB16 = (smem_u32(sB) & 0x3FFFFu) >> 4, sA16 = (smem_u32(sA) & 0x3FFFFu) >> 4;
-      const uint32_t b_lo_base = sB16 | ((uint32_t)(NPAD * 16 >> 4) << 16);
+      const uint32_t b_lo_base = sB16 | ((uint32_t)(NMMA * 16 >> 4) << 16);
       mbar_wait(b_full, 0);
       int next_wait = 0;
       for (int od = 0; od < ndo; ++od) {
@@ -232,14 +241,14 @@ k_conv_tc(const TIn* __restrict__ in, const TIn* __restrict__ bimg /*host-arrang
 #pragma unroll
         for (int kd = 0; kd < KD; ++kd) slot16[kd] = sA16 + (uint32_t)((od + kd) % g.S) * (slot_bytes >> 4);
         for (int c = issuer; c < g.nch; c += kMmaWarps) {
-          const uint32_t d_tmem = tmem_base + (uint32_t)(buf * acc_cols + c * NPAD);
+          const uint32_t d_tmem = tmem_base + (uint32_t)(buf * acc_cols + c * NMMA);
 #pragma unroll
           for (int kd = 0; kd < KD; ++kd) {
             const uint32_t a16 = slot16[kd] + (uint32_t)c * 128u;
 #pragma unroll
             for (int b = 0; b < NBLK; ++b) {
               const uint64_t ad = ((uint64_t)desc_hi << 32) | (uint64_t)((a16 + a_off[b]) | (a_lbo[b] << 16));
-              const uint64_t bd = ((uint64_t)desc_hi << 32) | (uint64_t)(b_lo_base + (uint32_t)((kd * NBLK + b) * NPAD * 2));
+              const uint64_t bd = ((uint64_t)desc_hi << 32) | (uint64_t)(b_lo_base + (uint32_t)((kd * NBLK + b) * NMMA * 2));
               if (leader) mma_f16(d_tmem, ad, bd, IDESC, (kd | b) != 0 ? 1u : 0u);
             }
           }
@@ -264,10 +273,10 @@ k_conv_tc(const TIn* __restrict__ in, const TIn* __restrict__ bimg /*host-arrang
         const int hh = l / g.P, ww = l - hh * g.P;
         const int h = h0 + hh, w = w0 + ww;
         const bool valid = hh < g.R && ww < g.TW && h < g.H && w < g.W;
-        const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * acc_cols + c * NPAD);
+        const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * acc_cols + c * NMMA);
         if constexpr (MODE == 1) {
           // N = 8 parity classes x COUT: class (pd,ph,pw) of input position (d,h,w) is output (2d+pd, 2h+ph, 2w+pw)
-          constexpr int COUT = NPAD / 8;
+          const int COUT = g.cout;
 #pragma unroll 1
           for (int n0 = 0; n0 < NPAD; n0 += 16) {
             uint32_t v[16];
@@ -275,7 +284,7 @@ k_conv_tc(const TIn* __restrict__ in, const TIn* __restrict__ bimg /*host-arrang
             if (valid) {
 #pragma unroll
               for (int k0 = 0; k0 < 16; k0 += 8) {
-                const int n = n0 + k0;
+                const int n = ns * NPAD + n0 + k0;
                 const int cls = n / COUT, co = n % COUT;
                 const int od2 = 2 * d + (cls >> 2), oh2 = 2 * h + ((cls >> 1) & 1), ow2 = 2 * w + (cls & 1);
                 const long long pos = ((((long long)(od2 + g.opd)) * g.oHp + (oh2 + 1)) * g.oWp + (ow2 + 1)) * 8;
@@ -304,6 +313,11 @@ k_conv_tc(const TIn* __restrict__ in, const TIn* __restrict__ bimg /*host-arrang
             tmem_ld16(t_row + (uint32_t)n0, v);
 #pragma unroll
             for (int i = 0; i < 16; ++i) acc[n0 + i] = __uint_as_float(v[i]);
+            if constexpr (HILO) {
+              tmem_ld16(t_row + (uint32_t)(NPAD + n0), v);
+#pragma unroll
+              for (int i = 0; i < 16; ++i) acc[n0 + i] += __uint_as_float(v[i]);
+            }
           }
           if (valid) {
             if constexpr (OUT_PLAIN) {
@@ -312,21 +326,22 @@ k_conv_tc(const TIn* __restrict__ in, const TIn* __restrict__ bimg /*host-arrang
               const long long pos = ((((long long)(d + g.pd)) * g.Hp + (h + 1)) * g.Wp + (w + 1)) * 8;
 #pragma unroll
               for (int c0 = 0; c0 < NPAD; c0 += 8) {
-                if (c0 < g.cout) {
+                const int co = ns * NPAD + c0;
+                if (co < g.cout) {
                   float o8[8];
 #pragma unroll
                   for (int i = 0; i < 8; ++i) {
-                    float x = acc[c0 + i] + (bias ? bias[c0 + i] : 0.f);
+                    float x = acc[c0 + i] + (bias ? bias[co + i] : 0.f);
                     if (g.relu) x = fmaxf(x, 0.f);
                     o8[i] = x;
                   }
                   if (g.has_res) {
                     float r8[8];
-                    load_vec<TOut, 8>(res + pos + (c0 >> 3) * g.res_gs, r8);
+                    load_vec<TOut, 8>(res + pos + (co >> 3) * g.res_gs, r8);
 #pragma unroll
                     for (int i = 0; i < 8; ++i) o8[i] += r8[i];
                   }
-                  store_vec<TOut, 8>(out + pos + (c0 >> 3) * g.out_gs, o8);
+                  store_vec<TOut, 8>(out + pos + (co >> 3) * g.out_gs, o8);
                 }
               }
             }
@@ -352,22 +367,34 @@ template <int CIN> inline size_t b_image_elems(int npad, int kd) { return (size_
 
 // w: folded fp32 weights [tap][cin][cout] (tap = (kd*3+kh)*3+kw).  Writes the canonical K-major no-swizzle image:
 // block(kd,b) = [k half (2)][n/8][n%8][8 k-elements]
+// nsplit > 1: the image holds nsplit consecutive slice images, slice s covering output channels [s*npad, (s+1)*npad).
 template <typename T, int CIN>
-inline void build_b_image(const float* w, int cin, int cout, int npad, int kd_n, std::vector<T>& img, T (*cvt)(float)) {
+inline void build_b_image(const float* w, int cin, int cout, int npad, int kd_n, std::vector<T>& img, T (*cvt)(float),
+                          int nsplit = 1, bool hilo = false, float (*back)(T) = nullptr) {
   constexpr int NBLK = blocks_per_kd<CIN>();
-  img.assign((size_t)kd_n * NBLK * npad * 16, cvt(0.f));
+  const int nmma = hilo ? 2 * npad : npad;
+  const size_t slice = (size_t)kd_n * NBLK * nmma * 16;
+  img.assign(slice * nsplit, cvt(0.f));
   for (int kd = 0; kd < kd_n; ++kd)
     for (int b = 0; b < NBLK; ++b)
       for (int half = 0; half < 2; ++half)
-        for (int n = 0; n < cout; ++n)
+        for (int nn = 0; nn < cout; ++nn)
           for (int e = 0; e < 8; ++e) {
+            const int n = nn % npad;
+            T* simg = img.data() + slice * (nn / npad);
             int tap9, ci;
             if (CIN >= 16) { tap9 = b / (CIN / 16); ci = (b % (CIN / 16)) * 16 + half * 8 + e; }
             else { tap9 = b < 4 ? 2 * b + half : (half == 0 ? -1 : 8); ci = e; }  // block 4 = (zero, tap 8)
             if (tap9 < 0 || tap9 >= 9 || ci >= cin) continue;
             const int tap = kd * 9 + tap9;
-            const float val = w[((size_t)tap * cin + ci) * cout + n];
-            img[(((size_t)(kd * NBLK + b) * 2 + half) * (npad / 8) + n / 8) * 64 + (n % 8) * 8 + e] = cvt(val);
+            const float val = w[((size_t)tap * cin + ci) * cout + nn];
+            T* blk = simg + ((size_t)(kd * NBLK + b) * 2 + half) * (nmma / 8) * 64;
+            const T hi = cvt(val);
+            blk[(n / 8) * 64 + (n % 8) * 8 + e] = hi;
+            if (hilo) {
+              const int n2 = npad + n;
+              blk[(n2 / 8) * 64 + (n2 % 8) * 8 + e] = cvt(val - back(hi));
+            }
           }
 }
 
@@ -375,10 +402,11 @@ inline void build_b_image(const float* w, int cin, int cout, int npad, int kd_n,
 // of the ConvTranspose3d).  Per axis, output parity p and input offset t (0 = same index, 1 = next index) select the
 // kernel index: p=0:t=0 -> k=1 ; p=1:t=0 -> k=2, t=1 -> k=0 ; (p=0,t=1) contributes nothing.
 template <typename T, int CIN>
-inline void build_b_image_deconv(const float* w, int cin, int cout, std::vector<T>& img, T (*cvt)(float)) {
+inline void build_b_image_deconv(const float* w, int cin, int cout, std::vector<T>& img, T (*cvt)(float), int nsplit = 1) {
   constexpr int NBLK = blocks_per_kd<CIN, 1>();
-  const int npad = 8 * cout;
-  img.assign((size_t)2 * NBLK * npad * 16, cvt(0.f));
+  const int npad = 8 * cout / nsplit;
+  const size_t slice = (size_t)2 * NBLK * npad * 16;
+  img.assign(slice * nsplit, cvt(0.f));
   auto kidx = [](int p, int t) { return p == 0 ? (t == 0 ? 1 : -1) : (t == 0 ? 2 : 0); };
   for (int td = 0; td < 2; ++td)
     for (int b = 0; b < NBLK; ++b)
@@ -391,9 +419,10 @@ inline void build_b_image_deconv(const float* w, int cin, int cout, std::vector<
               const int th = t / 2, tw = t % 2;
               const int kd = kidx(cls >> 2, td), kh = kidx((cls >> 1) & 1, th), kw = kidx(cls & 1, tw);
               if (kd < 0 || kh < 0 || kw < 0 || ci >= cin) continue;
-              const int n = cls * cout + co;
+              const int nfull = cls * cout + co, n = nfull % npad;
+              T* simg = img.data() + slice * (nfull / npad);
               const float val = w[((size_t)((kd * 3 + kh) * 3 + kw) * cin + ci) * cout + co];
-              img[(((size_t)(td * NBLK + b) * 2 + half) * (npad / 8) + n / 8) * 64 + (n % 8) * 8 + e] = cvt(val);
+              simg[(((size_t)(td * NBLK + b) * 2 + half) * (npad / 8) + n / 8) * 64 + (n % 8) * 8 + e] = cvt(val);
             }
 }
 

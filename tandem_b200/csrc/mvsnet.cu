@@ -21,6 +21,7 @@
 #include "mvsnet.h"
 #include "mvsnet_kernels.cuh"
 #include "conv_tc.cuh"
+#include "conv_tc_s2.cuh"
 #include "weights.h"
 
 namespace tdm {
@@ -89,6 +90,11 @@ struct DevConv {
   int npad = 0;
   bool tc_ok = false;
   bool tc_deconv = false;  // transposed conv evaluated as a GEMM over the input grid (N = 8 parity classes x cout)
+  int nsplit = 1;          // N slices (blockIdx.y) for the 64-channel layers
+  bool hilo = false;       // weights carried as hi + lo 16-bit halves (N doubled), see conv_tc.cuh
+  bool tc_s2 = false;      // stride-2 conv on the tensor-map (strided TMA) kernel, conv_tc_s2.cuh
+  void* bimg_s2 = nullptr;
+  int npad_s2 = 0, nsplit_s2 = 1;
 };
 
 struct LaunchRec {
@@ -126,7 +132,7 @@ class MvsnetEngine final : public MvsnetIface {
     if (worker_.joinable()) worker_.join();
     cudaSetDevice(device_);
     free_plan();
-    for (auto& kv : convs_) { cudaFree(kv.second.w); cudaFree(kv.second.bias); cudaFree(kv.second.bimg); }
+    for (auto& kv : convs_) { cudaFree(kv.second.w); cudaFree(kv.second.bias); cudaFree(kv.second.bimg); cudaFree(kv.second.bimg_s2); }
     if (select_state_) cudaFree(select_state_);
     if (stream_) cudaStreamDestroy(stream_);
   }
@@ -279,24 +285,49 @@ class MvsnetEngine final : public MvsnetIface {
     if constexpr (sizeof(TA) == 2) {
       const bool vol_in = key.size() > 6 && key.compare(key.size() - 6, 6, ".conv0") == 0 && key[0] == 's';
       const bool shape_ok = !fc.transposed && fc.kh == 3 && fc.kw == 3 && (fc.kd == 1 || fc.kd == 3) &&
-                            (fc.cin == 8 || fc.cin == 16 || fc.cin == 32) &&
-                            (fc.cout == 1 || fc.cout == 8 || fc.cout == 16 || fc.cout == 32);
+                            (((fc.cin == 8 || fc.cin == 16 || fc.cin == 32) &&
+                              (fc.cout == 1 || fc.cout == 8 || fc.cout == 16 || fc.cout == 32)) ||
+                             (fc.cin == 64 && fc.cout == 64 && fc.kd == 3));
       if (shape_ok) {
-        dc.npad = fc.cout < 16 ? 16 : fc.cout;
+        dc.npad = fc.cout < 16 ? 16 : (fc.cin == 64 ? 32 : fc.cout);
+        dc.nsplit = fc.cin == 64 ? 2 : 1;
+        dc.hilo = dc.npad <= 32 && fc.cin <= 32 && !(fc.kd == 3 && fc.cin == 32 && fc.cout == 32);
         dc.tc_ok = true;
         if (vol_in) upload_bimg<TV>(fc, dc); else upload_bimg<TA>(fc, dc);
       }
       const bool deconv_ok = fc.transposed && fc.kd == 3 && fc.kh == 3 && fc.kw == 3 &&
-                             ((fc.cin == 16 && fc.cout == 8) || (fc.cin == 32 && fc.cout == 16));
+                             ((fc.cin == 16 && fc.cout == 8) || (fc.cin == 32 && fc.cout == 16) || (fc.cin == 64 && fc.cout == 32));
       if (deconv_ok) {
-        dc.npad = 8 * fc.cout;
+        dc.nsplit = fc.cin == 64 ? 4 : 1;
+        dc.npad = 8 * fc.cout / dc.nsplit;
         dc.tc_ok = dc.tc_deconv = true;
         std::vector<TA> img;
         auto cvt = [](float v) -> TA { return from_host<TA>(v); };
         if (fc.cin == 16) tc::build_b_image_deconv<TA, 16>(fc.w.data(), fc.cin, fc.cout, img, +cvt);
-        else tc::build_b_image_deconv<TA, 32>(fc.w.data(), fc.cin, fc.cout, img, +cvt);
+        else if (fc.cin == 32) tc::build_b_image_deconv<TA, 32>(fc.w.data(), fc.cin, fc.cout, img, +cvt);
+        else tc::build_b_image_deconv<TA, 64>(fc.w.data(), fc.cin, fc.cout, img, +cvt, dc.nsplit);
         TDM_CUDA(cudaMalloc(&dc.bimg, img.size() * sizeof(TA)));
         TDM_CUDA(cudaMemcpy(dc.bimg, img.data(), img.size() * sizeof(TA), cudaMemcpyHostToDevice));
+      }
+    }
+    if constexpr (sizeof(TA) == 2) {
+      // stride-2 candidates (the stride itself is only known at launch): 3x3x3 convs of CostRegNet, 5x5 of FeatureNet
+      const bool s2_ok = !fc.transposed && fc.kh == fc.kw && (fc.kh == 3 || fc.kh == 5) &&
+                         ((fc.kd == 3 && fc.kh == 3 && ((fc.cin == 8 && fc.cout == 16) || (fc.cin == 16 && fc.cout == 32) ||
+                                                        (fc.cin == 32 && fc.cout == 64))) ||
+                          (fc.kd == 1 && fc.kh == 5 && ((fc.cin == 8 && fc.cout == 16) || (fc.cin == 16 && fc.cout == 32))));
+      if (s2_ok) {
+        dc.tc_s2 = true;
+        dc.nsplit_s2 = fc.cout == 64 ? 2 : 1;
+        dc.npad_s2 = fc.cout / dc.nsplit_s2;
+        std::vector<std::pair<int, int>> taps;
+        short off[tc::kMaxTaps + 1];
+        tc::s2_tap_table(fc.kh, 64, 4096, taps, off);   // only the ORDER matters for the B image
+        std::vector<TA> img;
+        auto cvt = [](float v) -> TA { return from_host<TA>(v); };
+        tc::build_b_image_s2<TA>(fc.w.data(), fc.cin, fc.cout, dc.npad_s2, fc.kd, fc.kh, taps, img, +cvt, dc.nsplit_s2);
+        TDM_CUDA(cudaMalloc(&dc.bimg_s2, img.size() * sizeof(TA)));
+        TDM_CUDA(cudaMemcpy(dc.bimg_s2, img.data(), img.size() * sizeof(TA), cudaMemcpyHostToDevice));
       }
     }
     convs_[key] = dc;
@@ -306,13 +337,16 @@ class MvsnetEngine final : public MvsnetIface {
   void upload_bimg(const FoldedConv& fc, DevConv& dc) {
     std::vector<TB> img;
     auto cvt = [](float v) -> TB { return from_host<TB>(v); };
-    if (fc.cin == 8) tc::build_b_image<TB, 8>(fc.w.data(), fc.cin, fc.cout, dc.npad, fc.kd, img, +cvt);
-    else if (fc.cin == 16) tc::build_b_image<TB, 16>(fc.w.data(), fc.cin, fc.cout, dc.npad, fc.kd, img, +cvt);
-    else tc::build_b_image<TB, 32>(fc.w.data(), fc.cin, fc.cout, dc.npad, fc.kd, img, +cvt);
+    auto back = [](TB v) -> float { return to_host<TB>(v); };
+    if (fc.cin == 8) tc::build_b_image<TB, 8>(fc.w.data(), fc.cin, fc.cout, dc.npad, fc.kd, img, +cvt, 1, dc.hilo, +back);
+    else if (fc.cin == 16) tc::build_b_image<TB, 16>(fc.w.data(), fc.cin, fc.cout, dc.npad, fc.kd, img, +cvt, 1, dc.hilo, +back);
+    else if (fc.cin == 32) tc::build_b_image<TB, 32>(fc.w.data(), fc.cin, fc.cout, dc.npad, fc.kd, img, +cvt, 1, dc.hilo, +back);
+    else tc::build_b_image<TB, 64>(fc.w.data(), fc.cin, fc.cout, dc.npad, fc.kd, img, +cvt, dc.nsplit);
     TDM_CUDA(cudaMalloc(&dc.bimg, img.size() * sizeof(TB)));
     TDM_CUDA(cudaMemcpy(dc.bimg, img.data(), img.size() * sizeof(TB), cudaMemcpyHostToDevice));
   }
   template <typename TB> static TB from_host(float v);
+  template <typename TB> static float to_host(TB v) { return (float)v; }
 
   void upload_weights() {
     const std::string f = "feature_net.";
@@ -395,6 +429,7 @@ class MvsnetEngine final : public MvsnetIface {
     return t;
   }
   void free_plan() {
+    s2_cache_.clear();
     for (auto& kv : bufs_) cudaFree(kv.second.p);
     bufs_.clear();
     if (h_bgr_) cudaFreeHost(h_bgr_);
@@ -492,9 +527,9 @@ class MvsnetEngine final : public MvsnetIface {
     k_conv_direct<TIn, TOut, CIN, COUT><<<cdiv(npos, 128), 128, 0, stream_>>>(p8<const TIn>(in), c.w, c.bias, r, o, plain, g);
   }
 
-  template <typename TIn, typename TOut, int CIN, int NPAD, int KD, bool PLAIN, int MODE = 0>
+  template <typename TIn, typename TOut, int CIN, int NPAD, int KD, bool PLAIN, int MODE = 0, bool HILO = false>
   void tc_inst(const DevBuf& in, const DevConv& c, const DevBuf* res, const DevBuf& out, bool relu) {
-    tc::Plan pl = tc::make_plan(CIN, NPAD, KD, in.D, in.H, in.W, in.pd, MODE);   // tiles live on the INPUT grid
+    tc::Plan pl = tc::make_plan(CIN, HILO ? 2 * NPAD : NPAD, KD, in.D, in.H, in.W, in.pd, MODE);   // tiles live on the INPUT grid
     tc::Geom& g = pl.g;
     g.oHp = out.H + 2; g.oWp = out.W + 2; g.opd = out.pd;
     const P8<const TIn> pi = p8<const TIn>(in);
@@ -513,13 +548,68 @@ class MvsnetEngine final : public MvsnetIface {
       op = po.p;
       if (res) { const P8<const TOut> pr = p8<const TOut>(*res); g.res_gs = pr.gs; rp = pr.p; }
     }
-    auto kern = tc::k_conv_tc<TIn, TOut, CIN, NPAD, KD, PLAIN, MODE>;
+    auto kern = tc::k_conv_tc<TIn, TOut, CIN, NPAD, KD, PLAIN, MODE, HILO>;
     static bool attr_set = false;
     if (!attr_set) {
       TDM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
       attr_set = true;
     }
-    kern<<<pl.grid, tc::kThreads, pl.smem, stream_>>>(pi.p, (const TIn*)c.bimg, c.bias, rp, op, plain, g);
+    kern<<<dim3(pl.grid, c.nsplit), tc::kThreads, pl.smem, stream_>>>(pi.p, (const TIn*)c.bimg, c.bias, rp, op, plain, g);
+  }
+
+  struct S2Cache { tc::PlanS2 plan; CUtensorMap tmap; };
+  std::map<std::string, S2Cache> s2_cache_;
+
+  template <int CIN, int NPAD, int KD, int KS>
+  void tc_s2_inst(const std::string& wkey, const DevBuf& in, const DevConv& c, const DevBuf& out, bool relu) {
+    auto it = s2_cache_.find(wkey);
+    if (it == s2_cache_.end()) {
+      S2Cache sc;
+      sc.plan = tc::make_plan_s2(CIN, NPAD, KD, KS, out.D, out.H, out.W);
+      tc::GeomS2& g = sc.plan.g;
+      const P8<TA> po = p8<TA>(out);
+      g.oHp = out.H + 2; g.oWp = out.W + 2; g.opd = out.pd; g.out_gs = po.gs;
+      g.ipd = in.pd; g.iDp = in.D + 2 * in.pd;
+      g.c0 = 1 - KS / 2;
+      g.relu = relu ? 1 : 0;
+      g.cout = c.cout;
+      std::vector<std::pair<int, int>> taps;
+      tc::s2_tap_table(KS, g.P, g.sub_pos, taps, g.tap_off);
+      // tensor map over the P8 input: dims {8 ch, Wp, Hp, groups*planes}, every second column / row per box
+      const cuuint64_t dims[4] = {8, (cuuint64_t)(in.W + 2), (cuuint64_t)(in.H + 2), (cuuint64_t)g.iDp * (CIN / 8)};
+      const cuuint64_t strides[3] = {16, (cuuint64_t)(in.W + 2) * 16, (cuuint64_t)(in.W + 2) * (in.H + 2) * 16};
+      const cuuint32_t box[4] = {8, (cuuint32_t)(2 * g.P), (cuuint32_t)(2 * g.RR), 1};
+      const cuuint32_t estr[4] = {1, 2, 2, 1};
+      const CUtensorMapDataType dt = std::is_same<TA, __nv_bfloat16>::value ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+      const CUresult r = tc::encode_tiled_fn()(&sc.tmap, dt, 4, in.p, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      TDM_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed for " + wkey + " (" + std::to_string((int)r) + ")");
+      it = s2_cache_.emplace(wkey, sc).first;
+    }
+    auto kern = tc::k_conv_tc_s2<TA, TA, CIN, NPAD, KD, KS>;
+    static bool attr_set = false;
+    if (!attr_set) {
+      TDM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      attr_set = true;
+    }
+    const tc::PlanS2& pl = it->second.plan;
+    kern<<<dim3(pl.grid, c.nsplit_s2), tc::kThreads, pl.smem, stream_>>>(it->second.tmap, (const TA*)c.bimg_s2, c.bias,
+                                                                         (TA*)out.p, pl.g);
+  }
+
+  bool conv_tc_s2_dispatch(const std::string& wkey, const DevBuf& bi, const DevConv& c, const DevBuf& bo, bool relu) {
+    if constexpr (sizeof(TA) != 2) {
+      return false;
+    } else {
+      if (bi.kind != 1 || bo.f32) return false;
+      if (c.kd == 3 && c.cin == 8) { tc_s2_inst<8, 16, 3, 3>(wkey, bi, c, bo, relu); return true; }
+      if (c.kd == 3 && c.cin == 16) { tc_s2_inst<16, 32, 3, 3>(wkey, bi, c, bo, relu); return true; }
+      if (c.kd == 3 && c.cin == 32) { tc_s2_inst<32, 32, 3, 3>(wkey, bi, c, bo, relu); return true; }
+      if (c.kd == 1 && c.cin == 8) { tc_s2_inst<8, 16, 1, 5>(wkey, bi, c, bo, relu); return true; }
+      if (c.kd == 1 && c.cin == 16) { tc_s2_inst<16, 32, 1, 5>(wkey, bi, c, bo, relu); return true; }
+      return false;
+    }
   }
 
   // returns true if the tcgen05 kernel was launched
@@ -533,23 +623,24 @@ class MvsnetEngine final : public MvsnetIface {
         if (bo.D != 2 * bi.D || bo.H != 2 * bi.H || bo.W != 2 * bi.W || bi.kind != 1) return false;
         if (c.cin == 16) { tc_inst<TA, TA, 16, 64, 2, false, 1>(bi, c, rp, bo, relu); return true; }
         if (c.cin == 32) { tc_inst<TA, TA, 32, 128, 2, false, 1>(bi, c, rp, bo, relu); return true; }
+        if (c.cin == 64) { tc_inst<TA, TA, 64, 64, 2, false, 1>(bi, c, rp, bo, relu); return true; }
         return false;
       }
-#define TDM_TC(TI, CI, NP, KDV)                                                            \
-  if (c.cin == CI && c.npad == NP && c.kd == KDV) {                                        \
-    tc_inst<TI, TA, CI, NP, KDV, false>(bi, c, rp, bo, relu);                              \
+#define TDM_TC(TI, CI, NP, KDV, HL)                                                        \
+  if (c.cin == CI && c.npad == NP && c.kd == KDV && c.hilo == HL) {                        \
+    tc_inst<TI, TA, CI, NP, KDV, false, 0, HL>(bi, c, rp, bo, relu);                       \
     return true;                                                                           \
   }
       if (bo.f32) {
-        if (c.cin == 8 && c.cout == 1 && c.kd == 3 && bi.kind == 1) { tc_inst<TA, TA, 8, 16, 3, true>(bi, c, nullptr, bo, false); return true; }
+        if (c.cin == 8 && c.cout == 1 && c.kd == 3 && bi.kind == 1 && c.hilo) { tc_inst<TA, TA, 8, 16, 3, true, 0, true>(bi, c, nullptr, bo, false); return true; }
         return false;
       }
       if (bi.kind == 2) {
-        TDM_TC(TV, 32, 16, 3) TDM_TC(TV, 16, 16, 3) TDM_TC(TV, 8, 16, 3)
+        TDM_TC(TV, 32, 16, 3, true) TDM_TC(TV, 16, 16, 3, true) TDM_TC(TV, 8, 16, 3, true)
         return false;
       }
-      TDM_TC(TA, 8, 16, 1) TDM_TC(TA, 16, 16, 1) TDM_TC(TA, 32, 32, 1) TDM_TC(TA, 32, 16, 1)
-      TDM_TC(TA, 16, 16, 3) TDM_TC(TA, 32, 32, 3)
+      TDM_TC(TA, 8, 16, 1, true) TDM_TC(TA, 16, 16, 1, true) TDM_TC(TA, 32, 32, 1, true) TDM_TC(TA, 32, 16, 1, true)
+      TDM_TC(TA, 16, 16, 3, true) TDM_TC(TA, 32, 32, 3, false) TDM_TC(TA, 64, 32, 3, false)
 #undef TDM_TC
       return false;
     }
@@ -579,6 +670,15 @@ class MvsnetEngine final : public MvsnetIface {
     if (use_tc_ && c.tc_ok && res_mode != 2 && (c.tc_deconv ? (sd == 2 && sh == 2 && sw == 2) : (sd == 1 && sh == 1 && sw == 1))) {
       rec_begin(wkey + "[tc]", bytes, 2.0 * macs);
       if (conv_tc_dispatch(bi, c, rp, bo, relu)) {
+        TDM_CUDA(cudaGetLastError());
+        rec_end();
+        return;
+      }
+      rec_cancel();
+    }
+    if (use_tc_ && c.tc_s2 && res_mode == 0 && sh == 2 && sw == 2 && sd == (c.kd == 3 ? 2 : 1)) {
+      rec_begin(wkey + "[tc-s2]", bytes, 2.0 * macs);
+      if (conv_tc_s2_dispatch(wkey, bi, c, bo, relu)) {
         TDM_CUDA(cudaGetLastError());
         rec_end();
         return;
@@ -674,7 +774,7 @@ class MvsnetEngine final : public MvsnetIface {
     k_select_init<<<1, 256, 0, stream_>>>(select_state_, (unsigned)cutoff);
     for (int pass = 0; pass < 3; ++pass) {
       k_select_hist<<<std::min(cdiv(n, 256 * 8), 592), 256, 0, stream_>>>(fbuf(k + "edge"), n, select_state_, pass);
-      k_select_scan<<<1, 256, 0, stream_>>>(select_state_, pass, fbuf("thr") + (s - 1));
+      k_select_scan<<<1, 1024, 0, stream_>>>(select_state_, pass, fbuf("thr") + (s - 1));
     }
     launch_count_ += 6;
     rec_end();
@@ -809,7 +909,7 @@ class MvsnetEngine final : public MvsnetIface {
   float c2w_[kMaxSrc + 1][16];
   float K_[27];
   float dmin_ = 0, dmax_ = 0, discard_ = 0;
-  bool filter_all_ = false, keep_ = true, use_tc_ = false;
+  bool filter_all_ = false, keep_ = true, use_tc_ = (sizeof(TA) == 2);  // tcgen05 convs are the default on 16-bit engines
   bool profiling_ = false;
   int launch_count_ = 0, launches_per_forward_ = 0;
   std::vector<LaunchRec> recs_;

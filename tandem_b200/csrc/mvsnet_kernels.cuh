@@ -433,24 +433,37 @@ __global__ void k_select_hist(const float* __restrict__ v, int n, SelectState* s
     if (h[i]) atomicAdd(&st->hist[i], h[i]);
 }
 
-__global__ void k_select_scan(SelectState* st, int pass, float* thr_out) {
-  // single thread: 2048 bins, negligible
-  if (threadIdx.x == 0 && blockIdx.x == 0) {
-    const int shift = pass == 0 ? 21 : (pass == 1 ? 10 : 0);
-    const int nb = pass == 2 ? 1024 : 2048;
-    unsigned k = st->k, cum = 0;
-    int bin = nb - 1;
-    for (int i = 0; i < nb; ++i) {
-      const unsigned c = st->hist[i];
-      if (k < cum + c) { bin = i; break; }
-      cum += c;
-    }
-    st->k = k - cum;
-    st->prefix |= ((unsigned)bin) << shift;
-    if (pass == 2) *thr_out = __uint_as_float(st->prefix);
+// one block of 1024 threads: parallel prefix over the 2048 bins, the thread whose bin pair contains rank k publishes
+__global__ void __launch_bounds__(1024) k_select_scan(SelectState* st, int pass, float* thr_out) {
+  __shared__ unsigned wsum[32];
+  const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+  const int shift = pass == 0 ? 21 : (pass == 1 ? 10 : 0);
+  const unsigned a = st->hist[2 * t], b = st->hist[2 * t + 1];
+  const unsigned k = st->k, prefix = st->prefix;
+  unsigned incl = a + b;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned n = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += n;
   }
+  if (lane == 31) wsum[w] = incl;
   __syncthreads();
-  for (int i = threadIdx.x; i < 2048; i += blockDim.x) st->hist[i] = 0;
+  unsigned off = 0;
+  for (int i = 0; i < w; ++i) off += wsum[i];
+  const unsigned excl = off + incl - (a + b);
+  __syncthreads();   // everybody has read st->hist / st->k before they are overwritten
+  st->hist[2 * t] = 0;
+  st->hist[2 * t + 1] = 0;
+  int bin = -1;
+  unsigned nk = 0;
+  if (k >= excl && k < excl + a) { bin = 2 * t; nk = k - excl; }
+  else if (k >= excl + a && k < excl + a + b) { bin = 2 * t + 1; nk = k - excl - a; }
+  if (bin >= 0) {
+    const unsigned np = prefix | ((unsigned)bin << shift);
+    st->k = nk;
+    st->prefix = np;
+    if (pass == 2) *thr_out = __uint_as_float(np);
+  }
 }
 
 __global__ void k_apply_edge_mask(const float* __restrict__ edge, const float* __restrict__ thr,

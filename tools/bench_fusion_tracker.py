@@ -1,0 +1,88 @@
+"""Secondary measurements: TSDF integrate + ray-cast at the initDr map size with a stream
+of synthetic 640x480 depth maps, the level-0 tracker evaluation, and - when oracle/_ref is present - the REFERENCE's own
+dr_fusion (compiled unmodified for sm_100a) on the same inputs on the same GPU.
+    python tools/bench_fusion_tracker.py [n_frames]
+Prints one JSON line per measurement."""
+import ctypes
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from tandem_b200 import CudaCoarseTracker, DrFusion, DrFusionOptions  # noqa: E402
+from tandem_b200.synthetic import RoomScene, circle_trajectory, tracker_case  # noqa: E402
+
+_fp = ctypes.POINTER(ctypes.c_float)
+n_frames = int(sys.argv[1]) if len(sys.argv) > 1 else 40
+H, W = 480, 640
+intr = dict(fx=320.0, fy=320.0, cx=319.5, cy=239.5)
+scene = RoomScene()
+poses = circle_trajectory(n_frames, radius=1.0)
+frames = [scene.render(p, H, W, **intr, noise_sigma=0.002, dropout=0.02, seed=k) for k, p in enumerate(poses)]
+for p in poses:
+    p[:3, 3] += np.float32(5.12)     # keep block (0,0,0) out of the map (reference quirk)
+
+opt = DrFusionOptions(height=H, width=W, **intr)
+f = DrFusion(opt)
+t0 = time.perf_counter()
+for (bgr, depth), pose in zip(frames, poses):
+    f.IntegrateScanAsync(bgr, depth, pose)
+    f.RenderAsync([pose])
+    f.GetRenderResult()
+f.Synchronize()
+e2e_ms = (time.perf_counter() - t0) * 1e3 / n_frames
+st = f.stats()
+mi, mr = f.run_resident(20)
+vis = st["visible_blocks"]
+alg = vis * 512 * 16 + 7 * H * W
+print(json.dumps({"what": "tsdf ours", "frames": n_frames, "allocated_blocks": st["allocated_blocks"], "visible_blocks_last": vis,
+                  "e2e_ms_per_frame(integrate+render+copies)": e2e_ms, "resident_allocate+integrate_ms": mi / 20,
+                  "resident_raycast_ms": mr / 20, "integrate_algorithmic_GB": alg / 1e9,
+                  "integrate_GBps": alg / (mi / 20 * 1e-3) / 1e9}))
+
+ref_lib = os.path.join(ROOT, "oracle", "_ref", "libdr_fusion_ref.so")
+if os.path.exists(ref_lib):
+    l = ctypes.CDLL(ref_lib)
+    l.ref_fusion_create.restype = ctypes.c_void_p
+    r = ctypes.c_void_p(l.ref_fusion_create(ctypes.byref(opt)))
+    rb, rd = np.zeros((H, W, 3), np.uint8), np.zeros((H, W), np.float32)
+    ti = tr = 0.0
+    nref = min(n_frames, 10)
+    for (bgr, depth), pose in list(zip(frames, poses))[:nref]:
+        b, d = np.ascontiguousarray(bgr), np.ascontiguousarray(depth)
+        t0 = time.perf_counter()
+        l.ref_fusion_integrate(r, ctypes.c_void_p(b.ctypes.data), d.ctypes.data_as(_fp), pose.ctypes.data_as(_fp))
+        l.ref_fusion_sync(r)
+        t1 = time.perf_counter()
+        l.ref_fusion_render(r, pose.ctypes.data_as(_fp), ctypes.c_void_p(rb.ctypes.data), rd.ctypes.data_as(_fp), H * W)
+        t2 = time.perf_counter()
+        ti += t1 - t0
+        tr += t2 - t1
+    print(json.dumps({"what": "tsdf reference dr_fusion (unmodified, sm_100a)", "frames": nref,
+                      "integrate_ms_per_frame(wall)": ti * 1e3 / nref, "render_ms_per_frame(wall)": tr * 1e3 / nref}))
+    l.ref_fusion_destroy(r)
+
+c = tracker_case()
+t = CudaCoarseTracker(c["w"], c["h"])
+t.init()
+t.setK(c["w"], c["h"], c["fx"], c["fy"], c["cx"], c["cy"])
+t.setReference(c["n"], c["pc_u"], c["pc_v"], c["pc_idepth"], c["pc_color"], c["ref_exposure"], c["ref_aff"])
+t.setNew(c["dInew"])
+t.calcResAndG(c["refToNew"], c["new_exposure"], c["new_aff"], c["cutoffTH"])
+ms = t.run_resident(200)
+t0 = time.perf_counter()
+for _ in range(200):
+    t.calcResAndG(c["refToNew"], c["new_exposure"], c["new_aff"], c["cutoffTH"])
+wall_fused = (time.perf_counter() - t0) / 200 * 1e6
+t0 = time.perf_counter()
+for _ in range(200):
+    t.calcRes(c["refToNew"], c["new_exposure"], c["new_aff"], c["cutoffTH"])
+    t.calcG(c["new_exposure"], c["new_aff"])
+wall_two = (time.perf_counter() - t0) / 200 * 1e6
+print(json.dumps({"what": "tracker ours", "n_points": c["n"], "kernel_us(fused, device)": ms / 200 * 1e3,
+                  "wall_us(fused call incl sync)": wall_fused, "wall_us(calcRes+calcG calls)": wall_two,
+                  "algorithmic_MB": (16 * c["n"] + 12 * c["w"] * c["h"] + 416) / 1e6}))
