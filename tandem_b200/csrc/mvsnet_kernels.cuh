@@ -271,6 +271,32 @@ k_cost_volume(const P8<const T> feats /*views on the D axis, ref first*/, const 
     float warped[C];
 #pragma unroll
     for (int c = 0; c < C; ++c) warped[c] = 0.f;
+    if constexpr (sizeof(T) == 2) {
+      // 16-bit engines: one reciprocal instead of the reference's four IEEE divisions (the normalise / un-normalise
+      // round trip of grid_sample is the identity up to 1 ulp), and no per-tap bounds tests: the P8 layout carries a
+      // zero halo of one position, which IS grid_sample's zeros padding for every sample with -1 <= ix < W, -1 <= iy < H.
+      const float inv = __frcp_rn(qz);
+      const float ix = qx * inv, iy = qy * inv;
+      if (!(qz < 0.001f) && ix >= -1.f && iy >= -1.f && ix < (float)p.W && iy < (float)p.H) {
+        const float x0f = floorf(ix), y0f = floorf(iy);
+        const float ax = ix - x0f, ay = iy - y0f;
+        const float w00 = (1.f - ax) * (1.f - ay), w01 = ax * (1.f - ay), w10 = (1.f - ax) * ay, w11 = ax * ay;
+        const T* tp = feats.p + feats.pos(s + 1, (int)y0f, (int)x0f);
+        const int row = feats.Wp * 8;
+#pragma unroll
+        for (int c0 = 0; c0 < C; c0 += 8) {
+          const T* tq = tp + (c0 >> 3) * feats.gs;
+          float f00[8], f01[8], f10[8], f11[8];
+          load_vec<T, 8>(tq, f00);
+          load_vec<T, 8>(tq + 8, f01);
+          load_vec<T, 8>(tq + row, f10);
+          load_vec<T, 8>(tq + row + 8, f11);
+#pragma unroll
+          for (int c = 0; c < 8; ++c)
+            warped[c0 + c] = fmaf(f11[c], w11, fmaf(f10[c], w10, fmaf(f01[c], w01, f00[c] * w00)));
+        }
+      }
+    } else {
     const float u = qx / qz, v = qy / qz;
     // grid_sample(align_corners=True) round trip through normalised coordinates
     const float gx = u / half_w - 1.f, gy = v / half_h - 1.f;
@@ -297,6 +323,7 @@ k_cost_volume(const P8<const T> feats /*views on the D axis, ref first*/, const 
         }
       }
     }
+    }  // exact (fp32 parity) path
     if (p.view_aggregation) {
       float dot = 0.f;
 #pragma unroll
@@ -316,8 +343,14 @@ k_cost_volume(const P8<const T> feats /*views on the D axis, ref first*/, const 
   }
   if (p.view_aggregation) {
     const float dv = (float)p.nsrc;
+    if constexpr (sizeof(T) == 2) {
+      const float idv = 1.f / dv;
 #pragma unroll
-    for (int c = 0; c < C; ++c) acc[c] = acc[c] / dv;
+      for (int c = 0; c < C; ++c) acc[c] *= idv;
+    } else {
+#pragma unroll
+      for (int c = 0; c < C; ++c) acc[c] = acc[c] / dv;
+    }
   } else {
     const float nv = (float)(p.nsrc + 1);
 #pragma unroll
