@@ -115,6 +115,11 @@ int tdm_fusion_render_async(tdm_fusion* h, const float* const* camera_poses, int
  * valid until the next get_render_result (tsdf_volume.cu:710-732). bgr_out/depth_out: arrays of n_poses. */
 int tdm_fusion_get_render_result(tdm_fusion* h, unsigned char** bgr_out, float** depth_out, int n_poses);
 int tdm_fusion_synchronize(tdm_fusion* h);
+/* Multi-GPU extension (not in the reference): restrict this instance to the Z-slab of voxel blocks with
+ * z_block_lo <= block.z < z_block_hi (block = 8 voxels; pass the owned range widened by one halo block so that trilinear
+ * reads never cross ranks). Every rank integrates the same (broadcast) scans; renders are combined by a per-pixel
+ * nearest-hit reduction (tandem_b200/parallel.py: reduce_nearest_hit). Call before the first scan. */
+int tdm_fusion_set_slab(tdm_fusion* h, int z_block_lo, int z_block_hi);
 /* Mesh (DrFusion::ExtractMeshAsync/GetMeshSync/GetMesh, dr_fusion.h:56-68): vertices as xyz float triples,
  * colours as rgb float triples, 3 vertices per triangle. Returns vertex count or <0. */
 long long tdm_fusion_extract_mesh(tdm_fusion* h, const float lower[3], const float upper[3],

@@ -75,6 +75,7 @@ def _declare(l):
         "tdm_fusion_render_async": (i, [vp, P(fp), i]),
         "tdm_fusion_get_render_result": (i, [vp, P(vp), P(fp), i]),
         "tdm_fusion_synchronize": (i, [vp]),
+        "tdm_fusion_set_slab": (i, [vp, i, i]),
         "tdm_fusion_extract_mesh": (c.c_longlong, [vp, fp, fp, fp, fp, c.c_size_t]),
         "tdm_fusion_get_stats": (i, [vp, P(FusionStats)]),
         "tdm_fusion_dump_blocks": (c.c_longlong, [vp, ip, vp, c.c_size_t]),

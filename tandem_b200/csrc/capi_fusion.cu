@@ -43,6 +43,13 @@ int tdm_fusion_get_render_result(tdm_fusion* h, unsigned char** bgr_out, float**
   return TDM_OK;
   TDM_API_END
 }
+int tdm_fusion_set_slab(tdm_fusion* h, int z_block_lo, int z_block_hi) {
+  TDM_API_BEGIN
+  TDM_CHECK(h, "null handle");
+  h->impl->set_slab(z_block_lo, z_block_hi);
+  return TDM_OK;
+  TDM_API_END
+}
 int tdm_fusion_synchronize(tdm_fusion* h) {
   TDM_API_BEGIN
   TDM_CHECK(h, "null handle");

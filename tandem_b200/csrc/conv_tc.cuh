@@ -22,6 +22,8 @@
 // issue work is spread over three warps); warp 1 also owns the TMEM allocation; warps 2..5 = epilogue (TMEM lane
 // quarter = warp_id % 4).
 #pragma once
+#include <cuda.h>
+
 #include <cmath>
 #include <vector>
 
@@ -45,6 +47,7 @@ struct Geom {
   int cout;               // real output channels (<= NPAD)
   int S;                  // ring slots
   int oHp, oWp, opd;      // padded dims / D halo of the OUTPUT tensor (differs from the input in deconv mode)
+  int iDp;                // padded plane count of the input: tensor-map dim 3 = channel_group * iDp + plane
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -71,8 +74,10 @@ __device__ __forceinline__ bool mbar_try(uint64_t* bar, uint32_t parity) {
 }
 // Bounded wait: a protocol bug must abort the kernel (trap -> launch error), never hang the GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  for (uint32_t i = 0; !mbar_try(bar, parity); ++i)
-    if (i > (1u << 24)) __trap();
+  if (mbar_try(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try(bar, parity))
+    if (clock64() - t0 > 4000000000ll) __trap();   // ~2 s at 1.9 GHz: no legitimate wait in these kernels is that long
 }
 // 1-D TMA bulk copy global -> shared, completion counted on an mbarrier (SASS: UBLKCP)
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
@@ -105,13 +110,23 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// Tiled TMA load of one box of a 4-D tensor map (SASS: UTMALDG); out-of-bounds elements are zero-filled.
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* tmap, int x0, int x1, int x2, int x3, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];" ::"r"(
+          smem_u32(dst)),
+      "l"(tmap), "r"(x0), "r"(x1), "r"(x2), "r"(x3), "r"(smem_u32(bar))
+      : "memory");
+}
+
+
 constexpr int kThreads = 256;   // warp 0 TMA, warp 1 MMA (+TMEM alloc), warps 2..5 epilogue, warps 6,7 MMA
 constexpr int kMmaWarps = 3;
 
 // blocks of B per kd plane: one block = one K=16 MMA step = NPAD x 16 elements in canonical order
 // MODE 0: 3x3 stencil per plane (9 taps).  MODE 1: transposed conv k3 s2 p1 op1 as a GEMM over the INPUT grid: 2x2 taps
 // per plane at offsets {0,1}^2 (stencil positions (1..2,1..2)), 2 planes, N = 8 output parity classes x COUT.
-template <int CIN, int MODE = 0> constexpr int blocks_per_kd() { return MODE == 1 ? 4 * (CIN / 16) : (CIN >= 16 ? 9 * (CIN / 16) : 5); }
+template <int CIN, int MODE = 0> constexpr int blocks_per_kd() { return MODE == 1 ? 4 * (CIN / 16) : (CIN >= 16 ? 9 * (CIN / 16) : 5); }  // MODE 3 == MODE 0 geometry
 
 // AFMT: 0 = f16, 1 = bf16 (a_format/b_format of the instruction descriptor).  OUT_PLAIN: fp32 [D][H][W] (prob conv).
 // HILO: the B image carries every weight twice, as W_hi = round16(W) in columns [0,NPAD) and W_lo = round16(W - W_hi)
@@ -119,14 +134,18 @@ template <int CIN, int MODE = 0> constexpr int blocks_per_kd() { return MODE == 
 // weight precision.  It is free here: at N <= 64 the instruction is bound by streaming the 4 KB A operand, not by N.
 template <typename TIn, typename TOut, int CIN, int NPAD, int KD, bool OUT_PLAIN, int MODE = 0, bool HILO = false>
 __global__ void __launch_bounds__(kThreads, 1)
-k_conv_tc(const TIn* __restrict__ in, const TIn* __restrict__ bimg /*host-arranged B image*/, const float* __restrict__ bias,
+k_conv_tc(const __grid_constant__ CUtensorMap tmap /*P8 input: {8, Wp, Hp, groups*planes}, box {8, P, R+2, 1}*/,
+          const TIn* __restrict__ bimg /*host-arranged B image*/, const float* __restrict__ bias,
           const TOut* __restrict__ res, TOut* __restrict__ out, float* __restrict__ plain_out, const __grid_constant__ Geom g) {
   constexpr int CG = CIN / 8;
   constexpr int NBLK = blocks_per_kd<CIN, MODE>();
   constexpr int NMMA = HILO ? 2 * NPAD : NPAD;   // instruction N and TMEM columns per chunk
-  static_assert(!(HILO && MODE == 1), "hi/lo weights are only wired for the plain convolution epilogue");
+  static_assert(!(HILO && MODE == 1), "hi/lo weights are not wired for the 3-D transposed-conv epilogue");
+  // MODE 3: 2-D "conv3x3 of a nearest-x2 up-sampled map" evaluated on the COARSE grid: 9 taps, N = 4 output parity
+  // classes x COUT (the 3x3 fine taps collapse onto 2x2 coarse neighbours; weights pre-summed on the host).
   constexpr int B_BYTES = KD * NBLK * NMMA * 32;
-  constexpr int PLANE0 = MODE == 1 ? 1 : 0;   // deconv reads input planes d and d+1 (padded indices d+1, d+2)
+  constexpr int PLANE0 = MODE == 1 ? 1 : 0;
+  constexpr bool CLASS_EPI = MODE == 1 || MODE == 3;   // deconv reads input planes d and d+1 (padded indices d+1, d+2)
   constexpr uint32_t AFMT = std::is_same<TIn, __nv_bfloat16>::value ? 1u : 0u;
   constexpr uint32_t IDESC = (1u << 4) | (AFMT << 7) | (AFMT << 10) | ((uint32_t)(NMMA >> 3) << 17) | ((128u >> 4) << 24);
 
@@ -180,21 +199,17 @@ k_conv_tc(const TIn* __restrict__ in, const TIn* __restrict__ bimg /*host-arrang
     if (lane == 0) {
       mbar_expect_tx(b_full, B_BYTES);
       bulk_g2s(sB, bimg, B_BYTES, b_full);
-      const int nrows = min(g.R + 2, g.Hp - h0);
-      const uint32_t row_bytes = (uint32_t)min(g.P, g.Wp - w0) * 16u;
-      const long long plane_elems = (long long)g.Hp * g.Wp * 8;
+      // one tiled TMA per (plane, channel group): box = (R+2) rows x P positions, rows / columns beyond the tensor are
+      // zero-filled by the TMA engine, so partial tiles need no special casing
+      const uint32_t box_bytes = (uint32_t)g.P * (uint32_t)(g.R + 2) * 16u;
       for (int rp = 0; rp < nin; ++rp) {
         const int slot = rp % g.S;
         if (rp >= g.S) mbar_wait(&empty[slot], ((rp / g.S) - 1) & 1);
-        mbar_expect_tx(&full[slot], row_bytes * (uint32_t)nrows * CG);
+        mbar_expect_tx(&full[slot], box_bytes * CG);
         const int pp = d0 + rp + PLANE0;  // padded plane index (pd == 1: plane d-1+kd+1; pd == 0: plane d)
 #pragma unroll 1
-        for (int cg = 0; cg < CG; ++cg) {
-          const TIn* src = in + cg * g.in_gs + pp * plane_elems + ((long long)h0 * g.Wp + w0) * 8;
-          uint8_t* dst = sA + (size_t)slot * slot_bytes + (size_t)cg * cg_bytes;
-          for (int r = 0; r < nrows; ++r)
-            bulk_g2s(dst + (size_t)r * g.P * 16, src + (long long)r * g.Wp * 8, row_bytes, &full[slot]);
-        }
+        for (int cg = 0; cg < CG; ++cg)
+          tma_load_4d(sA + (size_t)slot * slot_bytes + (size_t)cg * cg_bytes, &tmap, 0, w0, h0, cg * g.iDp + pp, &full[slot]);
       }
     }
   } else if (warp == 1 || warp >= 6) {
@@ -274,19 +289,25 @@ k_conv_tc(const TIn* __restrict__ in, const TIn* __restrict__ bimg /*host-arrang
         const int h = h0 + hh, w = w0 + ww;
         const bool valid = hh < g.R && ww < g.TW && h < g.H && w < g.W;
         const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * acc_cols + c * NMMA);
-        if constexpr (MODE == 1) {
-          // N = 8 parity classes x COUT: class (pd,ph,pw) of input position (d,h,w) is output (2d+pd, 2h+ph, 2w+pw)
+        if constexpr (CLASS_EPI) {
+          // N = 8 (MODE 1) or 4 (MODE 3) parity classes x COUT: class (pd,ph,pw) of input position (d,h,w) is output (2d+pd, 2h+ph, 2w+pw)
           const int COUT = g.cout;
 #pragma unroll 1
           for (int n0 = 0; n0 < NPAD; n0 += 16) {
             uint32_t v[16];
             tmem_ld16(t_row + (uint32_t)n0, v);
+            if constexpr (HILO) {
+              uint32_t v2[16];
+              tmem_ld16(t_row + (uint32_t)(NPAD + n0), v2);
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) + __uint_as_float(v2[i]));
+            }
             if (valid) {
 #pragma unroll
               for (int k0 = 0; k0 < 16; k0 += 8) {
                 const int n = ns * NPAD + n0 + k0;
                 const int cls = n / COUT, co = n % COUT;
-                const int od2 = 2 * d + (cls >> 2), oh2 = 2 * h + ((cls >> 1) & 1), ow2 = 2 * w + (cls & 1);
+                const int od2 = MODE == 1 ? 2 * d + (cls >> 2) : d, oh2 = 2 * h + ((cls >> 1) & 1), ow2 = 2 * w + (cls & 1);
                 const long long pos = ((((long long)(od2 + g.opd)) * g.oHp + (oh2 + 1)) * g.oWp + (ow2 + 1)) * 8;
                 float o8[8];
 #pragma unroll
@@ -426,6 +447,22 @@ inline void build_b_image_deconv(const float* w, int cin, int cout, std::vector<
             }
 }
 
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+inline EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    TDM_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qr));
+    TDM_CHECK(p != nullptr && qr == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled not available from the driver");
+    fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
 struct Plan {
   Geom g;
   int grid;
@@ -449,13 +486,13 @@ inline Plan make_plan(int cin, int npad, int kd, int D, int H, int W, int pd, in
   for (int S = s_hi; S >= s_lo; --S) {
     for (int tiles_w = 1; tiles_w <= 20; ++tiles_w) {
       const int TW = (W + tiles_w - 1) / tiles_w;
-      if (TW > 512) continue;
+      if (TW + 2 > 256) continue;               // TMA box dims <= 256
       if (tiles_w > 1 && TW < 30) break;
       const int tw_n = (W + TW - 1) / TW;
       const int P = TW + 2;
       for (int R = 1; R <= 32 && R <= H; ++R) {
         const int nch = (R * P + 127) / 128;
-        const int slot_pos = std::max((R + 2) * P, nch * 128 + 2 * P + 2) + 8;
+        const int slot_pos = (std::max((R + 2) * P, nch * 128 + 2 * P + 2) + 8 + 7) / 8 * 8;
         const size_t smem = bbytes + (size_t)S * cg * slot_pos * 16 + 256;
         if (smem > smem_limit || 2 * nch * npad > 512) break;
         const int th_n = (H + R - 1) / R;
@@ -467,8 +504,7 @@ inline Plan make_plan(int cin, int npad, int kd, int D, int H, int W, int pd, in
           const double amp = (double)(R + 2) / R * (double)P / TW * (kd == 3 ? (double)(DR + 2) / DR : (kd == 2 ? (double)(DR + 1) / DR : 1.0));
           const double waste = (double)nch * 128 / ((double)R * TW);
           const double quant = std::ceil(T / 148.0) / (T / 148.0);
-          const double tma = P * 16 >= 2048 ? 1.0 : 1.0 + 0.3 * (2048.0 - P * 16) / 2048.0;  // short bulk copies are inefficient
-          const double cost = amp * (0.75 + 0.25 * waste) * quant * tma * (S == s_hi ? 1.0 : 1.1);
+          const double cost = amp * (0.75 + 0.25 * waste) * quant * (S == s_hi ? 1.0 : 1.1);
           if (cost < best_cost - 1e-9) { best_cost = cost; bestR = R; bestTW = TW; bestS = S; bestDR = DR; }
           if (T > 4000) break;
         }
@@ -479,7 +515,7 @@ inline Plan make_plan(int cin, int npad, int kd, int D, int H, int W, int pd, in
   TDM_CHECK(bestR > 0, "conv_tc: no tile fits shared memory");
   g.S = bestS; g.R = bestR; g.TW = bestTW; g.P = bestTW + 2; g.DR = bestDR;
   g.nch = (g.R * g.P + 127) / 128;
-  g.slot_pos = std::max((g.R + 2) * g.P, g.nch * 128 + 2 * g.P + 2) + 8;
+  g.slot_pos = (std::max((g.R + 2) * g.P, g.nch * 128 + 2 * g.P + 2) + 8 + 7) / 8 * 8;   // 128-byte aligned TMA destinations
   g.tiles_w = (W + g.TW - 1) / g.TW;
   g.tiles_h = (H + g.R - 1) / g.R;
   g.tiles_d = (D + g.DR - 1) / g.DR;

@@ -10,8 +10,6 @@
 // downstream (descriptors with SBO = 128 B, TMEM accumulators, epilogue) is the stride-1 machinery of conv_tc.cuh.
 // Out-of-bounds rows / columns (the 5x5 kernels reach one position beyond the stored halo) are zero-filled by TMA.
 #pragma once
-#include <cuda.h>
-
 #include "conv_tc.cuh"
 
 namespace tdm {
@@ -33,14 +31,6 @@ struct GeomS2 {
   int ntaps;               // KS*KS
   short tap_off[kMaxTaps + 1];   // position offset of tap t inside a channel group's 4 sub-tiles (table order)
 };
-
-__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* tmap, int x0, int x1, int x2, int x3, uint64_t* bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];" ::"r"(
-          smem_u32(dst)),
-      "l"(tmap), "r"(x0), "r"(x1), "r"(x2), "r"(x3), "r"(smem_u32(bar))
-      : "memory");
-}
 
 template <int CIN, int KS> constexpr int s2_blocks() { return CIN >= 16 ? KS * KS * (CIN / 16) : (KS * KS + 1) / 2; }
 
@@ -234,22 +224,6 @@ k_conv_tc_s2(const __grid_constant__ CUtensorMap tmap, const TIn* __restrict__ b
 // ---------------------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-inline EncodeTiledFn encode_tiled_fn() {
-  static EncodeTiledFn fn = nullptr;
-  if (!fn) {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult qr;
-    TDM_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qr));
-    TDM_CHECK(p != nullptr && qr == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled not available from the driver");
-    fn = (EncodeTiledFn)p;
-  }
-  return fn;
-}
-
 // tap table order: sub-tile (row parity, col parity) major, then (kh/2, kw/2).  Returns (kh,kw) per table slot.
 inline void s2_tap_table(int KS, int P, int sub_pos, std::vector<std::pair<int, int>>& taps, short* off) {
   taps.clear();

@@ -39,6 +39,7 @@ struct FusionDev {
   uint2* voxels;             // [num_blocks*512] {sdf bits, c0|c1<<8|c2<<16|w<<24}
   int4* list;                // compact list of allocated blocks (x,y,z,ptr)
   int* counters;             // [0] #blocks allocated, [1] dropped, [2] visible (last scan), [3] new this scan
+  int slab_lo, slab_hi;      // Z-slab partition (block z in [slab_lo, slab_hi) is kept), default: everything
 };
 
 __device__ __forceinline__ float mul_(float a, float b) { return __fmul_rn(a, b); }
@@ -85,6 +86,7 @@ __device__ __forceinline__ long long hash_bucket(const tdm_fusion_options& o, in
 
 __device__ void insert_block(const FusionDev& d, int x, int y, int z) {
   if (x <= -kKeyBias || x >= kKeyBias || y <= -kKeyBias || y >= kKeyBias || z <= -kKeyBias || z >= kKeyBias) return;
+  if (z < d.slab_lo || z >= d.slab_hi) return;   // another rank's Z-slab
   const unsigned long long key = pack_key(x, y, z);
   const long long b = hash_bucket(d.o, x, y, z);
   for (int i = 0; i < d.o.bucket_size; ++i) {
@@ -320,6 +322,8 @@ class FusionImpl final : public FusionIface {
     TDM_CHECK(o.max_sdf_weight > 0 && o.max_sdf_weight <= 255, "max_sdf_weight must fit the u8 voxel weight");
     TDM_CUDA(cudaSetDevice(device_));
     d_.o = o;
+    d_.slab_lo = INT_MIN;
+    d_.slab_hi = INT_MAX;
     n_entries_ = (long long)o.num_buckets * o.bucket_size;
     int lo, hi;
     TDM_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
@@ -407,6 +411,13 @@ class FusionImpl final : public FusionIface {
     }
     free_half_ ^= 1;  // the returned half stays valid until the next GetRenderResult (tsdf_volume.cu:719-732)
     next_ = kIntegrate;
+  }
+
+  void set_slab(int z_lo, int z_hi) override {
+    TDM_CHECK(z_lo < z_hi, "empty slab");
+    TDM_CHECK(!have_scan_, "set_slab must be called before the first scan");
+    d_.slab_lo = z_lo;
+    d_.slab_hi = z_hi;
   }
 
   void synchronize() override {

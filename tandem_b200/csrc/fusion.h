@@ -14,6 +14,7 @@ class FusionIface {
   virtual void integrate_async(const unsigned char* bgr, const float* depth, const float* pose) = 0;
   virtual void render_async(const float* const* poses, int n) = 0;
   virtual void get_render_result(unsigned char** bgr, float** depth, int n) = 0;
+  virtual void set_slab(int z_block_lo, int z_block_hi) = 0;
   virtual void synchronize() = 0;
   virtual void get_stats(tdm_fusion_stats* s) = 0;
   virtual long long dump_blocks(int* coords, void* voxels, size_t cap) = 0;

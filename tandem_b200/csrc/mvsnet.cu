@@ -92,6 +92,7 @@ struct DevConv {
   bool tc_deconv = false;  // transposed conv evaluated as a GEMM over the input grid (N = 8 parity classes x cout)
   int nsplit = 1;          // N slices (blockIdx.y) for the 64-channel layers
   bool hilo = false;       // weights carried as hi + lo 16-bit halves (N doubled), see conv_tc.cuh
+  bool tc_up2 = false;     // MODE 3: conv3x3 of a nearest-x2 up-sampled map on the coarse grid (fused FPN tail)
   bool tc_s2 = false;      // stride-2 conv on the tensor-map (strided TMA) kernel, conv_tc_s2.cuh
   void* bimg_s2 = nullptr;
   int npad_s2 = 0, nsplit_s2 = 1;
@@ -118,6 +119,7 @@ class MvsnetEngine final : public MvsnetIface {
     int lo, hi;
     TDM_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
     TDM_CUDA(cudaStreamCreateWithPriority(&stream_, cudaStreamNonBlocking, lo));
+    for (auto& e : ev_out_) TDM_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     upload_weights();
     worker_ = std::thread([this] { this->loop(); });
   }
@@ -134,6 +136,8 @@ class MvsnetEngine final : public MvsnetIface {
     free_plan();
     for (auto& kv : convs_) { cudaFree(kv.second.w); cudaFree(kv.second.bias); cudaFree(kv.second.bimg); cudaFree(kv.second.bimg_s2); }
     if (select_state_) cudaFree(select_state_);
+    if (d_bs3_) cudaFree(d_bs3_);
+    for (auto& e : ev_out_) if (e) cudaEventDestroy(e);
     if (stream_) cudaStreamDestroy(stream_);
   }
 
@@ -162,9 +166,12 @@ class MvsnetEngine final : public MvsnetIface {
     ensure_plan(V, H, W);
     // copy inputs (owned by the caller only during this call); reference view first (dr_mvsnet.cpp:190-197)
     const size_t img = (size_t)H * W * 3;
+    // The staging copy of view v+1 overlaps the DMA of view v (the worker is idle here, so this thread may enqueue on
+    // the engine's stream); the worker then only launches the forward behind these copies.
     for (int vi = 0; vi < V; ++vi) {
       const int view = vi == 0 ? ref_index : (vi <= ref_index ? vi - 1 : vi);
       std::memcpy(h_bgr_ + (size_t)vi * img, bgrs[view], img);
+      TDM_CUDA(cudaMemcpyAsync(d_bgr_ + (size_t)vi * img, h_bgr_ + (size_t)vi * img, img, cudaMemcpyHostToDevice, stream_));
       std::memcpy(c2w_[vi], c2ws[view], 16 * sizeof(float));
     }
     std::memcpy(K_, K3x3x3, 27 * sizeof(float));
@@ -190,10 +197,11 @@ class MvsnetEngine final : public MvsnetIface {
     if (!worker_error_.empty()) { std::string e = worker_error_; worker_error_.clear(); throw Error(e); }
     if (!has_result_) throw Error("GetResult without a pending result (dr_mvsnet.cpp:100-102)");
     const size_t n = (size_t)H_ * W_;
-    if (depth) std::memcpy(depth, h_out_, n * 4);
-    if (conf) std::memcpy(conf, h_out_ + n, n * 4);
-    if (depth_dense) std::memcpy(depth_dense, h_out_ + 2 * n, n * 4);
-    if (conf_dense) std::memcpy(conf_dense, h_out_ + 3 * n, n * 4);
+    float* dst[4] = {depth, conf, depth_dense, conf_dense};
+    for (int k = 0; k < 4; ++k) {   // the copy of map k into caller memory overlaps the D2H of map k+1
+      TDM_CUDA(cudaEventSynchronize(ev_out_[k]));
+      if (dst[k]) std::memcpy(dst[k], h_out_ + k * n, n * 4);
+    }
     has_result_ = false;
   }
 
@@ -333,6 +341,48 @@ class MvsnetEngine final : public MvsnetIface {
     convs_[key] = dc;
   }
 
+  // Algebraic fusion of the FPN tail for stage 3 (module.py:522-530): feat3 = out3(up2(i2) + skip3(c3) + b3) is linear,
+  //   feat3 = [conv3x3(W3) o up2](i2 + b3)  +  conv3x3(W3 . Ws3)(c3)
+  // (adding b3 to i2 BEFORE the zero-padded up-sampling reproduces the bias' border behaviour exactly).  The first term
+  // is evaluated on the coarse grid (4 output parity classes, the 3x3 fine taps pre-summed onto the 3x3 coarse
+  // neighbourhood), the second is an 8->8 conv on c3 that adds the first as its residual.  The 138 MB tensor i3 is never
+  // formed.
+  void build_fused_fpn() {
+    const std::string f = "feature_net.";
+    const FoldedConv w3 = fold_conv(wf_, f + "out.stage3.weight", "", "", false);                        // [9][32][8]
+    const FoldedConv ws = fold_conv(wf_, f + "skip.stage3.weight", f + "skip.stage3.bias", "", false);   // [1][8][32]
+    FoldedConv a;   // coarse-grid operator: [9 coarse taps][32][4 classes * 8]
+    a.cin = 32; a.cout = 32; a.kd = 1; a.kh = 3; a.kw = 3;
+    a.w.assign((size_t)9 * 32 * 32, 0.f);
+    auto coarse = [](int p, int k) { return p == 0 ? (k == 0 ? -1 : 0) : (k == 2 ? 1 : 0); };  // fine tap k of parity p -> coarse offset
+    for (int ph = 0; ph < 2; ++ph)
+      for (int pw = 0; pw < 2; ++pw)
+        for (int kh = 0; kh < 3; ++kh)
+          for (int kw = 0; kw < 3; ++kw) {
+            const int ta = (coarse(ph, kh) + 1) * 3 + (coarse(pw, kw) + 1);
+            for (int m = 0; m < 32; ++m)
+              for (int co = 0; co < 8; ++co)
+                a.w[((size_t)ta * 32 + m) * 32 + (ph * 2 + pw) * 8 + co] += w3.w[((size_t)(kh * 3 + kw) * 32 + m) * 8 + co];
+          }
+    FoldedConv b;   // W3 . Ws3 : [9][8][8]
+    b.cin = 8; b.cout = 8; b.kd = 1; b.kh = 3; b.kw = 3;
+    b.w.assign((size_t)9 * 8 * 8, 0.f);
+    for (int t = 0; t < 9; ++t)
+      for (int ci = 0; ci < 8; ++ci)
+        for (int co = 0; co < 8; ++co) {
+          double acc = 0;
+          for (int m = 0; m < 32; ++m) acc += (double)w3.w[((size_t)t * 32 + m) * 8 + co] * (double)ws.w[(size_t)ci * 32 + m];
+          b.w[((size_t)t * 8 + ci) * 8 + co] = (float)acc;
+        }
+    add_conv("f.out3a", a);
+    convs_["f.out3a"].cout = 8;          // real channels per class; N = 4 classes x 8 = npad
+    convs_["f.out3a"].tc_up2 = true;
+    add_conv("f.out3b", b);
+    TDM_CUDA(cudaMalloc(&d_bs3_, 32 * 4));
+    TDM_CUDA(cudaMemcpy(d_bs3_, ws.bias.data(), 32 * 4, cudaMemcpyHostToDevice));
+    fused_fpn_ = true;
+  }
+
   template <typename TB>
   void upload_bimg(const FoldedConv& fc, DevConv& dc) {
     std::vector<TB> img;
@@ -362,6 +412,7 @@ class MvsnetEngine final : public MvsnetIface {
     add_conv("f.out3", fold_conv(wf_, f + "out.stage3.weight", "", "", false));
     add_conv("f.skip2", fold_conv(wf_, f + "skip.stage2.weight", f + "skip.stage2.bias", "", false));
     add_conv("f.skip3", fold_conv(wf_, f + "skip.stage3.weight", f + "skip.stage3.bias", "", false));
+    if constexpr (sizeof(TA) == 2) build_fused_fpn();
     for (int s = 1; s <= 3; ++s) {
       const std::string p = "cost_regularization_net.stage" + std::to_string(s) + ".";
       const std::string k = "s" + std::to_string(s) + ".";
@@ -430,6 +481,7 @@ class MvsnetEngine final : public MvsnetIface {
   }
   void free_plan() {
     s2_cache_.clear();
+    tc_cache_.clear();
     for (auto& kv : bufs_) cudaFree(kv.second.p);
     bufs_.clear();
     if (h_bgr_) cudaFreeHost(h_bgr_);
@@ -455,6 +507,7 @@ class MvsnetEngine final : public MvsnetIface {
     alloc("f.c1", 32, V, H / 4, W / 4);
     alloc("feat1", 32, V, H / 4, W / 4);
     alloc("f.i2", 32, V, H / 2, W / 2);
+    alloc("f.i2b", 32, V, H / 2, W / 2);
     alloc("feat2", 16, V, H / 2, W / 2);
     alloc("f.i3", 32, V, H, W);
     alloc("feat3", 8, V, H, W);
@@ -510,13 +563,21 @@ class MvsnetEngine final : public MvsnetIface {
   }
 
   template <typename TIn, typename TOut, int CIN, int COUT>
-  void conv_inst(const DevBuf& in, const DevConv& c, const DevBuf* res, const DevBuf& out, const ConvGeom& g) {
+  void conv_inst(const DevBuf& in, const DevConv& c, const DevBuf* res, const DevBuf& out, const ConvGeom& g,
+                 const DevBuf* out_b = nullptr, const float* bias_b = nullptr) {
     const long long npos = (long long)g.Do * g.Ho * g.Wo;
     P8<const TOut> r{};
     if (res) r = p8<const TOut>(*res);
-    P8<TOut> o{};
+    P8<TOut> o{}, ob{};
     float* plain = nullptr;
     if constexpr (COUT == 1) plain = (float*)out.p; else o = p8<TOut>(out);
+    if constexpr (COUT != 1) {
+      if (out_b) {
+        ob = p8<TOut>(*out_b);
+        k_conv_direct<TIn, TOut, CIN, COUT><<<cdiv(npos, 128), 128, 0, stream_>>>(p8<const TIn>(in), c.w, c.bias, r, o, plain, g, ob, bias_b);
+        return;
+      }
+    }
     if constexpr (COUT >= 16) {
       if (npos < 128ll * 592) {  // too few positions to fill the chip: split the output channels over blockIdx.y
         dim3 grid(cdiv(npos, 128), COUT / 8);
@@ -527,26 +588,46 @@ class MvsnetEngine final : public MvsnetIface {
     k_conv_direct<TIn, TOut, CIN, COUT><<<cdiv(npos, 128), 128, 0, stream_>>>(p8<const TIn>(in), c.w, c.bias, r, o, plain, g);
   }
 
+  struct TcCache { tc::Plan plan; CUtensorMap tmap; };
+  std::map<std::string, TcCache> tc_cache_;
+
   template <typename TIn, typename TOut, int CIN, int NPAD, int KD, bool PLAIN, int MODE = 0, bool HILO = false>
-  void tc_inst(const DevBuf& in, const DevConv& c, const DevBuf* res, const DevBuf& out, bool relu) {
-    tc::Plan pl = tc::make_plan(CIN, HILO ? 2 * NPAD : NPAD, KD, in.D, in.H, in.W, in.pd, MODE);   // tiles live on the INPUT grid
-    tc::Geom& g = pl.g;
-    g.oHp = out.H + 2; g.oWp = out.W + 2; g.opd = out.pd;
-    const P8<const TIn> pi = p8<const TIn>(in);
-    g.in_gs = pi.gs;
-    g.relu = relu ? 1 : 0;
-    g.has_res = res ? 1 : 0;
-    g.cout = c.cout;
+  void tc_inst(const std::string& wkey, const DevBuf& in, const DevConv& c, const DevBuf* res, const DevBuf& out, bool relu) {
+    auto it = tc_cache_.find(wkey);
+    if (it == tc_cache_.end()) {
+      TcCache tcx;
+      tcx.plan = tc::make_plan(CIN, HILO ? 2 * NPAD : NPAD, KD, in.D, in.H, in.W, in.pd, MODE);   // tiles live on the INPUT grid
+      tc::Geom& g = tcx.plan.g;
+      g.oHp = out.H + 2; g.oWp = out.W + 2; g.opd = out.pd;
+      g.iDp = in.D + 2 * in.pd;
+      g.in_gs = p8<const TIn>(in).gs;
+      g.relu = relu ? 1 : 0;
+      g.has_res = res ? 1 : 0;
+      g.cout = c.cout;
+      if constexpr (!PLAIN) {
+        g.out_gs = p8<TOut>(out).gs;
+        if (res) g.res_gs = p8<const TOut>(*res).gs;
+      }
+      const cuuint64_t dims[4] = {8, (cuuint64_t)(in.W + 2), (cuuint64_t)(in.H + 2), (cuuint64_t)g.iDp * (CIN / 8)};
+      const cuuint64_t strides[3] = {16, (cuuint64_t)(in.W + 2) * 16, (cuuint64_t)(in.W + 2) * (in.H + 2) * 16};
+      const cuuint32_t box[4] = {8, (cuuint32_t)g.P, (cuuint32_t)(g.R + 2), 1};
+      const cuuint32_t estr[4] = {1, 1, 1, 1};
+      const CUtensorMapDataType dt = std::is_same<TIn, __nv_bfloat16>::value ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+      const CUresult r = tc::encode_tiled_fn()(&tcx.tmap, dt, 4, in.p, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      TDM_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed for " + wkey + " (" + std::to_string((int)r) + ")");
+      it = tc_cache_.emplace(wkey, tcx).first;
+    }
+    const tc::Plan& pl = it->second.plan;
     TOut* op = nullptr;
     float* plain = nullptr;
     const TOut* rp = nullptr;
     if constexpr (PLAIN) {
       plain = (float*)out.p;
     } else {
-      const P8<TOut> po = p8<TOut>(out);
-      g.out_gs = po.gs;
-      op = po.p;
-      if (res) { const P8<const TOut> pr = p8<const TOut>(*res); g.res_gs = pr.gs; rp = pr.p; }
+      op = (TOut*)out.p;
+      if (res) rp = (const TOut*)res->p;
     }
     auto kern = tc::k_conv_tc<TIn, TOut, CIN, NPAD, KD, PLAIN, MODE, HILO>;
     static bool attr_set = false;
@@ -554,7 +635,7 @@ class MvsnetEngine final : public MvsnetIface {
       TDM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
       attr_set = true;
     }
-    kern<<<dim3(pl.grid, c.nsplit), tc::kThreads, pl.smem, stream_>>>(pi.p, (const TIn*)c.bimg, c.bias, rp, op, plain, g);
+    kern<<<dim3(pl.grid, c.nsplit), tc::kThreads, pl.smem, stream_>>>(it->second.tmap, (const TIn*)c.bimg, c.bias, rp, op, plain, pl.g);
   }
 
   struct S2Cache { tc::PlanS2 plan; CUtensorMap tmap; };
@@ -613,7 +694,7 @@ class MvsnetEngine final : public MvsnetIface {
   }
 
   // returns true if the tcgen05 kernel was launched
-  bool conv_tc_dispatch(const DevBuf& bi, const DevConv& c, const DevBuf* rp, const DevBuf& bo, bool relu) {
+  bool conv_tc_dispatch(const std::string& wkey, const DevBuf& bi, const DevConv& c, const DevBuf* rp, const DevBuf& bo, bool relu) {
     if constexpr (sizeof(TA) != 2) {
       return false;
     } else {
@@ -621,18 +702,18 @@ class MvsnetEngine final : public MvsnetIface {
       if (is3d != (bi.pd == 1)) return false;
       if (c.tc_deconv) {
         if (bo.D != 2 * bi.D || bo.H != 2 * bi.H || bo.W != 2 * bi.W || bi.kind != 1) return false;
-        if (c.cin == 16) { tc_inst<TA, TA, 16, 64, 2, false, 1>(bi, c, rp, bo, relu); return true; }
-        if (c.cin == 32) { tc_inst<TA, TA, 32, 128, 2, false, 1>(bi, c, rp, bo, relu); return true; }
-        if (c.cin == 64) { tc_inst<TA, TA, 64, 64, 2, false, 1>(bi, c, rp, bo, relu); return true; }
+        if (c.cin == 16) { tc_inst<TA, TA, 16, 64, 2, false, 1>(wkey, bi, c, rp, bo, relu); return true; }
+        if (c.cin == 32) { tc_inst<TA, TA, 32, 128, 2, false, 1>(wkey, bi, c, rp, bo, relu); return true; }
+        if (c.cin == 64) { tc_inst<TA, TA, 64, 64, 2, false, 1>(wkey, bi, c, rp, bo, relu); return true; }
         return false;
       }
 #define TDM_TC(TI, CI, NP, KDV, HL)                                                        \
   if (c.cin == CI && c.npad == NP && c.kd == KDV && c.hilo == HL) {                        \
-    tc_inst<TI, TA, CI, NP, KDV, false, 0, HL>(bi, c, rp, bo, relu);                       \
+    tc_inst<TI, TA, CI, NP, KDV, false, 0, HL>(wkey, bi, c, rp, bo, relu);                       \
     return true;                                                                           \
   }
       if (bo.f32) {
-        if (c.cin == 8 && c.cout == 1 && c.kd == 3 && bi.kind == 1 && c.hilo) { tc_inst<TA, TA, 8, 16, 3, true, 0, true>(bi, c, nullptr, bo, false); return true; }
+        if (c.cin == 8 && c.cout == 1 && c.kd == 3 && bi.kind == 1 && c.hilo) { tc_inst<TA, TA, 8, 16, 3, true, 0, true>(wkey, bi, c, nullptr, bo, false); return true; }
         return false;
       }
       if (bi.kind == 2) {
@@ -646,9 +727,25 @@ class MvsnetEngine final : public MvsnetIface {
     }
   }
 
+  void conv_up2(const std::string& wkey, const std::string& in, const std::string& out) {
+    if constexpr (sizeof(TA) == 2) {
+      const DevConv& c = convs_.at(wkey);
+      const DevBuf& bi = bufs_.at(in);
+      const DevBuf& bo = bufs_.at(out);
+      TDM_CHECK(c.tc_up2 && bo.H == 2 * bi.H && bo.W == 2 * bi.W && bo.D == bi.D, "conv_up2 shape mismatch");
+      rec_begin(wkey + "[tc-up2]", (double)bi.alg_bytes + (double)bo.alg_bytes, 2.0 * 9 * 32 * 8 * (double)bo.D * bo.H * bo.W);
+      tc_inst<TA, TA, 32, 32, 1, false, 3, true>(wkey, bi, c, nullptr, bo, false);
+      TDM_CUDA(cudaGetLastError());
+      rec_end();
+    } else {
+      throw Error("conv_up2 needs a 16-bit engine");
+    }
+  }
+
   // stride s* per axis; 2-D convs pass the view axis as D with kd=1.
   void conv(const std::string& wkey, const std::string& in, const std::string& out, int sd, int sh, int sw,
-            bool relu, int res_mode = 0, const std::string& res = "") {
+            bool relu, int res_mode = 0, const std::string& res = "", const std::string& out_b = "",
+            const float* bias_b = nullptr) {
     const DevConv& c = convs_.at(wkey);
     const DevBuf& bi = bufs_.at(in);
     const DevBuf& bo = bufs_.at(out);
@@ -669,7 +766,7 @@ class MvsnetEngine final : public MvsnetIface {
     const DevBuf* rp = res_mode ? &bufs_.at(res) : nullptr;
     if (use_tc_ && c.tc_ok && res_mode != 2 && (c.tc_deconv ? (sd == 2 && sh == 2 && sw == 2) : (sd == 1 && sh == 1 && sw == 1))) {
       rec_begin(wkey + "[tc]", bytes, 2.0 * macs);
-      if (conv_tc_dispatch(bi, c, rp, bo, relu)) {
+      if (conv_tc_dispatch(wkey, bi, c, rp, bo, relu)) {
         TDM_CUDA(cudaGetLastError());
         rec_end();
         return;
@@ -686,9 +783,10 @@ class MvsnetEngine final : public MvsnetIface {
       rec_cancel();
     }
     rec_begin(wkey, bytes, 2.0 * macs);
+    const DevBuf* obp = out_b.empty() ? nullptr : &bufs_.at(out_b);
 #define TDM_CONV_CASE(CI, CO)                                                        \
   if (c.cin == CI && c.cout == CO) {                                                 \
-    conv_inst<TA, TA, CI, CO>(bi, c, rp, bo, g);                                     \
+    conv_inst<TA, TA, CI, CO>(bi, c, rp, bo, g, obp, bias_b);                        \
   } else
     if (bo.f32) {
       TDM_CHECK(c.cin == 8 && c.cout == 1 && bi.kind == 1, "fp32 output only for the prob conv");
@@ -809,10 +907,17 @@ class MvsnetEngine final : public MvsnetIface {
     conv("f.conv2.1", "f.c2_0", "f.c2_1", 1, 1, 1, true);
     conv("f.conv2.2", "f.c2_1", "f.c1", 1, 1, 1, true);
     conv("f.out1", "f.c1", "feat1", 1, 1, 1, false);
-    conv("f.skip2", "f.c2", "f.i2", 1, 1, 1, false, 2, "f.c1");
-    conv("f.out2", "f.i2", "feat2", 1, 1, 1, false);
-    conv("f.skip3", "f.c3", "f.i3", 1, 1, 1, false, 2, "f.i2");
-    conv("f.out3", "f.i3", "feat3", 1, 1, 1, false);
+    if (fused_fpn_ && use_tc_) {
+      conv("f.skip2", "f.c2", "f.i2", 1, 1, 1, false, 2, "f.c1", "f.i2b", d_bs3_);
+      conv("f.out2", "f.i2", "feat2", 1, 1, 1, false);
+      conv_up2("f.out3a", "f.i2b", "feat3");
+      conv("f.out3b", "f.c3", "feat3", 1, 1, 1, false, 1, "feat3");
+    } else {
+      conv("f.skip2", "f.c2", "f.i2", 1, 1, 1, false, 2, "f.c1");
+      conv("f.out2", "f.i2", "feat2", 1, 1, 1, false);
+      conv("f.skip3", "f.c3", "f.i3", 1, 1, 1, false, 2, "f.i2");
+      conv("f.out3", "f.i3", "feat3", 1, 1, 1, false);
+    }
 
     for (int s = 1; s <= 3; ++s) {
       const std::string k = "s" + std::to_string(s) + ".";
@@ -870,13 +975,13 @@ class MvsnetEngine final : public MvsnetIface {
       std::string err;
       try {
         const size_t n = (size_t)H_ * W_;
-        TDM_CUDA(cudaMemcpyAsync(d_bgr_, h_bgr_, (size_t)V_ * n * 3, cudaMemcpyHostToDevice, stream_));
         forward(false);
-        TDM_CUDA(cudaMemcpyAsync(h_out_, fbuf("s3.depth"), n * 4, cudaMemcpyDeviceToHost, stream_));
-        TDM_CUDA(cudaMemcpyAsync(h_out_ + n, fbuf("s3.confidence"), n * 4, cudaMemcpyDeviceToHost, stream_));
-        TDM_CUDA(cudaMemcpyAsync(h_out_ + 2 * n, fbuf("s3.depth_dense"), n * 4, cudaMemcpyDeviceToHost, stream_));
-        TDM_CUDA(cudaMemcpyAsync(h_out_ + 3 * n, fbuf("s3.confidence_dense"), n * 4, cudaMemcpyDeviceToHost, stream_));
-        TDM_CUDA(cudaStreamSynchronize(stream_));
+        const char* names[4] = {"s3.depth", "s3.confidence", "s3.depth_dense", "s3.confidence_dense"};
+        for (int k = 0; k < 4; ++k) {
+          TDM_CUDA(cudaMemcpyAsync(h_out_ + k * n, fbuf(names[k]), n * 4, cudaMemcpyDeviceToHost, stream_));
+          TDM_CUDA(cudaEventRecord(ev_out_[k], stream_));
+        }
+        TDM_CUDA(cudaEventSynchronize(ev_out_[0]));   // result "ready" as soon as the first map is home; GetResult waits per map
       } catch (const std::exception& e) {
         err = e.what();
       }
@@ -906,9 +1011,12 @@ class MvsnetEngine final : public MvsnetIface {
   unsigned char* h_bgr_ = nullptr;
   unsigned char* d_bgr_ = nullptr;
   float* h_out_ = nullptr;
+  cudaEvent_t ev_out_[4] = {nullptr, nullptr, nullptr, nullptr};
   float c2w_[kMaxSrc + 1][16];
   float K_[27];
   float dmin_ = 0, dmax_ = 0, discard_ = 0;
+  float* d_bs3_ = nullptr;
+  bool fused_fpn_ = false;
   bool filter_all_ = false, keep_ = true, use_tc_ = (sizeof(TA) == 2);  // tcgen05 convs are the default on 16-bit engines
   bool profiling_ = false;
   int launch_count_ = 0, launches_per_forward_ = 0;

@@ -76,7 +76,8 @@ template <typename TIn, typename TOut, int CIN, int COUT, int COUT_T = COUT>
 __global__ void __launch_bounds__(128)
 k_conv_direct(const P8<const TIn> in, const float* __restrict__ wgt /*[taps][CIN][COUT]*/,
               const float* __restrict__ bias /*[COUT] or null*/, const P8<const TOut> res,
-              const P8<TOut> out, float* __restrict__ plain_out /*COUT==1: fp32 [D][H][W]*/, ConvGeom g) {
+              const P8<TOut> out, float* __restrict__ plain_out /*COUT==1: fp32 [D][H][W]*/, ConvGeom g,
+              const P8<TOut> out_b = P8<TOut>{}, const float* __restrict__ bias_b = nullptr /*optional 2nd output = out + bias_b*/) {
   constexpr int SLICE = CIN * COUT_T;
   constexpr int TAPS_PER_STAGE = (SLICE >= 4096) ? 1 : (4096 / SLICE);
   __shared__ __align__(16) float ws[TAPS_PER_STAGE * SLICE];
@@ -170,6 +171,11 @@ k_conv_direct(const P8<const TIn> in, const float* __restrict__ wgt /*[taps][CIN
 #pragma unroll
       for (int c = 0; c < 8; ++c) o8[c] = acc[c0 + c];
       store_vec<TOut, 8>(out.p + op + ((co0 + c0) >> 3) * out.gs, o8);
+      if (bias_b) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) o8[c] += bias_b[co0 + c0 + c];
+        store_vec<TOut, 8>(out_b.p + op + ((co0 + c0) >> 3) * out_b.gs, o8);
+      }
     }
   }
 }

@@ -85,6 +85,10 @@ class DrFusion:
             depths.append(d)
         return bgrs, depths
 
+    def set_slab(self, z_block_lo, z_block_hi):
+        """Multi-GPU extension: keep only voxel blocks with z_block_lo <= z < z_block_hi (see include/tandem_b200.h)."""
+        check(lib().tdm_fusion_set_slab(self._h, int(z_block_lo), int(z_block_hi)))
+
     def Synchronize(self):
         check(lib().tdm_fusion_synchronize(self._h))
 

@@ -35,3 +35,49 @@ def aggregate_throughput(dist, units_done: int, elapsed_ms: float, device="cpu")
     (total,) = reduce_sum(dist, [units_done], device)
     (ms,) = reduce_max(dist, [elapsed_ms], device)
     return total / (ms / 1e3)
+
+
+# ---- TSDF Z-slab partition --------------------------------------------------------------------------
+
+def slab_bounds(z_block_min: int, z_block_max: int, rank: int, world: int, halo: int = 1):
+    """Blocks z in [z_block_min, z_block_max) are split into `world` contiguous slabs.  Returns (owned_lo, owned_hi,
+    alloc_lo, alloc_hi): the rank OWNS [owned_lo, owned_hi) and additionally integrates `halo` blocks on either side so
+    that trilinear reads near the slab faces see the same voxels as a single-volume run."""
+    n = z_block_max - z_block_min
+    lo = z_block_min + (n * rank) // world
+    hi = z_block_min + (n * (rank + 1)) // world
+    return lo, hi, lo - halo, hi + halo
+
+
+def pack_hits(depth, bgr):
+    """(depth f32 (H,W), bgr u8 (H,W,3)) -> int64 keys ordered by depth; a miss (depth == 0) becomes +inf.
+    Positive IEEE floats order like their bit patterns, so min over keys == nearest hit, colour rides along."""
+    import numpy as np
+    d = np.ascontiguousarray(depth, np.float32)
+    bits = d.view(np.uint32).astype(np.int64)
+    bits = np.where(d > 0, bits, np.int64(0x7F800000))
+    col = (bgr[..., 0].astype(np.int64) | (bgr[..., 1].astype(np.int64) << 8) | (bgr[..., 2].astype(np.int64) << 16))
+    return (bits << 24) | col
+
+
+def unpack_hits(keys):
+    import numpy as np
+    bits = (keys >> 24).astype(np.uint32)
+    depth = bits.view(np.float32).copy()
+    depth[bits == 0x7F800000] = 0.0
+    col = keys & 0xFFFFFF
+    bgr = np.stack([(col & 0xFF), (col >> 8) & 0xFF, (col >> 16) & 0xFF], -1).astype(np.uint8)
+    bgr[depth == 0] = 0
+    return depth, bgr
+
+
+def reduce_nearest_hit(dist, depth, bgr, device="cpu"):
+    """The one exchange step of the slab-partitioned ray-cast: per-pixel nearest hit over ranks (all-reduce MIN of packed
+    keys, 2.46 MB at 640x480).  Valid because z-depth is monotone along a ray and the slabs are disjoint."""
+    import torch
+    keys = pack_hits(depth, bgr)
+    if dist is None:
+        return unpack_hits(keys)
+    t = torch.from_numpy(keys).to(device)
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    return unpack_hits(t.cpu().numpy())
