@@ -482,7 +482,9 @@ inline Plan make_plan(int cin, int npad, int kd, int D, int H, int W, int pd, in
   //        x wave quantisation on 148 SMs (one CTA per SM: time ~ ceil(T/148) tile-times for T tiles)
   double best_cost = 1e30;
   int bestR = 0, bestTW = 0, bestS = 0, bestDR = 0;
-  const int s_hi = kd == 3 ? 4 : 3, s_lo = kd == 3 ? 3 : 2;   // kd == 2 (deconv): 3 slots = 2 live + 1 prefetch
+  // mode 4 = input-stationary 3-D kernel (conv_tc_is.cuh): an input plane is consumed once -> ring of 3; its TMEM ring
+  // holds 4 plane accumulators per chunk
+  const int s_hi = mode == 4 ? 3 : (kd == 3 ? 4 : 3), s_lo = mode == 4 ? 3 : (kd == 3 ? 3 : 2);   // kd == 2 (deconv): 2 live + 1 prefetch
   for (int S = s_hi; S >= s_lo; --S) {
     for (int tiles_w = 1; tiles_w <= 20; ++tiles_w) {
       const int TW = (W + tiles_w - 1) / tiles_w;
@@ -494,7 +496,7 @@ inline Plan make_plan(int cin, int npad, int kd, int D, int H, int W, int pd, in
         const int nch = (R * P + 127) / 128;
         const int slot_pos = (std::max((R + 2) * P, nch * 128 + 2 * P + 2) + 8 + 7) / 8 * 8;
         const size_t smem = bbytes + (size_t)S * cg * slot_pos * 16 + 256;
-        if (smem > smem_limit || 2 * nch * npad > 512) break;
+        if (smem > smem_limit || (mode == 4 ? 4 : 2) * nch * npad > 512) break;
         const int th_n = (H + R - 1) / R;
         for (int dsplit = 1; dsplit <= D; ++dsplit) {
           const int DR = (D + dsplit - 1) / dsplit;

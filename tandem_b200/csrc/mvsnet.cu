@@ -18,10 +18,12 @@
 #include <thread>
 #include <vector>
 
+#include "copy_pool.h"
 #include "mvsnet.h"
 #include "mvsnet_kernels.cuh"
 #include "conv_tc.cuh"
 #include "conv_tc_s2.cuh"
+#include "conv_tc_is.cuh"
 #include "weights.h"
 
 namespace tdm {
@@ -92,6 +94,7 @@ struct DevConv {
   bool tc_deconv = false;  // transposed conv evaluated as a GEMM over the input grid (N = 8 parity classes x cout)
   int nsplit = 1;          // N slices (blockIdx.y) for the 64-channel layers
   bool hilo = false;       // weights carried as hi + lo 16-bit halves (N doubled), see conv_tc.cuh
+  void* bimg_is = nullptr; // input-stationary B image (3-D stride-1 convs), conv_tc_is.cuh
   bool tc_up2 = false;     // MODE 3: conv3x3 of a nearest-x2 up-sampled map on the coarse grid (fused FPN tail)
   bool tc_s2 = false;      // stride-2 conv on the tensor-map (strided TMA) kernel, conv_tc_s2.cuh
   void* bimg_s2 = nullptr;
@@ -134,7 +137,7 @@ class MvsnetEngine final : public MvsnetIface {
     if (worker_.joinable()) worker_.join();
     cudaSetDevice(device_);
     free_plan();
-    for (auto& kv : convs_) { cudaFree(kv.second.w); cudaFree(kv.second.bias); cudaFree(kv.second.bimg); cudaFree(kv.second.bimg_s2); }
+    for (auto& kv : convs_) { cudaFree(kv.second.w); cudaFree(kv.second.bias); cudaFree(kv.second.bimg); cudaFree(kv.second.bimg_s2); cudaFree(kv.second.bimg_is); }
     if (select_state_) cudaFree(select_state_);
     if (d_bs3_) cudaFree(d_bs3_);
     for (auto& e : ev_out_) if (e) cudaEventDestroy(e);
@@ -145,6 +148,7 @@ class MvsnetEngine final : public MvsnetIface {
     if (key == "filter_all_stages") filter_all_ = value != 0;
     else if (key == "keep_intermediates") keep_ = value != 0;
     else if (key == "use_tc") use_tc_ = value != 0;
+    else if (key == "use_is") use_is_ = value != 0;
     else throw Error("unknown option " + key);
   }
 
@@ -168,11 +172,30 @@ class MvsnetEngine final : public MvsnetIface {
     const size_t img = (size_t)H * W * 3;
     // The staging copy of view v+1 overlaps the DMA of view v (the worker is idle here, so this thread may enqueue on
     // the engine's stream); the worker then only launches the forward behind these copies.
-    for (int vi = 0; vi < V; ++vi) {
-      const int view = vi == 0 ? ref_index : (vi <= ref_index ? vi - 1 : vi);
-      std::memcpy(h_bgr_ + (size_t)vi * img, bgrs[view], img);
-      TDM_CUDA(cudaMemcpyAsync(d_bgr_ + (size_t)vi * img, h_bgr_ + (size_t)vi * img, img, cudaMemcpyHostToDevice, stream_));
-      std::memcpy(c2w_[vi], c2ws[view], 16 * sizeof(float));
+    // Each view is split into slices copied by the pool; a slice's H2D is enqueued by whichever thread finished copying it
+    // (CUDA stream calls are thread-safe; the order of the DMAs inside the stream does not matter, the forward is
+    // enqueued behind all of them).
+    {
+      std::vector<CopyPool::Job> jobs;
+      constexpr int kSlices = 2;
+      std::mutex err_mu;
+      cudaError_t first_err = cudaSuccess;
+      for (int vi = 0; vi < V; ++vi) {
+        const int view = vi == 0 ? ref_index : (vi <= ref_index ? vi - 1 : vi);
+        std::memcpy(c2w_[vi], c2ws[view], 16 * sizeof(float));
+        for (int sl = 0; sl < kSlices; ++sl) {
+          const size_t b0 = img * sl / kSlices, b1 = img * (sl + 1) / kSlices;
+          unsigned char* hp = h_bgr_ + (size_t)vi * img + b0;
+          unsigned char* dp = d_bgr_ + (size_t)vi * img + b0;
+          jobs.push_back({hp, bgrs[view] + b0, b1 - b0, [this, hp, dp, b0, b1, &err_mu, &first_err] {
+                            cudaSetDevice(device_);   // pool threads start on device 0
+                            const cudaError_t e = cudaMemcpyAsync(dp, hp, b1 - b0, cudaMemcpyHostToDevice, stream_);
+                            if (e != cudaSuccess) { std::lock_guard<std::mutex> lk(err_mu); first_err = e; }
+                          }});
+        }
+      }
+      pool_.run(jobs);
+      TDM_CUDA(first_err);
     }
     std::memcpy(K_, K3x3x3, 27 * sizeof(float));
     dmin_ = dmin; dmax_ = dmax; discard_ = discard;
@@ -198,9 +221,18 @@ class MvsnetEngine final : public MvsnetIface {
     if (!has_result_) throw Error("GetResult without a pending result (dr_mvsnet.cpp:100-102)");
     const size_t n = (size_t)H_ * W_;
     float* dst[4] = {depth, conf, depth_dense, conf_dense};
-    for (int k = 0; k < 4; ++k) {   // the copy of map k into caller memory overlaps the D2H of map k+1
-      TDM_CUDA(cudaEventSynchronize(ev_out_[k]));
-      if (dst[k]) std::memcpy(dst[k], h_out_ + k * n, n * 4);
+    {
+      // each map is copied to caller memory by the pool as soon as its D2H has landed (the D2H of map k+1 overlaps)
+      std::vector<CopyPool::Job> jobs;
+      TDM_CUDA(cudaEventSynchronize(ev_out_[3]));   // 4.9 MB over PCIe: ~0.1 ms; simpler than per-map hand-off
+      constexpr int kSlices = 2;
+      for (int k = 0; k < 4; ++k)
+        if (dst[k])
+          for (int sl = 0; sl < kSlices; ++sl) {
+            const size_t e0 = n * sl / kSlices, e1 = n * (sl + 1) / kSlices;
+            jobs.push_back({dst[k] + e0, h_out_ + k * n + e0, (e1 - e0) * 4, nullptr});
+          }
+      pool_.run(jobs);
     }
     has_result_ = false;
   }
@@ -394,6 +426,14 @@ class MvsnetEngine final : public MvsnetIface {
     else tc::build_b_image<TB, 64>(fc.w.data(), fc.cin, fc.cout, dc.npad, fc.kd, img, +cvt, dc.nsplit);
     TDM_CUDA(cudaMalloc(&dc.bimg, img.size() * sizeof(TB)));
     TDM_CUDA(cudaMemcpy(dc.bimg, img.data(), img.size() * sizeof(TB), cudaMemcpyHostToDevice));
+    if (fc.kd == 3 && fc.cin <= 32 && dc.nsplit == 1) {
+      std::vector<TB> im2;
+      if (fc.cin == 8) tc::build_b_image_is<TB, 8>(fc.w.data(), fc.cin, fc.cout, dc.npad, im2, +cvt, dc.hilo, +back);
+      else if (fc.cin == 16) tc::build_b_image_is<TB, 16>(fc.w.data(), fc.cin, fc.cout, dc.npad, im2, +cvt, dc.hilo, +back);
+      else tc::build_b_image_is<TB, 32>(fc.w.data(), fc.cin, fc.cout, dc.npad, im2, +cvt, dc.hilo, +back);
+      TDM_CUDA(cudaMalloc(&dc.bimg_is, im2.size() * sizeof(TB)));
+      TDM_CUDA(cudaMemcpy(dc.bimg_is, im2.data(), im2.size() * sizeof(TB), cudaMemcpyHostToDevice));
+    }
   }
   template <typename TB> static TB from_host(float v);
   template <typename TB> static float to_host(TB v) { return (float)v; }
@@ -638,6 +678,47 @@ class MvsnetEngine final : public MvsnetIface {
     kern<<<dim3(pl.grid, c.nsplit), tc::kThreads, pl.smem, stream_>>>(it->second.tmap, (const TIn*)c.bimg, c.bias, rp, op, plain, pl.g);
   }
 
+  template <typename TIn, typename TOut, int CIN, int NPAD, bool PLAIN, bool HILO>
+  void tc_is_inst(const std::string& wkey, const DevBuf& in, const DevConv& c, const DevBuf* res, const DevBuf& out, bool relu) {
+    const std::string key = wkey + "#is";
+    auto it = tc_cache_.find(key);
+    if (it == tc_cache_.end()) {
+      TcCache tcx;
+      tcx.plan = tc::make_plan(CIN, HILO ? 2 * NPAD : NPAD, 3, in.D, in.H, in.W, in.pd, 4);
+      tc::Geom& g = tcx.plan.g;
+      g.oHp = out.H + 2; g.oWp = out.W + 2; g.opd = out.pd;
+      g.iDp = in.D + 2 * in.pd;
+      g.in_gs = p8<const TIn>(in).gs;
+      g.relu = relu ? 1 : 0;
+      g.has_res = res ? 1 : 0;
+      g.cout = c.cout;
+      if constexpr (!PLAIN) {
+        g.out_gs = p8<TOut>(out).gs;
+        if (res) g.res_gs = p8<const TOut>(*res).gs;
+      }
+      const cuuint64_t dims[4] = {8, (cuuint64_t)(in.W + 2), (cuuint64_t)(in.H + 2), (cuuint64_t)g.iDp * (CIN / 8)};
+      const cuuint64_t strides[3] = {16, (cuuint64_t)(in.W + 2) * 16, (cuuint64_t)(in.W + 2) * (in.H + 2) * 16};
+      const cuuint32_t box[4] = {8, (cuuint32_t)g.P, (cuuint32_t)(g.R + 2), 1};
+      const cuuint32_t estr[4] = {1, 1, 1, 1};
+      const CUtensorMapDataType dt = std::is_same<TIn, __nv_bfloat16>::value ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+      const CUresult r = tc::encode_tiled_fn()(&tcx.tmap, dt, 4, in.p, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      TDM_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed for " + key);
+      it = tc_cache_.emplace(key, tcx).first;
+    }
+    const tc::Plan& pl = it->second.plan;
+    auto kern = tc::k_conv_tc_is<TIn, TOut, CIN, NPAD, PLAIN, HILO>;
+    static bool attr_set = false;
+    if (!attr_set) {
+      TDM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      attr_set = true;
+    }
+    kern<<<pl.grid, tc::kThreads, pl.smem, stream_>>>(it->second.tmap, (const TIn*)c.bimg_is, c.bias,
+                                                     PLAIN ? nullptr : (res ? (const TOut*)res->p : nullptr),
+                                                     PLAIN ? nullptr : (TOut*)out.p, PLAIN ? (float*)out.p : nullptr, pl.g);
+  }
+
   struct S2Cache { tc::PlanS2 plan; CUtensorMap tmap; };
   std::map<std::string, S2Cache> s2_cache_;
 
@@ -706,6 +787,23 @@ class MvsnetEngine final : public MvsnetIface {
         if (c.cin == 32) { tc_inst<TA, TA, 32, 128, 2, false, 1>(wkey, bi, c, rp, bo, relu); return true; }
         if (c.cin == 64) { tc_inst<TA, TA, 64, 64, 2, false, 1>(wkey, bi, c, rp, bo, relu); return true; }
         return false;
+      }
+      if (use_is_ && c.bimg_is && c.kd == 3) {
+        if (bo.f32) {
+          if (c.cin == 8 && c.cout == 1 && bi.kind == 1 && c.hilo) { tc_is_inst<TA, TA, 8, 16, true, true>(wkey, bi, c, nullptr, bo, false); return true; }
+          return false;
+        }
+#define TDM_IS(TI, CI, NP, HL)                                                             \
+  if (c.cin == CI && c.npad == NP && c.hilo == HL) {                                       \
+    tc_is_inst<TI, TA, CI, NP, false, HL>(wkey, bi, c, rp, bo, relu);                      \
+    return true;                                                                           \
+  }
+        if (bi.kind == 2) {
+          TDM_IS(TV, 32, 16, true) TDM_IS(TV, 16, 16, true) TDM_IS(TV, 8, 16, true)
+        } else {
+          TDM_IS(TA, 16, 16, true) TDM_IS(TA, 32, 32, false)
+        }
+#undef TDM_IS
       }
 #define TDM_TC(TI, CI, NP, KDV, HL)                                                        \
   if (c.cin == CI && c.npad == NP && c.kd == KDV && c.hilo == HL) {                        \
@@ -838,7 +936,7 @@ class MvsnetEngine final : public MvsnetIface {
     rec_begin(k + "cost_volume", (double)fb.alg_bytes + (double)vb.alg_bytes + (s > 1 ? 4.0 * vb.H * vb.W : 0.0),
               (double)n * p.nsrc * fb.C * 12.0);
     const float* dm = s > 1 ? fbuf(k + "dmin") : nullptr;
-    if (fb.C == 32) k_cost_volume<TA, TV, 32><<<cdiv(n, 128), 128, 0, stream_>>>(p8<const TA>(fb), dm, p8<TV>(vb), p);
+    if (fb.C == 32) k_cost_volume<TA, TV, 16, 2><<<cdiv(2 * n, 128), 128, 0, stream_>>>(p8<const TA>(fb), dm, p8<TV>(vb), p);
     else if (fb.C == 16) k_cost_volume<TA, TV, 16><<<cdiv(n, 128), 128, 0, stream_>>>(p8<const TA>(fb), dm, p8<TV>(vb), p);
     else if (fb.C == 8) k_cost_volume<TA, TV, 8><<<cdiv(n, 128), 128, 0, stream_>>>(p8<const TA>(fb), dm, p8<TV>(vb), p);
     else throw Error("unsupported feature channels");
@@ -1012,10 +1110,12 @@ class MvsnetEngine final : public MvsnetIface {
   unsigned char* d_bgr_ = nullptr;
   float* h_out_ = nullptr;
   cudaEvent_t ev_out_[4] = {nullptr, nullptr, nullptr, nullptr};
+  CopyPool pool_{3};   // + the calling thread = 4 copy lanes
   float c2w_[kMaxSrc + 1][16];
   float K_[27];
   float dmin_ = 0, dmax_ = 0, discard_ = 0;
   float* d_bs3_ = nullptr;
+  bool use_is_ = true;   // input-stationary kernel for the 3-D stride-1 convs
   bool fused_fpn_ = false;
   bool filter_all_ = false, keep_ = true, use_tc_ = (sizeof(TA) == 2);  // tcgen05 convs are the default on 16-bit engines
   bool profiling_ = false;
