@@ -140,12 +140,25 @@ class MvsnetEngine final : public MvsnetIface {
     for (auto& kv : convs_) { cudaFree(kv.second.w); cudaFree(kv.second.bias); cudaFree(kv.second.bimg); cudaFree(kv.second.bimg_s2); cudaFree(kv.second.bimg_is); }
     if (select_state_) cudaFree(select_state_);
     if (d_bs3_) cudaFree(d_bs3_);
+    if (h_params_) cudaFreeHost(h_params_);
+    if (d_params_) cudaFree(d_params_);
     for (auto& e : ev_out_) if (e) cudaEventDestroy(e);
     if (stream_) cudaStreamDestroy(stream_);
   }
 
   void set_option(const std::string& key, int value) override {
+    drop_graph();
     if (key == "filter_all_stages") filter_all_ = value != 0;
+    else if (key == "use_graph") use_graph_ = value != 0;
+    else if (key.rfind("depth_num_stage", 0) == 0 && key.size() == 16 && key[15] >= '1' && key[15] <= '3') {
+      // override the checkpoint's MODEL.DEPTH_NUM for one stage (BASELINE.json configs[0] uses 32 stage-1 hypotheses;
+      // CostRegNet is fully convolutional in D).  Forces a re-plan.
+      TDM_CHECK(value == 4 || (value > 0 && value % 8 == 0 && value <= 64), "depth_num must be 4 or a multiple of 8 up to 64");
+      depth_num_[key[15] - '1'] = value;
+      std::unique_lock<std::mutex> lk(mu_);
+      cv_done_.wait(lk, [this] { return !busy_; });
+      V_ = H_ = W_ = 0;   // ensure_plan rebuilds
+    }
     else if (key == "keep_intermediates") keep_ = value != 0;
     else if (key == "use_tc") use_tc_ = value != 0;
     else if (key == "use_is") use_is_ = value != 0;
@@ -487,6 +500,8 @@ class MvsnetEngine final : public MvsnetIface {
       }
     }
     TDM_CUDA(cudaMalloc(&select_state_, sizeof(SelectState)));
+    TDM_CUDA(cudaMallocHost(&h_params_, sizeof(CallParams)));
+    TDM_CUDA(cudaMalloc(&d_params_, sizeof(CallParams)));
   }
 
   // ---------------------------------------------------------------- buffers
@@ -520,6 +535,7 @@ class MvsnetEngine final : public MvsnetIface {
     return t;
   }
   void free_plan() {
+    drop_graph();
     s2_cache_.clear();
     tc_cache_.clear();
     for (auto& kv : bufs_) cudaFree(kv.second.p);
@@ -905,11 +921,10 @@ class MvsnetEngine final : public MvsnetIface {
     rec_end();
   }
 
-  void cost_volume(int s) {
+  // host side of K1: homographies H = K [R|t]_s^-1 (K [R|t]_r^-1)^-1 in double (module.py:795-808)
+  void fill_cv_params(int s, CvParams& p) {
     const std::string k = "s" + std::to_string(s) + ".";
-    const DevBuf& fb = bufs_.at("feat" + std::to_string(s));
     const DevBuf& vb = bufs_.at(k + "volume");
-    CvParams p;
     std::memset(&p, 0, sizeof(p));
     p.nsrc = V_ - 1; p.D = vb.D; p.H = vb.H; p.W = vb.W;
     const float* K = K_ + 9 * (s - 1);
@@ -932,9 +947,35 @@ class MvsnetEngine final : public MvsnetIface {
       p.gb1 = g.b1; p.gw2 = g.w2; p.gb2 = g.b2;
     }
     p.hyp = hyp_spec(s);
+  }
+
+  // everything that depends on the call's poses / depth range / discard percentage -> one pinned struct -> one H2D
+  void upload_call_params() {
+    for (int s = 1; s <= 3; ++s) {
+      fill_cv_params(s, h_params_->cv[s - 1]);
+      const HypSpec hs = hyp_spec(s);
+      h_params_->hyp[s - 1] = hs;
+      h_params_->half_range[s - 1] = ((float)hs.D / 2.f) * hs.interval;
+      const DevBuf& d = bufs_.at("s" + std::to_string(s) + ".depth_dense");
+      const int n = d.H * d.W;
+      // cutoff_index = trunc(H*W*(100-p)/100) in fp32, clamped (module.py:1347-1348)
+      const float cf = (float)n * (100.0f - discard_) / 100.0f;
+      long long cutoff = (long long)cf;
+      cutoff = std::max(0ll, std::min((long long)n - 1, cutoff));
+      h_params_->cutoff[s - 1] = (unsigned)cutoff;
+    }
+    TDM_CUDA(cudaMemcpyAsync(d_params_, h_params_, sizeof(CallParams), cudaMemcpyHostToDevice, stream_));
+  }
+
+  void cost_volume(int s) {
+    const std::string k = "s" + std::to_string(s) + ".";
+    const DevBuf& fb = bufs_.at("feat" + std::to_string(s));
+    const DevBuf& vb = bufs_.at(k + "volume");
+    const CvParams* p = &d_params_->cv[s - 1];
+    const int nsrc = V_ - 1;
     const long long n = (long long)vb.D * vb.H * vb.W;
     rec_begin(k + "cost_volume", (double)fb.alg_bytes + (double)vb.alg_bytes + (s > 1 ? 4.0 * vb.H * vb.W : 0.0),
-              (double)n * p.nsrc * fb.C * 12.0);
+              (double)n * nsrc * fb.C * 12.0);
     const float* dm = s > 1 ? fbuf(k + "dmin") : nullptr;
     if (fb.C == 32) k_cost_volume<TA, TV, 16, 2><<<cdiv(2 * n, 128), 128, 0, stream_>>>(p8<const TA>(fb), dm, p8<TV>(vb), p);
     else if (fb.C == 16) k_cost_volume<TA, TV, 16><<<cdiv(n, 128), 128, 0, stream_>>>(p8<const TA>(fb), dm, p8<TV>(vb), p);
@@ -959,15 +1000,11 @@ class MvsnetEngine final : public MvsnetIface {
     const std::string k = "s" + std::to_string(s) + ".";
     const DevBuf& d = bufs_.at(k + "depth_dense");
     const int n = d.H * d.W;
-    // cutoff_index = trunc(H*W*(100-p)/100) in fp32, clamped (module.py:1347-1348)
-    const float cf = (float)n * (100.0f - discard_) / 100.0f;
-    long long cutoff = (long long)cf;
-    cutoff = std::max(0ll, std::min((long long)n - 1, cutoff));
     rec_begin(k + "edge_metric", 8.0 * n, 0);
     k_edge_metric<<<cdiv(n, 128), 128, 0, stream_>>>(fbuf(k + "depth_dense"), fbuf(k + "edge"), d.H, d.W);
     rec_end();
     rec_begin(k + "percentile", 12.0 * n, 0);
-    k_select_init<<<1, 256, 0, stream_>>>(select_state_, (unsigned)cutoff);
+    k_select_init<<<1, 256, 0, stream_>>>(select_state_, &d_params_->cutoff[s - 1]);
     for (int pass = 0; pass < 3; ++pass) {
       k_select_hist<<<std::min(cdiv(n, 256 * 8), 592), 256, 0, stream_>>>(fbuf(k + "edge"), n, select_state_, pass);
       k_select_scan<<<1, 1024, 0, stream_>>>(select_state_, pass, fbuf("thr") + (s - 1));
@@ -982,8 +1019,36 @@ class MvsnetEngine final : public MvsnetIface {
     rec_end();
   }
 
-  // The whole graph of cva_mvsnet.py:98-184 on stream_, inputs already in d_bgr_.
+  // Per-call parameters are refreshed in device memory, then the (otherwise argument-invariant) kernel sequence is
+  // replayed as a CUDA graph: captured on the second forward of a plan (the first one warms the tensor-map / attribute
+  // caches), invalidated by free_plan() and by option changes.
   void forward(bool profiling) {
+    upload_call_params();
+    if (profiling || !use_graph_) { forward_launches(profiling); return; }
+    if (graph_exec_) { TDM_CUDA(cudaGraphLaunch(graph_exec_, stream_)); return; }
+    if (!warmed_) { forward_launches(false); warmed_ = true; return; }
+    cudaGraph_t graph = nullptr;
+    TDM_CUDA(cudaStreamBeginCapture(stream_, cudaStreamCaptureModeThreadLocal));
+    try {
+      forward_launches(false);
+    } catch (...) {
+      cudaStreamEndCapture(stream_, &graph);
+      if (graph) cudaGraphDestroy(graph);
+      throw;
+    }
+    TDM_CUDA(cudaStreamEndCapture(stream_, &graph));
+    TDM_CUDA(cudaGraphInstantiate(&graph_exec_, graph, 0));
+    cudaGraphDestroy(graph);
+    TDM_CUDA(cudaGraphLaunch(graph_exec_, stream_));
+  }
+  void drop_graph() {
+    if (graph_exec_) cudaGraphExecDestroy(graph_exec_);
+    graph_exec_ = nullptr;
+    warmed_ = false;
+  }
+
+  // The whole graph of cva_mvsnet.py:98-184 on stream_, inputs already in d_bgr_.
+  void forward_launches(bool profiling) {
     profiling_ = profiling;
     launch_count_ = 0;
     const int V = V_, H = H_, W = W_;
@@ -1025,7 +1090,7 @@ class MvsnetEngine final : public MvsnetIface {
         const DevBuf& pd = bufs_.at("s" + std::to_string(s - 1) + ".depth_dense");
         rec_begin(k + "adaptive_dmin", 4.0 * (pd.H * pd.W + dd.H * dd.W), 0);
         k_adaptive_dmin<<<cdiv(dd.H * dd.W, 256), 256, 0, stream_>>>((const float*)pd.p, pd.H, pd.W, fbuf(k + "dmin"),
-                                                                    ((float)hs.D / 2.f) * hs.interval);
+                                                                    &d_params_->half_range[s - 1]);
         TDM_CUDA(cudaGetLastError());
         rec_end();
       }
@@ -1047,9 +1112,9 @@ class MvsnetEngine final : public MvsnetIface {
         const int HW = dd.H * dd.W;
         rec_begin(k + "regress", 4.0 * HW * (hs.D + 3), 0);
         const float* dm = s > 1 ? fbuf(k + "dmin") : nullptr;
-        if (hs.D <= 8) k_regress<8><<<cdiv(HW, 128), 128, 0, stream_>>>(fbuf(k + "logits"), dm, fbuf(k + "depth_dense"), fbuf(k + "confidence_dense"), HW, hs);
-        else if (hs.D <= 32) k_regress<32><<<cdiv(HW, 128), 128, 0, stream_>>>(fbuf(k + "logits"), dm, fbuf(k + "depth_dense"), fbuf(k + "confidence_dense"), HW, hs);
-        else if (hs.D <= 64) k_regress<64><<<cdiv(HW, 128), 128, 0, stream_>>>(fbuf(k + "logits"), dm, fbuf(k + "depth_dense"), fbuf(k + "confidence_dense"), HW, hs);
+        if (hs.D <= 8) k_regress<8><<<cdiv(HW, 128), 128, 0, stream_>>>(fbuf(k + "logits"), dm, fbuf(k + "depth_dense"), fbuf(k + "confidence_dense"), HW, &d_params_->hyp[s - 1]);
+        else if (hs.D <= 32) k_regress<32><<<cdiv(HW, 128), 128, 0, stream_>>>(fbuf(k + "logits"), dm, fbuf(k + "depth_dense"), fbuf(k + "confidence_dense"), HW, &d_params_->hyp[s - 1]);
+        else if (hs.D <= 64) k_regress<64><<<cdiv(HW, 128), 128, 0, stream_>>>(fbuf(k + "logits"), dm, fbuf(k + "depth_dense"), fbuf(k + "confidence_dense"), HW, &d_params_->hyp[s - 1]);
         else throw Error("depth_num > 64 unsupported");
         TDM_CUDA(cudaGetLastError());
         rec_end();
@@ -1115,6 +1180,10 @@ class MvsnetEngine final : public MvsnetIface {
   float K_[27];
   float dmin_ = 0, dmax_ = 0, discard_ = 0;
   float* d_bs3_ = nullptr;
+  CallParams* h_params_ = nullptr;   // pinned
+  CallParams* d_params_ = nullptr;
+  cudaGraphExec_t graph_exec_ = nullptr;
+  bool warmed_ = false, use_graph_ = true;
   bool use_is_ = true;   // input-stationary kernel for the 3-D stride-1 convs
   bool fused_fpn_ = false;
   bool filter_all_ = false, keep_ = true, use_tc_ = (sizeof(TA) == 2);  // tcgen05 convs are the default on 16-bit engines

@@ -199,7 +199,8 @@ __device__ __forceinline__ float hyp_value(const HypSpec& h, float dmin_px, int 
 }
 
 __global__ void k_adaptive_dmin(const float* __restrict__ prev /*[h][w]*/, int h, int w,
-                                float* __restrict__ dmin /*[2h][2w]*/, float half_range) {
+                                float* __restrict__ dmin /*[2h][2w]*/, const float* __restrict__ half_range_p) {
+  const float half_range = *half_range_p;
   const int H = 2 * h, W = 2 * w;
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= H * W) return;
@@ -221,6 +222,9 @@ __global__ void k_adaptive_dmin(const float* __restrict__ prev /*[h][w]*/, int h
 // volume is written exactly once; the per-view warped volumes of the reference never exist.
 // ------------------------------------------------------------------------------------------------
 constexpr int kMaxSrc = 15;
+// Per-call parameters (homographies, depth range, filter rank) live in ONE device buffer that is refreshed by a small
+// async copy before every forward, so that the kernel arguments never change and the whole forward replays as a CUDA
+// graph.
 struct CvParams {
   int nsrc, D, H, W;
   float rot[kMaxSrc][9];
@@ -234,10 +238,25 @@ struct CvParams {
 // C = channels handled by ONE thread; CSPLIT adjacent lanes share a voxel and split its channels (C*CSPLIT in total):
 // halves the register footprint of the 32-channel stage (222 -> ~127 regs, 12 % -> 37 % occupancy) at the price of
 // one warp shuffle per view for the gate's dot product and duplicated (cheap) geometry.
+struct CallParams {
+  CvParams cv[3];
+  HypSpec hyp[3];
+  float half_range[3];
+  unsigned cutoff[3];
+};
+
 template <typename T, typename TV, int C, int CSPLIT = 1>
 __global__ void __launch_bounds__(128)
 k_cost_volume(P8<const T> feats /*views on the D axis, ref first*/, const float* __restrict__ dmin_map,
-              P8<TV> vol, const __grid_constant__ CvParams p) {
+              P8<TV> vol, const CvParams* __restrict__ pp /*device copy of the per-call parameters (graph-replayable)*/) {
+  // stage the ~1 KB of per-call parameters in shared memory once per CTA (they are read in the innermost loops)
+  __shared__ CvParams p;
+  {
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(pp);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(&p);
+    for (int k = threadIdx.x; k < (int)(sizeof(CvParams) / 4); k += blockDim.x) dst[k] = src[k];
+  }
+  __syncthreads();
   const long long n = (long long)p.D * p.H * p.W;
   long long i = (blockIdx.x * (long long)blockDim.x + threadIdx.x) / CSPLIT;
   const int part = threadIdx.x % CSPLIT;          // which slice of the channels this lane owns
@@ -388,7 +407,8 @@ k_cost_volume(P8<const T> feats /*views on the D axis, ref first*/, const float*
 // ------------------------------------------------------------------------------------------------
 template <int MAXD>
 __global__ void k_regress(const float* __restrict__ logits /*[D][H][W]*/, const float* __restrict__ dmin_map,
-                          float* __restrict__ depth, float* __restrict__ conf, int HW, HypSpec hyp) {
+                          float* __restrict__ depth, float* __restrict__ conf, int HW, const HypSpec* __restrict__ hyp_p) {
+  const HypSpec hyp = *hyp_p;
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= HW) return;
   const int D = hyp.D;
@@ -458,9 +478,9 @@ struct SelectState {
   unsigned hist[2048];
 };
 
-__global__ void k_select_init(SelectState* st, unsigned k) {
+__global__ void k_select_init(SelectState* st, const unsigned* __restrict__ k) {
   for (int i = threadIdx.x; i < 2048; i += blockDim.x) st->hist[i] = 0;
-  if (threadIdx.x == 0) { st->prefix = 0; st->k = k; }
+  if (threadIdx.x == 0) { st->prefix = 0; st->k = *k; }
 }
 
 // pass p: 0 -> bits 31..21 (11), 1 -> bits 20..10 (11), 2 -> bits 9..0 (10)

@@ -106,3 +106,33 @@ def tracker_case(H=480, W=640, fx=320.0, fy=320.0, cx=319.5, cy=239.5, seed=0, s
                 pc_idepth=(1.0 / z).astype(np.float32), pc_color=dI_r[v, u, 0].astype(np.float32), dInew=dI_n,
                 refToNew=refToNew, ref_exposure=1.0, new_exposure=1.05, ref_aff=np.array([0.01, 1.5]),
                 new_aff=np.array([0.03 + 0.001 * rng.standard_normal(), -0.8]), cutoffTH=20.0)
+
+
+def mvs_plane_window(V=4, H=256, W=320, f=300.0, z_plane=2.0, baseline=0.05, seed=0):
+    """BASELINE.json configs[0] shaped input: V views of a textured fronto-parallel plane at z = z_plane, cameras
+    translated along x by baseline*v (identity rotation), K = [[f,0,(W-1)/2],[0,f,(H-1)/2],[0,0,1]].  The texture is a sum
+    of 8 random 2-D sinusoids per channel evaluated at the plane point each pixel sees, so the views are geometrically
+    consistent.  Returns dict(bgrs [V x (H,W,3) u8], K (3,3) f32, c2ws [V x (4,4) f32], ref_index, depth_min, depth_max)."""
+    rng = np.random.default_rng(seed)
+    cx, cy = (W - 1) / 2.0, (H - 1) / 2.0
+    fr = rng.uniform(2.0, 14.0, (3, 8, 2))
+    ph = rng.uniform(0, 2 * np.pi, (3, 8))
+    am = rng.uniform(0.3, 1.0, (3, 8))
+    v, u = np.mgrid[0:H, 0:W].astype(np.float64)
+    bgrs, c2ws = [], []
+    for k in range(V):
+        tx = baseline * k
+        X = (u - cx) / f * z_plane + tx
+        Y = (v - cy) / f * z_plane
+        img = np.zeros((H, W, 3))
+        for c in range(3):
+            acc = np.zeros((H, W))
+            for j in range(8):
+                acc += am[c, j] * np.sin(fr[c, j, 0] * X + fr[c, j, 1] * Y + ph[c, j])
+            img[..., c] = 0.5 + 0.5 * acc / am[c].sum()
+        bgrs.append(np.clip(np.round(img * 255), 0, 255).astype(np.uint8))
+        T = np.eye(4, dtype=np.float32)
+        T[0, 3] = tx
+        c2ws.append(T)
+    K = np.array([[f, 0, cx], [0, f, cy], [0, 0, 1]], np.float32)
+    return dict(bgrs=bgrs, K=K, c2ws=c2ws, ref_index=V - 2 if V > 2 else 0, depth_min=0.5, depth_max=5.0, z_plane=z_plane)

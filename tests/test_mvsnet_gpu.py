@@ -192,3 +192,60 @@ def test_tcgen05_benchmark_config_abs_rel(golden_full):
     ar = _absrel(g["abl03_stage3_depth_dense"], out.depth_dense)
     print(f"C2 mixed16+tcgen05: Abs Rel {ar:.3e}")
     assert ar < 5e-4
+
+
+def _oracle_window(win, weights, dn_override=None, discard=10.0):
+    w, dn, va = load_tdmw(default_weights(weights))
+    if dn_override:
+        dn = dn_override
+    bgr = np.stack(win["bgrs"])
+    img, order = O.preprocess_bgr(bgr, win["ref_index"])
+    Ks = O.stage_intrinsics_cpp(win["K"])
+    c2w = torch.from_numpy(np.stack(win["c2ws"])[order])
+    with torch.no_grad():
+        return O.forward(w, dn, img, Ks, c2w, win["depth_min"], win["depth_max"], discard, va)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "mixed16"])
+def test_config1_small_window_and_replan(precision):
+    """BASELINE.json configs[0] shape (3 source + 1 reference view, 320x256, 32 stage-1 hypotheses) on a seeded synthetic
+    plane scene through CallAsync (C++-style stage intrinsics), then a second window of a different size and view count
+    on the SAME handle (re-plan), each against the oracle; the plane depth itself is recovered too."""
+    from tandem_b200.synthetic import mvs_plane_window
+    m = DrMvsnet(default_weights("abl03_view_aggregation"), precision=precision)
+    m.set_option("depth_num_stage1", 32)
+    for V, H, W, dn in ((4, 256, 320, (32, 32, 8)), (3, 192, 256, (32, 32, 8)), (2, 96, 128, (32, 32, 8))):
+        win = mvs_plane_window(V=V, H=H, W=W)
+        m.CallAsync(H, W, V, win["ref_index"], win["bgrs"], win["K"], win["c2ws"], win["depth_min"], win["depth_max"], 10.0)
+        out = m.GetResult()
+        ref = _oracle_window(win, "abl03_view_aggregation", dn)
+        d1 = m.stage_output(1, "depth_dense")
+        e1 = float(np.mean(np.abs(d1 - ref[0]["depth_dense"].numpy())))
+        ar = _absrel(ref[2]["depth_dense"].numpy(), out.depth_dense)
+        print(f"V={V} {W}x{H} {precision}: stage-1 mean-abs {e1:.3e} (bar 1e-3*dmax), stage-3 Abs Rel {ar:.3e}")
+        assert e1 <= 1e-3 * win["depth_max"]
+        # the 1e-3 budget is stated for the 7-view benchmark window; with 1-2 source views of a periodic texture the
+        # depth posterior is multi-modal and a few pixels flip mode under 16-bit rounding
+        assert ar < (1e-4 if precision == "fp32" else (1e-3 if V >= 4 else 5e-3))
+        if V >= 3:
+            inner = out.depth_dense[H // 4:-H // 4, W // 4:-W // 4]
+            assert abs(float(np.median(inner)) - win["z_plane"]) < 0.1 * win["z_plane"]
+
+
+def test_argument_errors_and_two_handles():
+    from tandem_b200 import TandemError
+    from tandem_b200.synthetic import mvs_plane_window
+    win = mvs_plane_window(V=3, H=96, W=128)
+    a = DrMvsnet(default_weights("abl03_view_aggregation"), precision="mixed16")
+    b = DrMvsnet(default_weights("abl03_view_aggregation"), precision="mixed16")
+    with pytest.raises(TandemError):   # H, W must be multiples of 32
+        a.CallAsync(100, 128, 3, 1, [np.zeros((100, 128, 3), np.uint8)] * 3, win["K"], win["c2ws"], 0.5, 5.0, 10.0)
+    with pytest.raises(TandemError):   # the same buffer passed for two views (dr_mvsnet.cpp:153-160)
+        a.CallAsync(96, 128, 3, 1, [win["bgrs"][0], win["bgrs"][0], win["bgrs"][2]], win["K"],
+                    [win["c2ws"][0], win["c2ws"][0], win["c2ws"][2]], 0.5, 5.0, 10.0)
+    for h in (a, b):                   # two engines in flight on one GPU
+        h.CallAsync(96, 128, 3, 1, win["bgrs"], win["K"], win["c2ws"], 0.5, 5.0, 10.0)
+    with pytest.raises(TandemError):   # CallAsync over an un-fetched result (dr_mvsnet.cpp:315-318)
+        a.CallAsync(96, 128, 3, 1, win["bgrs"], win["K"], win["c2ws"], 0.5, 5.0, 10.0)
+    ra, rb = a.GetResult(), b.GetResult()
+    assert np.array_equal(ra.depth_dense, rb.depth_dense) and np.array_equal(ra.confidence, rb.confidence)
