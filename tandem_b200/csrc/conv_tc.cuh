@@ -504,9 +504,14 @@ inline Plan make_plan(int cin, int npad, int kd, int D, int H, int W, int pd, in
           const int td_n = (D + DR - 1) / DR;
           const double T = (double)tw_n * th_n * td_n;
           const double amp = (double)(R + 2) / R * (double)P / TW * (kd == 3 ? (double)(DR + 2) / DR : (kd == 2 ? (double)(DR + 1) / DR : 1.0));
-          const double waste = (double)nch * 128 / ((double)R * TW);
-          const double quant = std::ceil(T / 148.0) / (T / 148.0);
-          const double cost = amp * (0.75 + 0.25 * waste) * quant * (S == s_hi ? 1.0 : 1.1);
+          // estimated kernel time in clocks: waves x (per-CTA fixed cost + instruction stream), inflated by halo re-reads.
+          // Measured on B200: ~55 clk per instruction at N <= 64 (operand streaming), more for wide N; ~8.5 k clk per
+          // CTA for prologue (barriers, TMEM alloc, B image), pipeline fill and the last plane's drain.
+          const double clk_mma = mode == 4 ? 40.0 + 0.35 * 3 * npad : (mode == 1 ? 35.0 + 0.45 * npad : 45.0 + 0.35 * npad);
+          const int planes_in = mode == 4 ? DR + 2 : DR;                       // instruction streams per tile
+          const double per_plane = (double)nch * nblk * (mode == 4 ? 1.25 : (double)kd) * clk_mma;
+          const double tile_clk = 8500.0 + planes_in * per_plane;
+          const double cost = std::ceil(T / 148.0) * tile_clk * (1.0 + 0.25 * (amp - 1.0)) * (S == s_hi ? 1.0 : 1.05);
           if (cost < best_cost - 1e-9) { best_cost = cost; bestR = R; bestTW = TW; bestS = S; bestDR = DR; }
           if (T > 4000) break;
         }
@@ -514,6 +519,7 @@ inline Plan make_plan(int cin, int npad, int kd, int D, int H, int W, int pd, in
     }
     if (bestR > 0 && S == s_hi) break;
   }
+  if (bestR == 0 && smem_limit < 225 * 1024) return make_plan(cin, npad, kd, D, H, W, pd, mode, 225 * 1024);   // soft limit
   TDM_CHECK(bestR > 0, "conv_tc: no tile fits shared memory");
   g.S = bestS; g.R = bestR; g.TW = bestTW; g.P = bestTW + 2; g.DR = bestDR;
   g.nch = (g.R * g.P + 127) / 128;

@@ -277,9 +277,9 @@ inline PlanS2 make_plan_s2(int cin, int npad, int kd, int ks, int D, int H, int 
           const double T = (double)tw_n * th_n * td_n;
           const double amp = (double)(2 * R + ks - 2) / (2 * R) * (double)(2 * TW + ks - 2) / (2 * TW) *
                              (kd == 3 ? (double)(2 * DR + 1) / (2 * DR) : 1.0);
-          const double waste = (double)nch * 128 / ((double)R * TW);
-          const double quant = std::ceil(T / 148.0) / (T / 148.0);
-          const double cost = amp * (0.75 + 0.25 * waste) * quant * (S == s_hi ? 1.0 : 1.1);
+          // same time model as conv_tc.cuh::make_plan
+          const double tile_clk = 8500.0 + (double)DR * nch * nblk * kd * (45.0 + 0.35 * npad);
+          const double cost = std::ceil(T / 148.0) * tile_clk * (1.0 + 0.25 * (amp - 1.0)) * (S == s_hi ? 1.0 : 1.05);
           if (cost < best_cost - 1e-9) { best_cost = cost; bR = R; bTW = TW; bS = S; bDR = DR; }
           if (T > 4000) break;
         }
@@ -287,6 +287,7 @@ inline PlanS2 make_plan_s2(int cin, int npad, int kd, int ks, int D, int H, int 
     }
     if (bR > 0 && S == s_hi) break;
   }
+  if (bR == 0 && smem_limit < 225 * 1024) return make_plan_s2(cin, npad, kd, ks, D, H, W, 225 * 1024);   // soft limit
   TDM_CHECK(bR > 0, "conv_tc_s2: no tile fits shared memory");
   g.S = bS; g.R = bR; g.TW = bTW; g.DR = bDR;
   g.P = bTW + hk; g.RR = bR + hk;

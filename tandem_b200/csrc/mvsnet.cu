@@ -30,6 +30,19 @@ namespace tdm {
 
 namespace {
 
+std::mutex g_slot_mu;
+bool g_slot_used[kMaxEngines] = {};
+int acquire_slot() {
+  std::lock_guard<std::mutex> lk(g_slot_mu);
+  for (int i = 0; i < kMaxEngines; ++i)
+    if (!g_slot_used[i]) { g_slot_used[i] = true; return i; }
+  throw Error("too many DrMvsnet instances alive in this process (max 8)");
+}
+void release_slot(int i) {
+  std::lock_guard<std::mutex> lk(g_slot_mu);
+  if (i >= 0 && i < kMaxEngines) g_slot_used[i] = false;
+}
+
 // ---- small host linear algebra (double) --------------------------------------------------------
 void mat4_mul(const double* a, const double* b, double* c) {
   for (int i = 0; i < 4; ++i)
@@ -122,6 +135,7 @@ class MvsnetEngine final : public MvsnetIface {
     int lo, hi;
     TDM_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
     TDM_CUDA(cudaStreamCreateWithPriority(&stream_, cudaStreamNonBlocking, lo));
+    slot_ = acquire_slot();
     for (auto& e : ev_out_) TDM_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     upload_weights();
     worker_ = std::thread([this] { this->loop(); });
@@ -139,6 +153,7 @@ class MvsnetEngine final : public MvsnetIface {
     free_plan();
     for (auto& kv : convs_) { cudaFree(kv.second.w); cudaFree(kv.second.bias); cudaFree(kv.second.bimg); cudaFree(kv.second.bimg_s2); cudaFree(kv.second.bimg_is); }
     if (select_state_) cudaFree(select_state_);
+    release_slot(slot_);
     if (d_bs3_) cudaFree(d_bs3_);
     if (h_params_) cudaFreeHost(h_params_);
     if (d_params_) cudaFree(d_params_);
@@ -150,6 +165,7 @@ class MvsnetEngine final : public MvsnetIface {
     drop_graph();
     if (key == "filter_all_stages") filter_all_ = value != 0;
     else if (key == "use_graph") use_graph_ = value != 0;
+    else if (key == "tc_smem_kb") { TDM_CHECK(value >= 48 && value <= 225, "tc_smem_kb out of range"); tc_smem_kb_ = value; tc_cache_.clear(); s2_cache_.clear(); }
     else if (key.rfind("depth_num_stage", 0) == 0 && key.size() == 16 && key[15] >= '1' && key[15] <= '3') {
       // override the checkpoint's MODEL.DEPTH_NUM for one stage (BASELINE.json configs[0] uses 32 stage-1 hypotheses;
       // CostRegNet is fully convolutional in D).  Forces a re-plan.
@@ -652,7 +668,7 @@ class MvsnetEngine final : public MvsnetIface {
     auto it = tc_cache_.find(wkey);
     if (it == tc_cache_.end()) {
       TcCache tcx;
-      tcx.plan = tc::make_plan(CIN, HILO ? 2 * NPAD : NPAD, KD, in.D, in.H, in.W, in.pd, MODE);   // tiles live on the INPUT grid
+      tcx.plan = tc::make_plan(CIN, HILO ? 2 * NPAD : NPAD, KD, in.D, in.H, in.W, in.pd, MODE, (size_t)tc_smem_kb_ * 1024);   // tiles live on the INPUT grid
       tc::Geom& g = tcx.plan.g;
       g.oHp = out.H + 2; g.oWp = out.W + 2; g.opd = out.pd;
       g.iDp = in.D + 2 * in.pd;
@@ -700,7 +716,7 @@ class MvsnetEngine final : public MvsnetIface {
     auto it = tc_cache_.find(key);
     if (it == tc_cache_.end()) {
       TcCache tcx;
-      tcx.plan = tc::make_plan(CIN, HILO ? 2 * NPAD : NPAD, 3, in.D, in.H, in.W, in.pd, 4);
+      tcx.plan = tc::make_plan(CIN, HILO ? 2 * NPAD : NPAD, 3, in.D, in.H, in.W, in.pd, 4, (size_t)tc_smem_kb_ * 1024);
       tc::Geom& g = tcx.plan.g;
       g.oHp = out.H + 2; g.oWp = out.W + 2; g.opd = out.pd;
       g.iDp = in.D + 2 * in.pd;
@@ -743,7 +759,7 @@ class MvsnetEngine final : public MvsnetIface {
     auto it = s2_cache_.find(wkey);
     if (it == s2_cache_.end()) {
       S2Cache sc;
-      sc.plan = tc::make_plan_s2(CIN, NPAD, KD, KS, out.D, out.H, out.W);
+      sc.plan = tc::make_plan_s2(CIN, NPAD, KD, KS, out.D, out.H, out.W, (size_t)tc_smem_kb_ * 1024);
       tc::GeomS2& g = sc.plan.g;
       const P8<TA> po = p8<TA>(out);
       g.oHp = out.H + 2; g.oWp = out.W + 2; g.opd = out.pd; g.out_gs = po.gs;
@@ -965,21 +981,22 @@ class MvsnetEngine final : public MvsnetIface {
       h_params_->cutoff[s - 1] = (unsigned)cutoff;
     }
     TDM_CUDA(cudaMemcpyAsync(d_params_, h_params_, sizeof(CallParams), cudaMemcpyHostToDevice, stream_));
+    TDM_CUDA(cudaMemcpyToSymbolAsync(c_call_params, h_params_, sizeof(CallParams), (size_t)slot_ * sizeof(CallParams),
+                                     cudaMemcpyHostToDevice, stream_));
   }
 
   void cost_volume(int s) {
     const std::string k = "s" + std::to_string(s) + ".";
     const DevBuf& fb = bufs_.at("feat" + std::to_string(s));
     const DevBuf& vb = bufs_.at(k + "volume");
-    const CvParams* p = &d_params_->cv[s - 1];
     const int nsrc = V_ - 1;
     const long long n = (long long)vb.D * vb.H * vb.W;
     rec_begin(k + "cost_volume", (double)fb.alg_bytes + (double)vb.alg_bytes + (s > 1 ? 4.0 * vb.H * vb.W : 0.0),
               (double)n * nsrc * fb.C * 12.0);
     const float* dm = s > 1 ? fbuf(k + "dmin") : nullptr;
-    if (fb.C == 32) k_cost_volume<TA, TV, 16, 2><<<cdiv(2 * n, 128), 128, 0, stream_>>>(p8<const TA>(fb), dm, p8<TV>(vb), p);
-    else if (fb.C == 16) k_cost_volume<TA, TV, 16><<<cdiv(n, 128), 128, 0, stream_>>>(p8<const TA>(fb), dm, p8<TV>(vb), p);
-    else if (fb.C == 8) k_cost_volume<TA, TV, 8><<<cdiv(n, 128), 128, 0, stream_>>>(p8<const TA>(fb), dm, p8<TV>(vb), p);
+    if (fb.C == 32) k_cost_volume<TA, TV, 16, 2><<<cdiv(2 * n, 128), 128, 0, stream_>>>(p8<const TA>(fb), dm, p8<TV>(vb), slot_, s - 1);
+    else if (fb.C == 16) k_cost_volume<TA, TV, 16><<<cdiv(n, 128), 128, 0, stream_>>>(p8<const TA>(fb), dm, p8<TV>(vb), slot_, s - 1);
+    else if (fb.C == 8) k_cost_volume<TA, TV, 8><<<cdiv(n, 128), 128, 0, stream_>>>(p8<const TA>(fb), dm, p8<TV>(vb), slot_, s - 1);
     else throw Error("unsupported feature channels");
     TDM_CUDA(cudaGetLastError());
     rec_end();
@@ -1184,6 +1201,8 @@ class MvsnetEngine final : public MvsnetIface {
   CallParams* d_params_ = nullptr;
   cudaGraphExec_t graph_exec_ = nullptr;
   bool warmed_ = false, use_graph_ = true;
+  int slot_ = 0;           // index into c_call_params
+  int tc_smem_kb_ = 225;   // shared-memory budget of the tile planner (<= 113 lets two CTAs share an SM)
   bool use_is_ = true;   // input-stationary kernel for the 3-D stride-1 convs
   bool fused_fpn_ = false;
   bool filter_all_ = false, keep_ = true, use_tc_ = (sizeof(TA) == 2);  // tcgen05 convs are the default on 16-bit engines

@@ -245,18 +245,17 @@ struct CallParams {
   unsigned cutoff[3];
 };
 
+// One slot per engine instance (several DrMvsnet handles may be in flight on a device); refreshed stream-ordered with
+// cudaMemcpyToSymbolAsync before each forward.  Constant memory keeps the homographies as uniform operands of the inner
+// loops (measured: reading them through a global pointer or shared memory costs the cost-volume kernel 10-15 %).
+constexpr int kMaxEngines = 8;
+__constant__ CallParams c_call_params[kMaxEngines];
+
 template <typename T, typename TV, int C, int CSPLIT = 1>
 __global__ void __launch_bounds__(128)
 k_cost_volume(P8<const T> feats /*views on the D axis, ref first*/, const float* __restrict__ dmin_map,
-              P8<TV> vol, const CvParams* __restrict__ pp /*device copy of the per-call parameters (graph-replayable)*/) {
-  // stage the ~1 KB of per-call parameters in shared memory once per CTA (they are read in the innermost loops)
-  __shared__ CvParams p;
-  {
-    const uint32_t* src = reinterpret_cast<const uint32_t*>(pp);
-    uint32_t* dst = reinterpret_cast<uint32_t*>(&p);
-    for (int k = threadIdx.x; k < (int)(sizeof(CvParams) / 4); k += blockDim.x) dst[k] = src[k];
-  }
-  __syncthreads();
+              P8<TV> vol, int slot, int stage /*per-call parameters: c_call_params[slot].cv[stage] (graph-replayable)*/) {
+  const CvParams& p = c_call_params[slot].cv[stage];
   const long long n = (long long)p.D * p.H * p.W;
   long long i = (blockIdx.x * (long long)blockDim.x + threadIdx.x) / CSPLIT;
   const int part = threadIdx.x % CSPLIT;          // which slice of the channels this lane owns

@@ -11,6 +11,9 @@ V, H, W = g["bgr"].shape[:3]
 m = DrMvsnet(default_weights("abl03_view_aggregation"), precision=prec)
 if tc >= 0:
     m.set_option("use_tc", tc)
+for kv in sys.argv[3:]:
+    k, v = kv.split("=")
+    m.set_option(k, int(v))
 bgrs = [np.ascontiguousarray(g["bgr"][v]) for v in range(V)]
 c2ws = [np.ascontiguousarray(g["c2w"][v]) for v in range(V)]
 m.CallAsync(H, W, V, int(g["ref_index"]), bgrs, g["K3"], c2ws, float(g["depth_min"]), float(g["depth_max"]), float(g["discard"]))
