@@ -292,7 +292,21 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmap /*P8 input: {8, Wp, Hp, group
         if constexpr (CLASS_EPI) {
           // N = 8 (MODE 1) or 4 (MODE 3) parity classes x COUT: class (pd,ph,pw) of input position (d,h,w) is output (2d+pd, 2h+ph, 2w+pw)
           const int COUT = g.cout;
-#pragma unroll 1
+          // All skip-tensor reads of this row are issued up front (NPAD/8 independent 16-byte loads): with only four
+          // epilogue warps per SM, eight dependent load->add->store round trips per chunk would serialise ~600 clk of
+          // HBM latency each and make the epilogue 20x slower than the MMAs that feed it.
+          uint4 rbuf[NPAD / 8];
+          if (valid && g.has_res) {
+#pragma unroll
+            for (int k = 0; k < NPAD / 8; ++k) {
+              const int n = ns * NPAD + k * 8;
+              const int cls = n / COUT, co = n % COUT;
+              const int od2 = MODE == 1 ? 2 * d + (cls >> 2) : d, oh2 = 2 * h + ((cls >> 1) & 1), ow2 = 2 * w + (cls & 1);
+              const long long pos = ((((long long)(od2 + g.opd)) * g.oHp + (oh2 + 1)) * g.oWp + (ow2 + 1)) * 8;
+              rbuf[k] = __ldg(reinterpret_cast<const uint4*>(res + pos + (co >> 3) * g.res_gs));
+            }
+          }
+#pragma unroll
           for (int n0 = 0; n0 < NPAD; n0 += 16) {
             uint32_t v[16];
             tmem_ld16(t_row + (uint32_t)n0, v);
@@ -317,16 +331,25 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmap /*P8 input: {8, Wp, Hp, group
                   o8[i] = x;
                 }
                 if (g.has_res) {
-                  float r8[8];
-                  load_vec<TOut, 8>(res + pos + (co >> 3) * g.res_gs, r8);
+                  const TOut* rv = reinterpret_cast<const TOut*>(&rbuf[(n0 + k0) / 8]);
 #pragma unroll
-                  for (int i = 0; i < 8; ++i) o8[i] += r8[i];
+                  for (int i = 0; i < 8; ++i) o8[i] += to_f<TOut>(rv[i]);
                 }
                 store_vec<TOut, 8>(out + pos + (co >> 3) * g.out_gs, o8);
               }
             }
           }
         } else {
+          uint4 rbuf[NPAD / 8];
+          const long long pos0 = ((((long long)(d + g.pd)) * g.Hp + (h + 1)) * g.Wp + (w + 1)) * 8;
+          if constexpr (!OUT_PLAIN) {
+            if (valid && g.has_res) {   // skip-tensor reads issued before the TMEM loads (latency overlap)
+#pragma unroll
+              for (int k = 0; k < NPAD / 8; ++k)
+                if (ns * NPAD + k * 8 < g.cout)
+                  rbuf[k] = __ldg(reinterpret_cast<const uint4*>(res + pos0 + ((ns * NPAD + k * 8) >> 3) * g.res_gs));
+            }
+          }
           uint32_t v[16];
           float acc[NPAD];
 #pragma unroll
@@ -357,10 +380,9 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmap /*P8 input: {8, Wp, Hp, group
                     o8[i] = x;
                   }
                   if (g.has_res) {
-                    float r8[8];
-                    load_vec<TOut, 8>(res + pos + (co >> 3) * g.res_gs, r8);
+                    const TOut* rv = reinterpret_cast<const TOut*>(&rbuf[c0 / 8]);
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) o8[i] += r8[i];
+                    for (int i = 0; i < 8; ++i) o8[i] += to_f<TOut>(rv[i]);
                   }
                   store_vec<TOut, 8>(out + pos + (co >> 3) * g.out_gs, o8);
                 }

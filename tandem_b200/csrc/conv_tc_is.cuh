@@ -169,6 +169,15 @@ k_conv_tc_is(const __grid_constant__ CUtensorMap tmap, const TIn* __restrict__ b
         const int h = h0 + hh, w = w0 + ww;
         const bool valid = hh < g.R && ww < g.TW && h < g.H && w < g.W;
         const uint32_t t_row = lane_base + (uint32_t)c * chunk_cols + (uint32_t)r * NMMA;
+        uint4 rbuf[NPAD / 8];
+        const long long pos0 = ((((long long)(d + g.pd)) * g.Hp + (h + 1)) * g.Wp + (w + 1)) * 8;
+        if constexpr (!OUT_PLAIN) {
+          if (valid && g.has_res) {   // skip-tensor reads issued before the TMEM loads (latency overlap)
+#pragma unroll
+            for (int k = 0; k < NPAD / 8; ++k)
+              if (k * 8 < g.cout) rbuf[k] = __ldg(reinterpret_cast<const uint4*>(res + pos0 + k * g.res_gs));
+          }
+        }
         uint32_t v[16];
         float acc[NPAD];
 #pragma unroll
@@ -200,10 +209,9 @@ k_conv_tc_is(const __grid_constant__ CUtensorMap tmap, const TIn* __restrict__ b
                   o8[i] = x;
                 }
                 if (g.has_res) {
-                  float r8[8];
-                  load_vec<TOut, 8>(res + pos + (c0 >> 3) * g.res_gs, r8);
+                  const TOut* rv = reinterpret_cast<const TOut*>(&rbuf[c0 / 8]);
 #pragma unroll
-                  for (int i = 0; i < 8; ++i) o8[i] += r8[i];
+                  for (int i = 0; i < 8; ++i) o8[i] += to_f<TOut>(rv[i]);
                 }
                 store_vec<TOut, 8>(out + pos + (c0 >> 3) * g.out_gs, o8);
               }

@@ -8,6 +8,8 @@
 // memory (6.45 MB instead of 25.8 MB fp32), everything else stays on the device until the four output maps
 // are copied back in one pinned D2H.
 #include <algorithm>
+#include <cstdio>
+#include <cstdlib>
 #include <atomic>
 #include <condition_variable>
 #include <cstring>
@@ -689,6 +691,9 @@ class MvsnetEngine final : public MvsnetIface {
                                                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
       TDM_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed for " + wkey + " (" + std::to_string((int)r) + ")");
+      if (std::getenv("TDM_DEBUG_PLAN"))
+        fprintf(stderr, "[plan] %-14s mode %d cin %d N %d kd %d in %dx%dx%d -> R %d TW %d DR %d S %d nch %d tiles %d x nsplit %d smem %zu\n", wkey.c_str(), MODE, CIN,
+                HILO ? 2 * NPAD : NPAD, KD, in.D, in.H, in.W, g.R, g.TW, g.DR, g.S, g.nch, tcx.plan.grid, c.nsplit, tcx.plan.smem);
       it = tc_cache_.emplace(wkey, tcx).first;
     }
     const tc::Plan& pl = it->second.plan;
@@ -737,6 +742,9 @@ class MvsnetEngine final : public MvsnetIface {
                                                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
       TDM_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed for " + key);
+      if (std::getenv("TDM_DEBUG_PLAN"))
+        fprintf(stderr, "[plan] %-14s IS cin %d N 3x%d in %dx%dx%d -> R %d TW %d DR %d S %d nch %d tiles %d smem %zu\n", key.c_str(), CIN, HILO ? 2 * NPAD : NPAD,
+                in.D, in.H, in.W, g.R, g.TW, g.DR, g.S, g.nch, tcx.plan.grid, tcx.plan.smem);
       it = tc_cache_.emplace(key, tcx).first;
     }
     const tc::Plan& pl = it->second.plan;
@@ -779,6 +787,9 @@ class MvsnetEngine final : public MvsnetIface {
                                                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
       TDM_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed for " + wkey + " (" + std::to_string((int)r) + ")");
+      if (std::getenv("TDM_DEBUG_PLAN"))
+        fprintf(stderr, "[plan] %-14s S2 cin %d N %d kd %d ks %d out %dx%dx%d -> R %d TW %d DR %d S %d nch %d tiles %d x nsplit %d smem %zu\n", wkey.c_str(), CIN, NPAD, KD, KS,
+                out.D, out.H, out.W, g.R, g.TW, g.DR, g.S, g.nch, sc.plan.grid, c.nsplit_s2, sc.plan.smem);
       it = s2_cache_.emplace(wkey, sc).first;
     }
     auto kern = tc::k_conv_tc_s2<TA, TA, CIN, NPAD, KD, KS>;
