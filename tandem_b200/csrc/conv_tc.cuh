@@ -120,6 +120,12 @@ __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* tmap, 
 }
 
 
+// Programmatic dependent launch: a kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start
+// while its predecessor drains; everything before pdl_wait() (barrier init, TMEM allocation, the weight image load)
+// overlaps the predecessor's tail, everything that touches activations comes after it.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 constexpr int kThreads = 256;   // warp 0 TMA, warp 1 MMA (+TMEM alloc), warps 2..5 epilogue, warps 6,7 MMA
 constexpr int kMmaWarps = 3;
 
@@ -184,6 +190,9 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmap /*P8 input: {8, Wp, Hp, group
     for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], kMmaWarps); mbar_init(&acc_empty[b], 4); }
     mbar_init(b_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    mbar_expect_tx(b_full, B_BYTES);          // weights do not depend on the previous kernel: fetch them before pdl_wait
+    bulk_g2s(sB, bimg, B_BYTES, b_full);
+    pdl_launch_dependents();
   }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(tmem_cols) : "memory");
@@ -193,12 +202,11 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmap /*P8 input: {8, Wp, Hp, group
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+  pdl_wait();   // from here on activations written by the previous kernel are read and our outputs are written
 
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      mbar_expect_tx(b_full, B_BYTES);
-      bulk_g2s(sB, bimg, B_BYTES, b_full);
       // one tiled TMA per (plane, channel group): box = (R+2) rows x P positions, rows / columns beyond the tensor are
       // zero-filled by the TMA engine, so partial tiles need no special casing
       const uint32_t box_bytes = (uint32_t)g.P * (uint32_t)(g.R + 2) * 16u;

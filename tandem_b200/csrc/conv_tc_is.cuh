@@ -70,6 +70,9 @@ k_conv_tc_is(const __grid_constant__ CUtensorMap tmap, const TIn* __restrict__ b
     for (int r = 0; r < RS; ++r) { mbar_init(&acc_full[r], kMmaWarps); mbar_init(&acc_empty[r], 4); }
     mbar_init(b_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    mbar_expect_tx(b_full, B_BYTES);          // weights do not depend on the previous kernel: fetch them before pdl_wait
+    bulk_g2s(sB, bimg, B_BYTES, b_full);
+    pdl_launch_dependents();
   }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(tmem_cols) : "memory");
@@ -79,12 +82,11 @@ k_conv_tc_is(const __grid_constant__ CUtensorMap tmap, const TIn* __restrict__ b
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+  pdl_wait();   // from here on activations written by the previous kernel are read and our outputs are written
 
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      mbar_expect_tx(b_full, B_BYTES);
-      bulk_g2s(sB, bimg, B_BYTES, b_full);
       const uint32_t box_bytes = (uint32_t)g.P * (uint32_t)(g.R + 2) * 16u;
       for (int rp = 0; rp < nin; ++rp) {
         const int slot = rp % g.S;

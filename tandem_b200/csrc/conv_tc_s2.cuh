@@ -78,6 +78,9 @@ k_conv_tc_s2(const __grid_constant__ CUtensorMap tmap, const TIn* __restrict__ b
     for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], kMmaWarps); mbar_init(&acc_empty[b], 4); }
     mbar_init(b_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    mbar_expect_tx(b_full, B_BYTES);          // weights do not depend on the previous kernel: fetch them before pdl_wait
+    bulk_g2s(sB, bimg, B_BYTES, b_full);
+    pdl_launch_dependents();
   }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(tmem_cols) : "memory");
@@ -87,12 +90,11 @@ k_conv_tc_s2(const __grid_constant__ CUtensorMap tmap, const TIn* __restrict__ b
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+  pdl_wait();   // from here on activations written by the previous kernel are read and our outputs are written
 
   if (warp == 0) {
     // ===================== TMA producer: 4 parity sub-tiles per channel group per input plane =====================
     if (lane == 0) {
-      mbar_expect_tx(b_full, B_BYTES);
-      bulk_g2s(sB, bimg, B_BYTES, b_full);
       const uint32_t box_bytes = (uint32_t)g.P * (uint32_t)g.RR * 16u;
       const int col0 = 2 * w0 + g.c0, row0 = 2 * h0 + g.c0;
       for (int rp = 0; rp < nin; ++rp) {

@@ -167,6 +167,7 @@ class MvsnetEngine final : public MvsnetIface {
     drop_graph();
     if (key == "filter_all_stages") filter_all_ = value != 0;
     else if (key == "use_graph") use_graph_ = value != 0;
+    else if (key == "use_pdl") use_pdl_ = value != 0;
     else if (key == "tc_smem_kb") { TDM_CHECK(value >= 48 && value <= 225, "tc_smem_kb out of range"); tc_smem_kb_ = value; tc_cache_.clear(); s2_cache_.clear(); }
     else if (key.rfind("depth_num_stage", 0) == 0 && key.size() == 16 && key[15] >= '1' && key[15] <= '3') {
       // override the checkpoint's MODEL.DEPTH_NUM for one stage (BASELINE.json configs[0] uses 32 stage-1 hypotheses;
@@ -662,6 +663,23 @@ class MvsnetEngine final : public MvsnetIface {
     k_conv_direct<TIn, TOut, CIN, COUT><<<cdiv(npos, 128), 128, 0, stream_>>>(p8<const TIn>(in), c.w, c.bias, r, o, plain, g);
   }
 
+  // tensor-core kernels are launched with programmatic stream serialization (PDL): their prologue and weight-image
+  // load overlap the tail of the previous kernel (see pdl_wait() in conv_tc.cuh)
+  template <typename Kern, typename... Args>
+  void launch_pdl(Kern kern, dim3 grid, size_t smem, Args... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(tc::kThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream_;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = use_pdl_ ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    TDM_CUDA(cudaLaunchKernelEx(&cfg, kern, args...));
+  }
+
   struct TcCache { tc::Plan plan; CUtensorMap tmap; };
   std::map<std::string, TcCache> tc_cache_;
 
@@ -712,7 +730,7 @@ class MvsnetEngine final : public MvsnetIface {
       TDM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
       attr_set = true;
     }
-    kern<<<dim3(pl.grid, c.nsplit), tc::kThreads, pl.smem, stream_>>>(it->second.tmap, (const TIn*)c.bimg, c.bias, rp, op, plain, pl.g);
+    launch_pdl(kern, dim3(pl.grid, c.nsplit), pl.smem, it->second.tmap, (const TIn*)c.bimg, (const float*)c.bias, rp, op, plain, pl.g);
   }
 
   template <typename TIn, typename TOut, int CIN, int NPAD, bool PLAIN, bool HILO>
@@ -754,9 +772,9 @@ class MvsnetEngine final : public MvsnetIface {
       TDM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
       attr_set = true;
     }
-    kern<<<pl.grid, tc::kThreads, pl.smem, stream_>>>(it->second.tmap, (const TIn*)c.bimg_is, c.bias,
-                                                     PLAIN ? nullptr : (res ? (const TOut*)res->p : nullptr),
-                                                     PLAIN ? nullptr : (TOut*)out.p, PLAIN ? (float*)out.p : nullptr, pl.g);
+    launch_pdl(kern, dim3(pl.grid, 1), pl.smem, it->second.tmap, (const TIn*)c.bimg_is, (const float*)c.bias,
+               (const TOut*)(PLAIN ? nullptr : (res ? res->p : nullptr)), (TOut*)(PLAIN ? nullptr : out.p),
+               (float*)(PLAIN ? out.p : nullptr), pl.g);
   }
 
   struct S2Cache { tc::PlanS2 plan; CUtensorMap tmap; };
@@ -799,8 +817,7 @@ class MvsnetEngine final : public MvsnetIface {
       attr_set = true;
     }
     const tc::PlanS2& pl = it->second.plan;
-    kern<<<dim3(pl.grid, c.nsplit_s2), tc::kThreads, pl.smem, stream_>>>(it->second.tmap, (const TA*)c.bimg_s2, c.bias,
-                                                                         (TA*)out.p, pl.g);
+    launch_pdl(kern, dim3(pl.grid, c.nsplit_s2), pl.smem, it->second.tmap, (const TA*)c.bimg_s2, (const float*)c.bias, (TA*)out.p, pl.g);
   }
 
   bool conv_tc_s2_dispatch(const std::string& wkey, const DevBuf& bi, const DevConv& c, const DevBuf& bo, bool relu) {
@@ -1211,7 +1228,7 @@ class MvsnetEngine final : public MvsnetIface {
   CallParams* h_params_ = nullptr;   // pinned
   CallParams* d_params_ = nullptr;
   cudaGraphExec_t graph_exec_ = nullptr;
-  bool warmed_ = false, use_graph_ = true;
+  bool warmed_ = false, use_graph_ = true, use_pdl_ = false;   // PDL measured slower (1.86 vs 1.73 ms): dependents squat on SM resources while they wait
   int slot_ = 0;           // index into c_call_params
   int tc_smem_kb_ = 225;   // shared-memory budget of the tile planner (<= 113 lets two CTAs share an SM)
   bool use_is_ = true;   // input-stationary kernel for the 3-D stride-1 convs
