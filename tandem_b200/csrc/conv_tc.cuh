@@ -126,7 +126,8 @@ __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* tmap, 
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
-constexpr int kThreads = 256;   // warp 0 TMA, warp 1 MMA (+TMEM alloc), warps 2..5 epilogue, warps 6,7 MMA
+constexpr int kThreads = 384;   // warp 0 TMA, warps 1,6,7 MMA (warp 1 also TMEM alloc), warps 2..5 + 8..11 epilogue
+constexpr int kEpiGroups = 2;   // two epilogue warpgroups alternate over the chunks of a plane (TMEM lane quarter = warp % 4)
 constexpr int kMmaWarps = 3;
 
 // blocks of B per kd plane: one block = one K=16 MMA step = NPAD x 16 elements in canonical order
@@ -187,7 +188,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmap /*P8 input: {8, Wp, Hp, group
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < g.S; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], kMmaWarps); }
-    for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], kMmaWarps); mbar_init(&acc_empty[b], 4); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], kMmaWarps); mbar_init(&acc_empty[b], 4 * kEpiGroups); }
     mbar_init(b_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     mbar_expect_tx(b_full, B_BYTES);          // weights do not depend on the previous kernel: fetch them before pdl_wait
@@ -220,7 +221,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmap /*P8 input: {8, Wp, Hp, group
           tma_load_4d(sA + (size_t)slot * slot_bytes + (size_t)cg * cg_bytes, &tmap, 0, w0, h0, cg * g.iDp + pp, &full[slot]);
       }
     }
-  } else if (warp == 1 || warp >= 6) {
+  } else if (warp == 1 || warp == 6 || warp == 7) {
     // ===================== MMA issuers (warp-uniform; one elected lane issues) =====================
     const int issuer = warp == 1 ? 0 : warp - 5;   // 0,1,2
     const bool leader = lane == 0;
@@ -286,12 +287,13 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmap /*P8 input: {8, Wp, Hp, group
   } else {
     // ===================== epilogue (warps 2..5) =====================
     const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const int egroup = warp >= 8 ? 1 : 0;
     for (int od = 0; od < ndo; ++od) {
       const int buf = od & 1;
       mbar_wait(&acc_full[buf], (od >> 1) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const int d = d0 + od;
-      for (int c = 0; c < g.nch; ++c) {
+      for (int c = egroup; c < g.nch; c += kEpiGroups) {
         const int l = c * 128 + q * 32 + lane;
         const int hh = l / g.P, ww = l - hh * g.P;
         const int h = h0 + hh, w = w0 + ww;

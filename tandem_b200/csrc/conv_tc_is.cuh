@@ -67,7 +67,7 @@ k_conv_tc_is(const __grid_constant__ CUtensorMap tmap, const TIn* __restrict__ b
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < g.S; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], kMmaWarps); }
-    for (int r = 0; r < RS; ++r) { mbar_init(&acc_full[r], kMmaWarps); mbar_init(&acc_empty[r], 4); }
+    for (int r = 0; r < RS; ++r) { mbar_init(&acc_full[r], kMmaWarps); mbar_init(&acc_empty[r], 4 * kEpiGroups); }
     mbar_init(b_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     mbar_expect_tx(b_full, B_BYTES);          // weights do not depend on the previous kernel: fetch them before pdl_wait
@@ -97,7 +97,7 @@ k_conv_tc_is(const __grid_constant__ CUtensorMap tmap, const TIn* __restrict__ b
           tma_load_4d(sA + (size_t)slot * slot_bytes + (size_t)cg * cg_bytes, &tmap, 0, w0, h0, cg * g.iDp + d0 + rp, &full[slot]);
       }
     }
-  } else if (warp == 1 || warp >= 6) {
+  } else if (warp == 1 || warp == 6 || warp == 7) {
     // ===================== MMA issuers =====================
     const int issuer = warp == 1 ? 0 : warp - 5;
     const bool leader = lane == 0;
@@ -153,8 +153,10 @@ k_conv_tc_is(const __grid_constant__ CUtensorMap tmap, const TIn* __restrict__ b
   } else {
     // ===================== epilogue (warps 2..5): zero, drain, re-zero =====================
     const int qd = warp & 3;
+    const int egroup = warp >= 8 ? 1 : 0;
     const uint32_t lane_base = tmem_base + ((uint32_t)(qd * 32) << 16);
-    for (uint32_t col = 0; col < tmem_cols; col += 16) tmem_st16_zero(lane_base + col);
+    for (int c = egroup; c < g.nch; c += kEpiGroups)      // each group zeroes (and later drains) its own chunks
+      for (uint32_t col = 0; col < chunk_cols; col += 16) tmem_st16_zero(lane_base + (uint32_t)c * chunk_cols + col);
     tmem_wait_st();
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncwarp();
@@ -165,7 +167,7 @@ k_conv_tc_is(const __grid_constant__ CUtensorMap tmap, const TIn* __restrict__ b
       mbar_wait(&acc_full[r], (od >> 2) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const int d = d0 + od;
-      for (int c = 0; c < g.nch; ++c) {
+      for (int c = egroup; c < g.nch; c += kEpiGroups) {
         const int l = c * 128 + qd * 32 + lane;
         const int hh = l / g.P, ww = l - hh * g.P;
         const int h = h0 + hh, w = w0 + ww;

@@ -75,7 +75,7 @@ k_conv_tc_s2(const __grid_constant__ CUtensorMap tmap, const TIn* __restrict__ b
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < g.S; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], kMmaWarps); }
-    for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], kMmaWarps); mbar_init(&acc_empty[b], 4); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], kMmaWarps); mbar_init(&acc_empty[b], 4 * kEpiGroups); }
     mbar_init(b_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     mbar_expect_tx(b_full, B_BYTES);          // weights do not depend on the previous kernel: fetch them before pdl_wait
@@ -112,7 +112,7 @@ k_conv_tc_s2(const __grid_constant__ CUtensorMap tmap, const TIn* __restrict__ b
         }
       }
     }
-  } else if (warp == 1 || warp >= 6) {
+  } else if (warp == 1 || warp == 6 || warp == 7) {
     // ===================== MMA issuers =====================
     const int issuer = warp == 1 ? 0 : warp - 5;
     const bool leader = lane == 0;
@@ -174,12 +174,13 @@ k_conv_tc_s2(const __grid_constant__ CUtensorMap tmap, const TIn* __restrict__ b
   } else {
     // ===================== epilogue (warps 2..5) =====================
     const int q = warp & 3;
+    const int egroup = warp >= 8 ? 1 : 0;
     for (int od = 0; od < ndo; ++od) {
       const int buf = od & 1;
       mbar_wait(&acc_full[buf], (od >> 1) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const int d = d0 + od;
-      for (int c = 0; c < g.nch; ++c) {
+      for (int c = egroup; c < g.nch; c += kEpiGroups) {
         const int l = c * 128 + q * 32 + lane;
         const int hh = l / g.P, ww = l - hh * g.P;
         const int h = h0 + hh, w = w0 + ww;
