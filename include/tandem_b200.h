@@ -81,6 +81,9 @@ long long tdm_mvsnet_debug_tensor(tdm_mvsnet* h, const char* name, float* out, s
  * handle's stream with inputs already in HBM (no H2D/D2H inside), timed with CUDA events on that stream.
  * ms_total receives the elapsed milliseconds; launches (optional) the kernel launches per forward. */
 int tdm_mvsnet_run_resident(tdm_mvsnet* h, int iters, float* ms_total, int* launches);
+/* Same clock over n handles of one device: iters_total forwards issued round-robin, each handle on its own stream (the
+ * windows are independent, so their kernels may overlap on the GPU); ms_total spans first launch .. last completion. */
+int tdm_mvsnet_run_resident_multi(tdm_mvsnet* const* hs, int n, int iters_total, float* ms_total, int* launches);
 /* Per-kernel CUDA-event timing of one resident forward: writes lines "name ms algorithmic_bytes flops\n"
  * into buf (NUL terminated). Returns bytes written or <0. */
 long long tdm_mvsnet_profile(tdm_mvsnet* h, char* buf, size_t capacity);

@@ -1,4 +1,5 @@
 // extern "C" entry points for the MVSNet engine + library-wide helpers (include/tandem_b200.h).
+#include <vector>
 #include <cstring>
 #include <string>
 
@@ -107,6 +108,33 @@ int tdm_mvsnet_run_resident(tdm_mvsnet* h, int iters, float* ms_total, int* laun
   TDM_API_BEGIN
   TDM_CHECK(h && ms_total, "null argument");
   h->impl->run_resident(iters, ms_total, launches);
+  return TDM_OK;
+  TDM_API_END
+}
+int tdm_mvsnet_run_resident_multi(tdm_mvsnet* const* hs, int n, int iters_total, float* ms_total, int* launches) {
+  TDM_API_BEGIN
+  TDM_CHECK(hs && ms_total && n >= 1 && n <= 16 && iters_total >= 1, "bad argument");
+  for (int j = 0; j < n; ++j) TDM_CHECK(hs[j] && hs[j]->impl->resident_device() == hs[0]->impl->resident_device(), "handles must share a device");
+  TDM_CUDA(cudaSetDevice(hs[0]->impl->resident_device()));
+  std::vector<cudaStream_t> st(n);
+  for (int j = 0; j < n; ++j) st[j] = (cudaStream_t)hs[j]->impl->resident_stream();
+  hs[0]->impl->resident_launch(0);   // drains every engine's worker before the clock starts
+  for (int j = 1; j < n; ++j) hs[j]->impl->resident_launch(0);
+  std::vector<cudaEvent_t> ev(n + 1);
+  for (auto& e : ev) TDM_CUDA(cudaEventCreate(&e));
+  TDM_CUDA(cudaEventRecord(ev[0], st[0]));
+  for (int j = 1; j < n; ++j) TDM_CUDA(cudaStreamWaitEvent(st[j], ev[0], 0));
+  int nl = 0;
+  for (int it = 0; it < iters_total; ++it) nl = hs[it % n]->impl->resident_launch(1);   // round robin, one stream per engine
+  for (int j = 1; j < n; ++j) {
+    TDM_CUDA(cudaEventRecord(ev[j], st[j]));
+    TDM_CUDA(cudaStreamWaitEvent(st[0], ev[j], 0));
+  }
+  TDM_CUDA(cudaEventRecord(ev[n], st[0]));
+  TDM_CUDA(cudaEventSynchronize(ev[n]));
+  TDM_CUDA(cudaEventElapsedTime(ms_total, ev[0], ev[n]));
+  for (auto& e : ev) cudaEventDestroy(e);
+  if (launches) *launches = nl;
   return TDM_OK;
   TDM_API_END
 }

@@ -168,6 +168,7 @@ class MvsnetEngine final : public MvsnetIface {
     if (key == "filter_all_stages") filter_all_ = value != 0;
     else if (key == "use_graph") use_graph_ = value != 0;
     else if (key == "use_pdl") use_pdl_ = value != 0;
+    else if (key == "cv_variant") { TDM_CHECK(value >= 0 && value <= 4, "cv_variant out of range"); cv_variant_ = value; }
     else if (key == "tc_smem_kb") { TDM_CHECK(value >= 48 && value <= 225, "tc_smem_kb out of range"); tc_smem_kb_ = value; tc_cache_.clear(); s2_cache_.clear(); }
     else if (key.rfind("depth_num_stage", 0) == 0 && key.size() == 16 && key[15] >= '1' && key[15] <= '3') {
       // override the checkpoint's MODEL.DEPTH_NUM for one stage (BASELINE.json configs[0] uses 32 stage-1 hypotheses;
@@ -322,6 +323,16 @@ class MvsnetEngine final : public MvsnetIface {
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
     if (launches) *launches = launches_per_forward_;
+  }
+
+  void* resident_stream() override { return (void*)stream_; }
+  int resident_device() const override { return device_; }
+  int resident_launch(int iters) override {
+    wait();
+    TDM_CHECK(have_inputs_, "run_resident: no window submitted yet");
+    TDM_CUDA(cudaSetDevice(device_));
+    for (int i = 0; i < iters; ++i) forward(false);
+    return launches_per_forward_;
   }
 
   std::string profile() override {
@@ -989,6 +1000,12 @@ class MvsnetEngine final : public MvsnetIface {
       const Gate& g = gates_[s - 1];
       for (int c = 0; c < g.C; ++c) p.gw1[c] = g.w1[c];
       p.gb1 = g.b1; p.gw2 = g.w2; p.gb2 = g.b2;
+      float mx = 0.f;
+      for (int c = 0; c < g.C; ++c) mx = std::max(mx, std::fabs(g.w1[c]));
+      int e = 0;
+      if (mx > 0.f && std::isfinite(mx)) std::frexp(mx, &e);      // mx = m * 2^e, m in [0.5, 1)
+      p.gw1_scale = std::ldexp(1.f, -e);
+      p.dot_unscale = 4096.f / p.gw1_scale;
     }
     p.hyp = hyp_spec(s);
   }
@@ -1022,7 +1039,30 @@ class MvsnetEngine final : public MvsnetIface {
     rec_begin(k + "cost_volume", (double)fb.alg_bytes + (double)vb.alg_bytes + (s > 1 ? 4.0 * vb.H * vb.W : 0.0),
               (double)n * nsrc * fb.C * 12.0);
     const float* dm = s > 1 ? fbuf(k + "dmin") : nullptr;
-    if (fb.C == 32) k_cost_volume<TA, TV, 16, 2><<<cdiv(2 * n, 128), 128, 0, stream_>>>(p8<const TA>(fb), dm, p8<TV>(vb), slot_, s - 1);
+    bool done = false;
+    if constexpr (std::is_same<TA, __half>::value) {
+      if (va_ && cv_variant_ > 0) {
+        done = true;
+        const int nd = (cv_variant_ == 2 || cv_variant_ == 4) ? 4 : (fb.C == 8 ? 4 : 2);
+        const bool h16 = cv_variant_ >= 3;
+        const long long thr = (long long)cdiv(vb.D, nd) * vb.H * vb.W * (fb.C == 32 ? 2 : 1);
+        const unsigned grid = (unsigned)cdiv(thr, 128);
+        auto go = [&](auto kern) { kern<<<grid, 128, 0, stream_>>>(p8<const __half>(fb), dm, p8<TV>(vb), slot_, s - 1); };
+        if (fb.C == 32) {
+          if (nd == 2) { if (h16) go(k_cost_volume_va16<TV, 16, 2, 2, true>); else go(k_cost_volume_va16<TV, 16, 2, 2, false>); }
+          else         { if (h16) go(k_cost_volume_va16<TV, 16, 2, 4, true>); else go(k_cost_volume_va16<TV, 16, 2, 4, false>); }
+        } else if (fb.C == 16) {
+          if (nd == 2) { if (h16) go(k_cost_volume_va16<TV, 16, 1, 2, true>); else go(k_cost_volume_va16<TV, 16, 1, 2, false>); }
+          else         { if (h16) go(k_cost_volume_va16<TV, 16, 1, 4, true>); else go(k_cost_volume_va16<TV, 16, 1, 4, false>); }
+        } else if (fb.C == 8) {
+          if (h16) go(k_cost_volume_va16<TV, 8, 1, 4, true>); else go(k_cost_volume_va16<TV, 8, 1, 4, false>);
+        } else {
+          throw Error("unsupported feature channels");
+        }
+      }
+    }
+    if (done) {}
+    else if (fb.C == 32) k_cost_volume<TA, TV, 16, 2><<<cdiv(2 * n, 128), 128, 0, stream_>>>(p8<const TA>(fb), dm, p8<TV>(vb), slot_, s - 1);
     else if (fb.C == 16) k_cost_volume<TA, TV, 16><<<cdiv(n, 128), 128, 0, stream_>>>(p8<const TA>(fb), dm, p8<TV>(vb), slot_, s - 1);
     else if (fb.C == 8) k_cost_volume<TA, TV, 8><<<cdiv(n, 128), 128, 0, stream_>>>(p8<const TA>(fb), dm, p8<TV>(vb), slot_, s - 1);
     else throw Error("unsupported feature channels");
@@ -1228,6 +1268,7 @@ class MvsnetEngine final : public MvsnetIface {
   CallParams* h_params_ = nullptr;   // pinned
   CallParams* d_params_ = nullptr;
   cudaGraphExec_t graph_exec_ = nullptr;
+  int cv_variant_ = 3;   // 0: generic cost-volume kernel; 1-4: k_cost_volume_va16 (ND 2/2/4 | 4/4/4, fp32 | fp16 accumulate)
   bool warmed_ = false, use_graph_ = true, use_pdl_ = false;   // PDL measured slower (1.86 vs 1.73 ms): dependents squat on SM resources while they wait
   int slot_ = 0;           // index into c_call_params
   int tc_smem_kb_ = 225;   // shared-memory budget of the tile planner (<= 113 lets two CTAs share an SM)

@@ -18,6 +18,10 @@ class MvsnetIface {
   virtual long long debug_tensor(const std::string& name, float* out, size_t cap, int* dims4) = 0;
   virtual void run_resident(int iters, float* ms_total, int* launches) = 0;
   virtual std::string profile() = 0;
+  // building blocks of tdm_mvsnet_run_resident_multi (several engines of one device timed together)
+  virtual void* resident_stream() = 0;                 // cudaStream_t
+  virtual int resident_device() const = 0;
+  virtual int resident_launch(int iters) = 0;          // enqueue iters forwards, no synchronisation; returns launches per forward
 };
 
 MvsnetIface* make_mvsnet(const std::string& weights_path, int precision, int device);

@@ -233,6 +233,8 @@ struct CvParams {
   float trans[kMaxSrc][3];
   float gw1[64];       // folded gate layer 1 weights (per channel)
   float gb1, gw2, gb2; // folded scalars
+  float gw1_scale;     // power of two with max|gw1| * gw1_scale in [0.5, 1): keeps the fp16 copy of gw1 in the normal range
+  float dot_unscale;   // 4096 / gw1_scale: undoes the fp16 path's operand scaling of the gate's dot product
   int view_aggregation;
   HypSpec hyp;
 };
@@ -423,6 +425,166 @@ k_cost_volume(P8<const T> feats /*views on the D axis, ref first*/, const float*
 #pragma unroll
       for (int c = 0; c < 8; ++c) o8[c] = acc[c0 + c];
       store_vec<TV, 8>(vol.p + op + (c0 >> 3) * vol.gs, o8);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// a6': view-aggregation cost volume, fp16 features (the mixed16 engine's kernel; k_cost_volume above stays the exact fp32
+// parity path and the variance path).  The generic kernel is instruction-issue bound (ncu: 60-82 % issue slots, ~160
+// instructions per (voxel, view) sample at C = 8, DRAM 1-4 %), so this one removes instructions:
+//  * one thread owns ND consecutive depth hypotheses of a pixel: the view's R*[x y 1]^T, its constant-bank loads and the
+//    gate weights are shared by ND samples, and the ND samples walk along the epipolar line (L1 locality);
+//  * packed fp16 math up to the squared difference: the bilinear chain starts from -ref, so it yields (warped - ref)
+//    directly; all fp16 operands carry a 1/64 scale (weights and ref; exact, a power of two) so the square, scaled by
+//    1/4096, cannot overflow before |warped - ref| = 16376 (features are fp16 themselves; max seen 115);
+//  * the gate's dot product runs in HFMA2 against a normalised fp16 copy of gw1 and is un-scaled in fp32;
+//  * accumulation over views stays fp32 (ACC16 = false) as packed FFMA2, or fp16 (ACC16 = true, study variant);
+//  * rcp.approx instead of the IEEE reciprocal, 32-bit element offsets.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float rcp_approx(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+  unsigned long long ra, rb, rc, rd;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b.x), "f"(b.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(rc) : "f"(c.x), "f"(c.y));
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+  float2 d;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(rd));
+  return d;
+}
+
+template <typename TV, int C /*channels of one thread*/, int CSPLIT, int ND, bool ACC16>
+__global__ void __launch_bounds__(128)
+k_cost_volume_va16(P8<const __half> feats, const float* __restrict__ dmin_map, P8<TV> vol, int slot, int stage) {
+  const CvParams& p = c_call_params[slot].cv[stage];
+  constexpr float kS = 1.f / 64.f;
+  const int HW = p.H * p.W;
+  const int ngrp = (p.D + ND - 1) / ND;
+  const int n = ngrp * HW;
+  int i = (int)((blockIdx.x * (long long)blockDim.x + threadIdx.x) / CSPLIT);
+  const int part = threadIdx.x % CSPLIT;
+  const bool active = i < n;
+  if (!active) i = n - 1;                          // keep the lane alive for the shuffles; its stores are masked
+  const int dg = i / HW, pix = i - dg * HW;
+  const int y = pix / p.W, x = pix - y * p.W;
+  const int d0 = dg * ND;
+  const __half* fbase = feats.p + (size_t)part * (C / 8) * feats.gs;
+  const int fgs = (int)feats.gs;
+
+  __half2 nref[C / 2], gwh[C / 2];
+  {
+    const __half* rp = fbase + feats.pos(0, y, x);
+    const __half2 ms = __float2half2_rn(-kS);
+#pragma unroll
+    for (int c0 = 0; c0 < C; c0 += 8) {
+      const uint4 q = __ldg(reinterpret_cast<const uint4*>(rp + (size_t)(c0 >> 3) * feats.gs));
+      const __half2* h = reinterpret_cast<const __half2*>(&q);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) nref[c0 / 2 + k] = __hmul2(h[k], ms);
+    }
+#pragma unroll
+    for (int k = 0; k < C / 2; ++k)
+      gwh[k] = __floats2half2_rn(p.gw1[part * C + 2 * k] * p.gw1_scale, p.gw1[part * C + 2 * k + 1] * p.gw1_scale);
+  }
+  float depth[ND];
+  {
+    const float dmn = p.hyp.adaptive ? dmin_map[pix] : 0.f;
+#pragma unroll
+    for (int k = 0; k < ND; ++k) depth[k] = hyp_value(p.hyp, dmn, min(d0 + k, p.D - 1));
+  }
+  float2 acc[ND][C / 2];
+  __half2 acch[ND][C / 2];
+#pragma unroll
+  for (int k = 0; k < ND; ++k)
+#pragma unroll
+    for (int c = 0; c < C / 2; ++c) { acc[k][c] = make_float2(0.f, 0.f); acch[k][c] = __float2half2_rn(0.f); }
+
+  const float fx = (float)x, fy = (float)y, Wf = (float)p.W, Hf = (float)p.H;
+  const int row = feats.Wp * 8;
+  for (int s = 0; s < p.nsrc; ++s) {
+    const float* R = p.rot[s];
+    const float* t = p.trans[s];
+    const float rx = R[0] * fx + R[1] * fy + R[2];
+    const float ry = R[3] * fx + R[4] * fy + R[5];
+    const float rz = R[6] * fx + R[7] * fy + R[8];
+    const float t0 = t[0], t1 = t[1], t2 = t[2];
+    const int vbase = ((s + 1 + feats.pd) * feats.Hp + 1) * feats.Wp + 1;
+#pragma unroll
+    for (int k = 0; k < ND; ++k) {
+      const float qx = fmaf(rx, depth[k], t0), qy = fmaf(ry, depth[k], t1), qz = fmaf(rz, depth[k], t2);
+      const float inv = rcp_approx(qz);
+      const float ix = qx * inv, iy = qy * inv;
+      __half2 df[C / 2];
+      if (!(qz < 0.001f) && ix >= -1.f && iy >= -1.f && ix < Wf && iy < Hf) {
+        const float x0f = floorf(ix), y0f = floorf(iy);
+        const float ax = ix - x0f, ay = iy - y0f;
+        const float wy1 = ay * kS, wy0 = fmaf(-ay, kS, kS), wx0 = 1.f - ax;
+        const __half2 h00 = __float2half2_rn(wx0 * wy0), h01 = __float2half2_rn(ax * wy0);
+        const __half2 h10 = __float2half2_rn(wx0 * wy1), h11 = __float2half2_rn(ax * wy1);
+        const __half* tp = fbase + (size_t)(unsigned)((vbase + (int)y0f * feats.Wp + (int)x0f) * 8);
+#pragma unroll
+        for (int c0 = 0; c0 < C; c0 += 8) {
+          const __half* tq = tp + (c0 >> 3) * fgs;
+          const uint4 q00 = __ldg(reinterpret_cast<const uint4*>(tq)), q01 = __ldg(reinterpret_cast<const uint4*>(tq + 8));
+          const uint4 q10 = __ldg(reinterpret_cast<const uint4*>(tq + row)), q11 = __ldg(reinterpret_cast<const uint4*>(tq + row + 8));
+          const __half2* a00 = reinterpret_cast<const __half2*>(&q00);
+          const __half2* a01 = reinterpret_cast<const __half2*>(&q01);
+          const __half2* a10 = reinterpret_cast<const __half2*>(&q10);
+          const __half2* a11 = reinterpret_cast<const __half2*>(&q11);
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            df[c0 / 2 + j] = __hfma2(a11[j], h11, __hfma2(a10[j], h10, __hfma2(a01[j], h01, __hfma2(a00[j], h00, nref[c0 / 2 + j]))));
+        }
+      } else {
+#pragma unroll
+        for (int c = 0; c < C / 2; ++c) df[c] = nref[c];     // grid_sample's zeros padding: warped = 0
+      }
+      __half2 dh = __float2half2_rn(0.f);
+#pragma unroll
+      for (int c = 0; c < C / 2; ++c) {
+        df[c] = __hmul2(df[c], df[c]);                       // (warped - ref)^2 / 4096
+        dh = __hfma2(df[c], gwh[c], dh);
+      }
+      const float2 dl = __half22float2(dh);
+      float dot = dl.x + dl.y;
+      if constexpr (CSPLIT == 2) dot += __shfl_xor_sync(0xffffffffu, dot, 1);
+      const float h1 = fmaxf(fmaf(dot, p.dot_unscale, p.gb1), 0.f);
+      const float g = fmaxf(fmaf(p.gw2, h1, p.gb2), 0.f) + 1.f;
+      if constexpr (ACC16) {
+        const __half2 gh = __float2half2_rn(g);
+#pragma unroll
+        for (int c = 0; c < C / 2; ++c) acch[k][c] = __hfma2(df[c], gh, acch[k][c]);
+      } else {
+        const float2 g2 = make_float2(g, g);
+#pragma unroll
+        for (int c = 0; c < C / 2; ++c) acc[k][c] = ffma2(__half22float2(df[c]), g2, acc[k][c]);
+      }
+    }
+  }
+  if (active) {
+    const float sc = 4096.f / (float)p.nsrc;
+    TV* vbase_p = vol.p + (size_t)part * (C / 8) * vol.gs;
+#pragma unroll
+    for (int k = 0; k < ND; ++k) {
+      if (d0 + k < p.D) {
+        const long long op = vol.pos(d0 + k, y, x);
+#pragma unroll
+        for (int c0 = 0; c0 < C; c0 += 8) {
+          float o8[8];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float2 v = ACC16 ? __half22float2(acch[k][c0 / 2 + j]) : acc[k][c0 / 2 + j];
+            o8[2 * j] = v.x * sc;
+            o8[2 * j + 1] = v.y * sc;
+          }
+          store_vec<TV, 8>(vbase_p + op + (size_t)(c0 >> 3) * vol.gs, o8);
+        }
+      }
     }
   }
 }

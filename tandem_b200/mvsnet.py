@@ -118,6 +118,15 @@ class DrMvsnet:
         check(lib().tdm_mvsnet_run_resident(self._h, iters, ctypes.byref(ms), ctypes.byref(nl)))
         return ms.value, nl.value
 
+    @staticmethod
+    def run_resident_multi(handles, iters_total):
+        """iters_total resident forwards round-robin over several handles of one device, one CUDA-event clock."""
+        arr = (ctypes.c_void_p * len(handles))(*[h._h.value for h in handles])
+        ms = ctypes.c_float()
+        nl = ctypes.c_int()
+        check(lib().tdm_mvsnet_run_resident_multi(arr, len(handles), iters_total, ctypes.byref(ms), ctypes.byref(nl)))
+        return ms.value, nl.value
+
     def profile(self):
         buf = ctypes.create_string_buffer(1 << 16)
         check(lib().tdm_mvsnet_profile(self._h, buf, len(buf)))

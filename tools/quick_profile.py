@@ -17,12 +17,15 @@ for kv in sys.argv[3:]:
 bgrs = [np.ascontiguousarray(g["bgr"][v]) for v in range(V)]
 c2ws = [np.ascontiguousarray(g["c2w"][v]) for v in range(V)]
 m.CallAsync(H, W, V, int(g["ref_index"]), bgrs, g["K3"], c2ws, float(g["depth_min"]), float(g["depth_max"]), float(g["discard"]))
-m.GetResult()
+out = m.GetResult()
+ref = g["abl03_stage3_depth_dense"]
+msk = ref > 0
+print(f"Abs Rel vs reference model output: {float(np.mean(np.abs(ref[msk] - out.depth_dense[msk]) / ref[msk])):.3e}")
 ms, nl = m.run_resident(3)
 ms, nl = m.run_resident(10)
 print(f"{prec} tc={tc}: resident forward {ms / 10:.3f} ms, {nl} launches")
 rows = m.profile()
 tot = sum(r[1] for r in rows)
-for name, t, b, fl in sorted(rows, key=lambda r: -r[1])[:40]:
+for name, t, b, fl in sorted(rows, key=lambda r: -r[1])[:int(os.environ.get('TOPK', '40'))]:
     print(f"{name:20s} {t:8.3f} ms {100 * t / tot:5.1f}%  {b / t / 1e6 if t > 0 else 0:9.1f} GB/s  {fl / t / 1e9 if t > 0 else 0:9.2f} TFLOP/s")
 print(f"sum of kernels {tot:.3f} ms")
