@@ -158,6 +158,24 @@ def dist_setup(n):
     return rank, world, local, dist
 
 
+def ncu_traffic(record_name):
+    """DRAM bytes (read + write) per launch of the roofline kernel, from the committed `ncu --set full` capture of the
+    same kernel (profiles/rNN_ncu_traffic.json, written by tools/summarise_profiles.py). None when no capture matches."""
+    import glob
+    files = sorted(glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r*_ncu_traffic.json")))
+    if not files or not record_name.endswith("cost_volume"):
+        return None, None
+    pat = {"s1": "k_cost_volume_va16<__nv_bfloat16, 16, 2,", "s2": "k_cost_volume_va16<__nv_bfloat16, 16, 1,",
+           "s3": "k_cost_volume_va16<__nv_bfloat16, 8, 1,"}.get(record_name[:2])
+    try:
+        for k, v in json.load(open(files[-1])).items():
+            if pat and pat in k:
+                return float(v), os.path.basename(files[-1])
+    except (OSError, ValueError):
+        pass
+    return None, None
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -275,8 +293,11 @@ def main():
         peak, how = measured_peaks()
         ach = top[2] / (top[1] * 1e-3) / 1e9
         alg_total = sum(r[2] for r in rows)
+        traffic, traffic_src = ncu_traffic(top[0])
         roof = {"bound": "hbm", "kernel": top[0], "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                "traffic": None, "peak_source": how, "kernel_ms": top[1], "kernel_share_of_step": top[1] / tot,
+                "traffic": traffic, "traffic_source": traffic_src, "algorithmic_bytes": top[2],
+                "note": "the kernel is issue/L1-bound (ncu: DRAM < 5 %, issue 57-73 %, L1/TEX 54-90 %); hbm is the nearest of the two allowed bounds",
+                "peak_source": how, "kernel_ms": top[1], "kernel_share_of_step": top[1] / tot,
                 "step_algorithmic_GB": alg_total / 1e9, "step_achieved_GBps": alg_total / (ms_dev / a.steps * 1e-3) / 1e9,
                 "step_frac_of_peak": alg_total / (ms_dev / a.steps * 1e-3) / 1e9 / peak}
         cpu = None
