@@ -6,7 +6,9 @@
 
 #include <Eigen/Dense>
 
-struct tdm_tracker;  // include/tandem_b200.h
+struct tdm_tracker;   // include/tandem_b200.h
+struct tdm_pyramid;
+struct tdm_fusion;
 
 class CudaCoarseTracker {
 public:
@@ -35,6 +37,28 @@ public:
   Eigen::Matrix<double, 6, 1> calcResAndG(Eigen::Matrix<double, 4, 4> const &refToNew, float new_exposure,
                                           Eigen::Vector2d const &aff_g2l, float cutoffTH,
                                           Eigen::Matrix<double, 8, 8> &H_out, Eigen::Matrix<double, 8, 1> &b_out);
+
+  // Extensions for the stages either side of the evaluation:
+  //  * setNewFromPyramid: setNew from a device-resident FrameHessian::makeImages replacement (tdm_pyramid);
+  //  * setReferenceDense: the dense part of CoarseTracker::setCoarseTrackingRef + setReference; the depth map is the
+  //    render_index-th map of the last DrFusion::RenderAsync and never leaves the device;
+  //  * track: one pyramid level of CoarseTracker::trackNewestCoarse without host round trips.
+  void setNewFromPyramid(tdm_pyramid *pyramid, int level);
+
+  int setReferenceDense(tdm_fusion *fusion, int render_index, Eigen::Matrix<double, 4, 4> const &T_depth_to_ref,
+                        int tracking_step, bool dense_only, int n_sparse, float const *pc_u, float const *pc_v,
+                        float const *pc_idepth, float const *pc_color, float const *idepth0, tdm_pyramid *ref_pyramid,
+                        float ref_exposure, Eigen::Vector2d const &ref_aff_g2l);
+
+  struct TrackResult {
+    Eigen::Matrix<double, 4, 4> refToNew;
+    Eigen::Vector2d aff_g2l;
+    Eigen::Matrix<double, 6, 1> res;
+    int iterations;
+    float levelCutoffRepeat;
+  };
+  TrackResult track(Eigen::Matrix<double, 4, 4> const &refToNew, Eigen::Vector2d const &aff_g2l, float new_exposure,
+                    float coarseCutoffTH, int maxIterations, float lambdaExtrapolationLimit, bool fix_a, bool fix_b);
 
   void synchronize();
 

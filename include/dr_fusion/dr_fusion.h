@@ -57,6 +57,9 @@ public:
 
     void Synchronize();
 
+    // Extension: the C-ABI handle, so that CudaCoarseTracker::setReferenceDense can read the rendered depth on the device.
+    tdm_fusion* handle() const { return handle_; }
+
     size_t dr_mesh_num = 0;
     const size_t dr_mesh_num_max = 60000000;
     float* dr_mesh_vert;

@@ -164,6 +164,57 @@ int tdm_tracker_calc_res_g(tdm_tracker* t, const double* refToNew, float new_exp
 int tdm_tracker_synchronize(tdm_tracker* t);
 int tdm_tracker_run_resident(tdm_tracker* t, int iters, float* ms_total);
 
+/* ------------------------------------------------------------------------------------------------
+ * SURVEY.md 8(f) "next" rows: the host stages either side of the evaluation, moved onto the device.  These entry
+ * points have no counterpart in the reference's class (they replace code ABOVE its boundary); INTEGRATION.md shows
+ * the three call sites in CoarseTracker.cpp / HessianBlocks.cpp that would switch to them.
+ * ---------------------------------------------------------------------------------------------- */
+/* n2  FrameHessian::makeImages (tandem/src/FullSystem/HessianBlocks.cpp:128-191): grey pyramid by 2x2 means +
+ *     central-difference gradients for `levels` levels (level l is (w>>l) x (h>>l), globalCalib.cpp:84-85).
+ *     build() uploads the w*h grey image (1.2 MB instead of the 3.7 MB float3 image setNew uploads) and is asynchronous;
+ *     get_level() copies one level back (dI: (I,dx,dy) float3 per pixel; abs_squared_grad: dx^2+dy^2, no gamma weights). */
+typedef struct tdm_pyramid tdm_pyramid;
+int tdm_pyramid_create(int w, int h, int levels, int device, tdm_pyramid** out);
+void tdm_pyramid_destroy(tdm_pyramid* p);
+int tdm_pyramid_build(tdm_pyramid* p, const float* gray);
+int tdm_pyramid_get_level(tdm_pyramid* p, int level, float* dI, float* abs_squared_grad);
+/* setNew (cuda_coarse_tracker.cpp:99-102) without the host round trip: device-to-device from a pyramid level whose size
+ * equals the tracker's (a tracker instance per level puts levels 1..3 of CoarseTracker.cpp:774 on the GPU as well). */
+int tdm_tracker_set_new_from_pyramid(tdm_tracker* t, tdm_pyramid* p, int level);
+
+/* n1  the dense part of CoarseTracker::setCoarseTrackingRef (tandem/src/FullSystem/CoarseTracker.cpp:655-732) followed by
+ *     setReference: forward-warps the dense depth map (host pointer, or the render_index-th map of the last
+ *     tdm_fusion_render_async - device resident, no PCIe hop) with T_depth_to_ref = ref.camToWorld^-1 * depth.camToWorld
+ *     (row-major), keeps the nearest depth per target pixel, and appends the hit pixels in raster order behind the
+ *     n_sparse sparse points of makeCoarseDepthL0.  pc_* hold n_sparse + 1 entries: the extra one is the slot the
+ *     reference's `++pc_n` skips (CoarseTracker.cpp:717-722) and is uploaded as is; NULL is allowed when n_sparse == 0.
+ *     idepth0 (h*w, the sparse inverse-depth image idepth[0]) may be NULL.  The grey values of the reference keyframe
+ *     come from ref_gray (h*w floats) or from level 0 of a pyramid.  *pc_n receives the reference's pc_n[0]. */
+int tdm_tracker_set_reference_dense(tdm_tracker* t, const float* depth, tdm_fusion* depth_from_fusion, int render_index,
+                                    const double T_depth_to_ref[16], int tracking_step, int dense_only, int n_sparse,
+                                    const float* pc_u, const float* pc_v, const float* pc_idepth, const float* pc_color,
+                                    const float* idepth0, const float* ref_gray, tdm_pyramid* ref_gray_from_pyramid,
+                                    float ref_exposure, const double ref_aff_g2l[2], int* pc_n);
+/* Reads the first n reference points back (tests, debugging). Any output pointer may be NULL. */
+int tdm_tracker_get_reference(tdm_tracker* t, int n, float* pc_u, float* pc_v, float* pc_idepth, float* pc_color);
+
+/* n3  one pyramid level of CoarseTracker::trackNewestCoarse (CoarseTracker.cpp:761-916) without host round trips:
+ *     initial evaluation with cutoff doubling (:775-790), then up to max_iterations damped Gauss-Newton steps with the
+ *     reference's accept / lambda / extrapolation / termination rules; fix_a / fix_b = setting_affineOptModeA/B < 0.
+ *     Blocking; the caller keeps the coarse-to-fine logic (repeat a level when cutoff_repeat > 1, abort thresholds). */
+typedef struct tdm_track_result {
+  double ref_to_new[16];   /* row-major */
+  double aff_g2l[2];
+  double res[6];           /* resOld of the accepted state: E, numTermsInE, flow T, 0, flow RT, saturated ratio */
+  int iterations;          /* executed LM iterations */
+  int evaluations;         /* fused residual + normal-equation evaluations launched */
+  float cutoff_repeat;     /* levelCutoffRepeat */
+  float device_ms;         /* CUDA-event time of the whole loop */
+} tdm_track_result;
+int tdm_tracker_track(tdm_tracker* t, const double refToNew[16], const double aff_g2l[2], float new_exposure,
+                      float coarse_cutoff_th, int max_iterations, float lambda_extrapolation_limit, int fix_a, int fix_b,
+                      tdm_track_result* out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -141,3 +141,51 @@ class TrackerOracle:
                                       int(self.out7[2]), acc.ctypes.data_as(_dp), H.ctypes.data_as(_dp),
                                       b.ctypes.data_as(_dp))
         return H, b
+
+
+class FrontOracle:
+    """oracle/front_oracle.c: image pyramid + gradients (n2) and the dense tracking reference (n1)."""
+
+    def __init__(self):
+        self._l = _load("libfront_oracle.so")
+        self._l.front_oracle_dense_reference.restype = ctypes.c_int
+
+    def make_images(self, gray, levels):
+        g = np.ascontiguousarray(gray, np.float32)
+        h, w = g.shape
+        tot = sum((w >> l) * (h >> l) for l in range(levels))
+        dI = np.zeros(3 * tot, np.float32)
+        ag = np.zeros(tot, np.float32)
+        self._l.front_oracle_make_images(g.ctypes.data_as(_fp), w, h, levels, dI.ctypes.data_as(_fp), ag.ctypes.data_as(_fp))
+        out, off = [], 0
+        for l in range(levels):
+            wl, hl = w >> l, h >> l
+            out.append((dI[3 * off:3 * (off + wl * hl)].reshape(hl, wl, 3), ag[off:off + wl * hl].reshape(hl, wl)))
+            off += wl * hl
+        return out
+
+    def krki(self, T, fx, fy, cx, cy):
+        T = np.ascontiguousarray(T, np.float64)
+        a, b = np.zeros(9, np.float32), np.zeros(3, np.float32)
+        self._l.front_oracle_krki(T.ctypes.data_as(_dp), ctypes.c_float(fx), ctypes.c_float(fy), ctypes.c_float(cx),
+                                  ctypes.c_float(cy), a.ctypes.data_as(_fp), b.ctypes.data_as(_fp))
+        return a, b
+
+    def dense_reference(self, depth, T_depth_to_ref, K4, step, dense_only, sparse, idepth0, ref_gray):
+        """sparse = (pc_u, pc_v, pc_idepth, pc_color) with n_before + 1 entries each (last = stale slot) or None."""
+        d = np.ascontiguousarray(depth, np.float32)
+        h, w = d.shape
+        krki, kt = self.krki(T_depth_to_ref, *K4)
+        nb = 0 if sparse is None else len(sparse[0]) - 1
+        arrs = [np.zeros(nb + 1 + w * h, np.float32) for _ in range(4)]
+        if sparse is not None:
+            for a, s in zip(arrs, sparse):
+                a[:nb + 1] = s
+        proj = np.zeros(w * h, np.float32)
+        id0 = None if idepth0 is None else np.ascontiguousarray(idepth0, np.float32)
+        rg = np.ascontiguousarray(ref_gray, np.float32)
+        n = self._l.front_oracle_dense_reference(
+            d.ctypes.data_as(_fp), w, h, int(step), krki.ctypes.data_as(_fp), kt.ctypes.data_as(_fp), int(bool(dense_only)), nb,
+            None if id0 is None else id0.ctypes.data_as(_fp), rg.ctypes.data_as(_fp), arrs[0].ctypes.data_as(_fp),
+            arrs[1].ctypes.data_as(_fp), arrs[2].ctypes.data_as(_fp), arrs[3].ctypes.data_as(_fp), proj.ctypes.data_as(_fp))
+        return n, [a[:n + 1] for a in arrs], proj.reshape(h, w)

@@ -84,6 +84,44 @@ Eigen::Matrix<double, 6, 1> CudaCoarseTracker::calcResAndG(Eigen::Matrix<double,
   return r;
 }
 
+void CudaCoarseTracker::setNewFromPyramid(tdm_pyramid* pyramid, int level) {
+  chk(tdm_tracker_set_new_from_pyramid(handle_, pyramid, level), "CudaCoarseTracker::setNewFromPyramid");
+}
+
+int CudaCoarseTracker::setReferenceDense(tdm_fusion* fusion, int render_index, Eigen::Matrix<double, 4, 4> const& T_depth_to_ref,
+                                         int tracking_step, bool dense_only, int n_sparse, float const* pc_u, float const* pc_v,
+                                         float const* pc_idepth, float const* pc_color, float const* idepth0,
+                                         tdm_pyramid* ref_pyramid, float ref_exposure, Eigen::Vector2d const& ref_aff) {
+  double T[16];
+  to_row_major(T_depth_to_ref, T);
+  const double a[2] = {ref_aff(0), ref_aff(1)};
+  int pc_n = 0;
+  chk(tdm_tracker_set_reference_dense(handle_, nullptr, fusion, render_index, T, tracking_step, dense_only ? 1 : 0, n_sparse,
+                                      pc_u, pc_v, pc_idepth, pc_color, idepth0, nullptr, ref_pyramid, ref_exposure, a, &pc_n),
+      "CudaCoarseTracker::setReferenceDense");
+  return pc_n;
+}
+
+CudaCoarseTracker::TrackResult CudaCoarseTracker::track(Eigen::Matrix<double, 4, 4> const& refToNew, Eigen::Vector2d const& aff,
+                                                        float new_exposure, float coarseCutoffTH, int maxIterations,
+                                                        float lambdaExtrapolationLimit, bool fix_a, bool fix_b) {
+  double T[16];
+  to_row_major(refToNew, T);
+  const double a[2] = {aff(0), aff(1)};
+  tdm_track_result r;
+  chk(tdm_tracker_track(handle_, T, a, new_exposure, coarseCutoffTH, maxIterations, lambdaExtrapolationLimit, fix_a ? 1 : 0,
+                        fix_b ? 1 : 0, &r),
+      "CudaCoarseTracker::track");
+  TrackResult out;
+  for (int rr = 0; rr < 4; ++rr)
+    for (int c = 0; c < 4; ++c) out.refToNew(rr, c) = r.ref_to_new[4 * rr + c];
+  out.aff_g2l = Eigen::Vector2d(r.aff_g2l[0], r.aff_g2l[1]);
+  for (int i = 0; i < 6; ++i) out.res(i) = r.res[i];
+  out.iterations = r.iterations;
+  out.levelCutoffRepeat = r.cutoff_repeat;
+  return out;
+}
+
 void CudaCoarseTracker::synchronize() { chk(tdm_tracker_synchronize(handle_), "CudaCoarseTracker::synchronize"); }
 
 void CudaCoarseTracker::startTiming() {

@@ -4,4 +4,4 @@ of those classes over the C ABI in include/tandem_b200.h; all compute is in libt
 from ._lib import TandemError, lib  # noqa: F401
 from .mvsnet import DrMvsnet, DrMvsnetOutput, default_weights  # noqa: F401
 from .fusion import DrFusion, DrFusionOptions  # noqa: F401
-from .tracker import CudaCoarseTracker  # noqa: F401
+from .tracker import CudaCoarseTracker, ImagePyramid  # noqa: F401

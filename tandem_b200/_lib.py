@@ -48,6 +48,11 @@ class FusionStats(ctypes.Structure):
                 ("dropped_blocks", ctypes.c_longlong), ("candidate_blocks", ctypes.c_longlong)]
 
 
+class TrackResult(ctypes.Structure):
+    _fields_ = [("ref_to_new", ctypes.c_double * 16), ("aff_g2l", ctypes.c_double * 2), ("res", ctypes.c_double * 6),
+                ("iterations", ctypes.c_int), ("evaluations", ctypes.c_int), ("cutoff_repeat", ctypes.c_float), ("device_ms", ctypes.c_float)]
+
+
 def _declare(l):
     c = ctypes
     P = c.POINTER
@@ -91,6 +96,14 @@ def _declare(l):
         "tdm_tracker_calc_res_g": (i, [vp, dp, f, dp, f, dp, dp, dp]),
         "tdm_tracker_synchronize": (i, [vp]),
         "tdm_tracker_run_resident": (i, [vp, i, fp]),
+        "tdm_pyramid_create": (i, [i, i, i, i, P(vp)]),
+        "tdm_pyramid_destroy": (None, [vp]),
+        "tdm_pyramid_build": (i, [vp, fp]),
+        "tdm_pyramid_get_level": (i, [vp, i, fp, fp]),
+        "tdm_tracker_set_new_from_pyramid": (i, [vp, vp, i]),
+        "tdm_tracker_set_reference_dense": (i, [vp, fp, vp, i, dp, i, i, i, fp, fp, fp, fp, fp, fp, vp, f, dp, ip]),
+        "tdm_tracker_get_reference": (i, [vp, i, fp, fp, fp, fp]),
+        "tdm_tracker_track": (i, [vp, dp, dp, f, f, i, f, i, i, P(TrackResult)]),
     }
     missing = []
     for name, (res, args) in sigs.items():

@@ -453,6 +453,12 @@ class FusionImpl final : public FusionIface {
     return n;
   }
 
+  const float* render_depth_device(int i, void** ready_event, int* device) override {
+    TDM_CHECK(i >= 0 && i < n_rendered_, "render_depth_device: no such render");
+    if (ready_event) *ready_event = (void*)ev_render_;
+    if (device) *device = device_;
+    return d_depth_out_ + (size_t)i * d_.o.height * d_.o.width;
+  }
   void run_resident(int iters, float* ms_int, float* ms_render) override {
     TDM_CHECK(have_scan_, "run_resident: no scan submitted yet");
     TDM_CUDA(cudaSetDevice(device_));

@@ -19,6 +19,8 @@ class FusionIface {
   virtual void get_stats(tdm_fusion_stats* s) = 0;
   virtual long long dump_blocks(int* coords, void* voxels, size_t cap) = 0;
   virtual void run_resident(int iters, float* ms_int, float* ms_render) = 0;
+  // device copy of the i-th depth map of the last RenderAsync + the event recorded behind it (tracker reference, n1)
+  virtual const float* render_depth_device(int i, void** ready_event, int* device) = 0;
 };
 
 FusionIface* make_fusion(const tdm_fusion_options& o, int device);

@@ -101,3 +101,61 @@ def test_tracker_oracle_gauss_newton_descends():
     assert r1[0] / r1[1] < r0[0] / r0[1], "true relative pose must explain the new image better than identity"
     H, b = t.calcG(1.0, np.zeros(2))
     assert np.allclose(H, H.T) and np.all(np.linalg.eigvalsh(H[:6, :6]) > -1e-6)
+
+
+def test_front_oracle_pyramid_and_dense_reference():
+    """Sanity of the n2 / n1 restatements (oracle/front_oracle.c) on cases whose answer is known in closed form."""
+    from oracle.cpu import FrontOracle
+    f = FrontOracle()
+    h, w = 48, 64
+    yy, xx = np.mgrid[0:h, 0:w].astype(np.float32)
+    gray = 3.0 * xx + 5.0 * yy                                    # a plane: gradients are the slopes, 2x2 means stay planar
+    lv = f.make_images(gray, 3)
+    assert [l[0].shape for l in lv] == [(48, 64, 3), (24, 32, 3), (12, 16, 3)]
+    assert np.allclose(lv[0][0][2:-2, 2:-2, 1], 3.0) and np.allclose(lv[0][0][2:-2, 2:-2, 2], 5.0)
+    assert np.allclose(lv[1][0][2:-2, 2:-2, 1], 6.0) and np.allclose(lv[1][0][2:-2, 2:-2, 2], 10.0)
+    assert np.allclose(lv[1][0][..., 0], 0.25 * (gray[0::2, 0::2] + gray[0::2, 1::2] + gray[1::2, 0::2] + gray[1::2, 1::2]))
+    assert np.all(lv[0][0][0, :, 1:] == 0) and np.all(lv[0][0][-1, :, 1:] == 0)       # first / last row: no gradients
+    assert np.allclose(lv[0][1][3, 3], 3.0 ** 2 + 5.0 ** 2)
+    # identity transform: every valid interior pixel maps onto itself
+    depth = np.full((h, w), 2.0, np.float32)
+    depth[10, 10] = 0.0
+    K4 = (40.0, 40.0, 31.5, 23.5)
+    n, arrs, proj = f.dense_reference(depth, np.eye(4), K4, 1, True, None, None, gray)
+    interior = (w - 6) * (h - 6) - 1                              # 3 <= u <= w-4, 3 <= v <= h-4, minus the hole
+    assert n == interior and proj[10, 10] == -1 and proj[5, 5] == 2.0
+    assert arrs[0][0] == 0 and arrs[0][1] == 3 and arrs[1][1] == 3          # slot 0 = the skipped slot; first point (3,3)
+    assert np.allclose(arrs[2][1:n + 1], 0.5) and arrs[3][1] == gray[3, 3]
+    # nearest depth wins when two source pixels land on one target pixel
+    T = np.eye(4)
+    d2 = depth.copy()
+    d2[20, 20], d2[20, 21] = 1.0, 2.0
+    T[0, 3] = 0.0
+    _, _, proj2 = f.dense_reference(d2, T, K4, 1, True, None, None, gray)
+    assert proj2[20, 20] == 1.0
+    # sparse points stay in front, dense points skip pixels that already carry a sparse inverse depth
+    sparse = [np.array([7, 9, 0], np.float32), np.array([8, 8, 0], np.float32), np.array([0.4, 0.6, 0], np.float32),
+              np.array([10, 20, 0], np.float32)]
+    id0 = np.zeros((h, w), np.float32)
+    id0[8, 7], id0[8, 9] = 0.4, 0.6
+    n3, arrs3, _ = f.dense_reference(depth, np.eye(4), K4, 1, False, sparse, id0, gray)
+    assert n3 == 2 + interior - 2 and arrs3[0][0] == 7 and arrs3[0][1] == 9
+
+
+def test_lm_driver_converges_with_oracle_tracker():
+    """The host restatement of trackNewestCoarse's level loop (oracle/lm_driver.py) reduces the pose error and the energy."""
+    from oracle.lm_driver import se3_exp, track_level0
+    c = tracker_case(H=120, W=160, fx=80.0, fy=80.0, cx=79.5, cy=59.5)
+    t = TrackerOracle(c["w"], c["h"])
+    t.setK(c["w"], c["h"], c["fx"], c["fy"], c["cx"], c["cy"])
+    t.setReference(c["n"], c["pc_u"], c["pc_v"], c["pc_idepth"], c["pc_color"], c["ref_exposure"], c["ref_aff"])
+    t.setNew(c["dInew"])
+    r0 = t.calcRes(np.eye(4), c["new_exposure"], c["ref_aff"], 20.0)
+    r = track_level0(t, np.eye(4), c["ref_aff"], c["new_exposure"], max_iterations=10)
+    assert r["iterations"] >= 3 and r["res"][0] / r["res"][1] < 0.5 * r0[0] / r0[1]
+    D0 = np.linalg.inv(c["refToNew"])
+    D1 = np.linalg.inv(c["refToNew"]) @ r["refToNew"]
+    assert np.linalg.norm(D1[:3, 3]) < 0.5 * np.linalg.norm(D0[:3, 3])
+    E = se3_exp([0.1, -0.2, 0.3, 0.02, -0.01, 0.03])
+    assert np.allclose(E[:3, :3] @ E[:3, :3].T, np.eye(3), atol=1e-12) and abs(np.linalg.det(E[:3, :3]) - 1) < 1e-12
+    assert np.allclose(se3_exp(np.zeros(6)), np.eye(4))
