@@ -8,6 +8,7 @@ timeout 300 python bench.py > gpurun_out/${R}_bench.json 2> gpurun_out/${R}_benc
 timeout 300 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/${R}_bench_reference.json 2>> gpurun_out/${R}_bench.err
 TOPK=80 timeout 200 python tools/quick_profile.py mixed16 > gpurun_out/${R}_kernels.txt 2>&1
 timeout 200 python tools/bench_fusion_tracker.py > gpurun_out/${R}_fusion_tracker.txt 2>&1
+timeout 300 python tools/bench_loop.py 120 > gpurun_out/${R}_loop.txt 2>&1
 # every launch of the bench command with its device time (cold-cache, serialised: shares, not absolutes)
 timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-file gpurun_out/${R}_launches.csv \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline --inflight 1 > gpurun_out/${R}_bench_under_ncu.log 2>&1

@@ -125,7 +125,7 @@ def main():
                                  "limiter (L1/TEX throughput includes shared memory), see DESIGN.md section 5."))
     json.dump(traffic, open(os.path.join(P, f"{R}_ncu_traffic.json"), "w"), indent=1)
     summarise_launches()
-    for f in ("bench.json", "bench_reference.json", "kernels.txt", "fusion_tracker.txt", "pytest_gpu.log"):
+    for f in ("bench.json", "bench_reference.json", "kernels.txt", "fusion_tracker.txt", "loop.txt", "pytest_gpu.log"):
         s = os.path.join(G, f"{R}_{f}")
         if os.path.exists(s):
             shutil.copy(s, os.path.join(P, f"{R}_{f}"))
