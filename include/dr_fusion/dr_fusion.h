@@ -67,7 +67,6 @@ public:
 
 private:
     tdm_fusion* handle_;
-    float mesh_lower_[3], mesh_upper_[3];
     int n_render_ = 0;
 };
 

@@ -123,10 +123,23 @@ int tdm_fusion_synchronize(tdm_fusion* h);
  * reads never cross ranks). Every rank integrates the same (broadcast) scans; renders are combined by a per-pixel
  * nearest-hit reduction (tandem_b200/parallel.py: reduce_nearest_hit). Call before the first scan. */
 int tdm_fusion_set_slab(tdm_fusion* h, int z_block_lo, int z_block_hi);
-/* Mesh (DrFusion::ExtractMeshAsync/GetMeshSync/GetMesh, dr_fusion.h:56-68): vertices as xyz float triples,
- * colours as rgb float triples, 3 vertices per triangle. Returns vertex count or <0. */
+/* Mesh (dr_fusion.h:56-68; TsdfVolume::ExtractMeshAsync / GetMeshSync / ExtractMesh, tsdf_volume.cu:739-839; kernel
+ * marching_cubes/mesh_extractor.cu:244-265): marching cubes over the cells of the box [lower, upper) at voxel spacing.
+ * Output layout of GetMeshSync: vertices as xyz float triples, colours as rgb float triples in [0,1], 3 consecutive
+ * vertices per triangle (no index buffer). Triangle ORDER is unspecified (the reference appends with atomicAdd).
+ *   tdm_fusion_extract_mesh_async = ExtractMeshAsync: launches the extraction on the fusion stream and returns; only legal
+ *     where IntegrateScanAsync is legal (tsdf_volume.cu:760-763) and not twice in a row (:769-772);
+ *   tdm_fusion_get_mesh = GetMeshSync: waits, copies 3*triangles vertices out, returns the vertex count (error if it exceeds
+ *     max_vertices, :796-799);
+ *   tdm_fusion_extract_mesh = TsdfVolume::ExtractMesh (blocking, no call-order check; DrFusion::GetMesh / SaveMeshToFile);
+ *     with vert == cols == NULL it only returns the vertex count and keeps the mesh on the device, so that the next call
+ *     (with buffers of that size) copies it out without extracting again. */
 long long tdm_fusion_extract_mesh(tdm_fusion* h, const float lower[3], const float upper[3],
                                   float* vert, float* cols, size_t max_vertices);
+int tdm_fusion_extract_mesh_async(tdm_fusion* h, const float lower[3], const float upper[3]);
+long long tdm_fusion_get_mesh(tdm_fusion* h, float* vert, float* cols, size_t max_vertices);
+/* Device time (CUDA events) of the last extraction: classify + scan + emit. */
+int tdm_fusion_last_mesh_ms(tdm_fusion* h, float* ms);
 /* Introspection for parity tests and the roofline: counters of the last integrate / render. */
 typedef struct tdm_fusion_stats {
   long long allocated_blocks;      /* total blocks in the map */
@@ -138,8 +151,13 @@ int tdm_fusion_get_stats(tdm_fusion* h, tdm_fusion_stats* out);
 /* Dump the block map: xyz int triples (sorted lexicographically) into coords (capacity in blocks) and,
  * if voxels != NULL, 512 voxels per block as {float sdf; uint8 c0,c1,c2; uint8 weight} (8 B each). */
 long long tdm_fusion_dump_blocks(tdm_fusion* h, int* coords, void* voxels, size_t capacity_blocks);
-/* Device-resident measurement of integrate+render for the last submitted scan/pose. */
+/* Device-resident measurement of integrate+render for the last submitted scan/pose (sums over iters);
+ * tdm_fusion_last_alloc_ms: the allocation kernel's share of ms_integrate, per iteration. */
 int tdm_fusion_run_resident(tdm_fusion* h, int iters, float* ms_integrate, float* ms_render);
+int tdm_fusion_last_alloc_ms(tdm_fusion* h, float* ms);
+/* A/B switches for measurements (results are bit-identical either way): "alloc_filter" (CTA-level shared-memory filter in
+ * front of the hash table during allocation, default 1), "raycast_cache8" (8-entry per-ray block cache, default 1). */
+int tdm_fusion_set_option(tdm_fusion* h, const char* name, int value);
 
 /* ------------------------------------------------------------------------------------------------
  * Coarse tracker, pyramid level 0 (replaces CudaCoarseTracker; cuda_coarse_tracker.h:9-82)

@@ -76,6 +76,19 @@ class TsdfOracle:
         return dict(allocated_blocks=out[0], visible_blocks=out[1], dropped_blocks=out[2], candidate_blocks=out[3],
                     render_distinct_voxels=out[4])
 
+    def extract_mesh(self, lower, upper):
+        """Brute-force marching cubes over the box (mesh_extractor.cu:244-265) -> (vert (n,3), cols (n,3) rgb)."""
+        lo = np.ascontiguousarray(lower, np.float32)
+        up = np.ascontiguousarray(upper, np.float32)
+        self._l.tsdf_oracle_extract_mesh.restype = ctypes.c_long
+        n = self._l.tsdf_oracle_extract_mesh(self._h, lo.ctypes.data_as(_fp), up.ctypes.data_as(_fp), None, None, ctypes.c_long(0))
+        vert = np.empty((n, 3), np.float32)
+        cols = np.empty((n, 3), np.float32)
+        m = self._l.tsdf_oracle_extract_mesh(self._h, lo.ctypes.data_as(_fp), up.ctypes.data_as(_fp), vert.ctypes.data_as(_fp),
+                                             cols.ctypes.data_as(_fp), ctypes.c_long(n))
+        assert m == n
+        return vert, cols
+
     def dump_blocks(self):
         n = self.stats()["allocated_blocks"]
         coords = np.empty((n, 3), np.int32)

@@ -2,6 +2,7 @@
 // (tandem/libdr/dr_fusion/src/dr_fusion/dr_fusion.h), compiled unmodified from /root/reference by
 // oracle/ref_build.mk into oracle/_ref/libdr_fusion_ref.so.  Used only by tests (-m gpu) to pin our CPU oracle and
 // CUDA path against the reference run on the same B200, and as an on-box GPU baseline in profiles/.
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -27,3 +28,17 @@ void ref_fusion_render(void* h, const float* pose, unsigned char* bgr_out, float
 void ref_fusion_sync(void* h) { static_cast<DrFusion*>(h)->Synchronize(); }
 
 }  // extern "C"
+
+// DrFusion::GetMesh (dr_fusion.cpp:95-149) - vertices / colours copied out, the reference's mallocs released
+extern "C" long long ref_fusion_get_mesh(void* h, float* lower, float* upper, float* vert, float* cols, long long cap_vertices) {
+  DrMesh m = static_cast<DrFusion*>(h)->GetMesh(lower, upper);
+  const long long n = (long long)m.num;
+  const long long k = n < cap_vertices ? n : cap_vertices;
+  if (k > 0 && vert && cols) {
+    std::memcpy(vert, m.vert, (size_t)k * 3 * sizeof(float));
+    std::memcpy(cols, m.cols, (size_t)k * 3 * sizeof(float));
+  }
+  free(m.vert);
+  free(m.cols);
+  return n;
+}

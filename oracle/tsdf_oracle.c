@@ -369,3 +369,107 @@ long tsdf_oracle_dump(const Tsdf* t, int* coords, Voxel* voxels, long cap) {
   free(tmp);
   return n;
 }
+
+/* ================= marching cubes =================
+ * Restates ExtractMeshKernel / ExtractMeshAtPosition / TrilinearInterpolation / VertexInterpolation
+ * (marching_cubes/mesh_extractor.cu:24-104, 106-135, 137-243, 244-265) and the vertex / colour layout of
+ * TsdfVolume::GetMeshSync (tsdf_volume.cu:781-839): brute force over every cell of the bounding box in linear cell
+ * order (x fastest), so the oracle's output order is the reference's for a single thread; the reference appends with
+ * atomicAdd (mesh.cu:21-24), i.e. its order is arbitrary -> tests compare sorted triangle sets.
+ * Where the reference's nvcc build (default -fmad=true) contracts a*b+c, this restatement calls fmaf() explicitly
+ * (the file is built with -ffp-contract=off, so nothing else is fused): the cell position i*s+lower
+ * (mesh_extractor.cu:258-261), the trilinear accumulation distance += W*sdf (:41-96) and the edge vertex
+ * p1+mu*(p2-p1) (:121-123).  The CUDA kernel uses the same fmaf / __f*_rn sequence, so the two are bit-identical.
+ */
+#include "mc_tables.h"
+
+static int w2g1(float x, float s) { return (int)(x / s + signf_(x) * 0.5f); } /* one axis of tsdf_volume.cu:109-113 */
+
+static Voxel voxel_at(Tsdf* t, int gx, int gy, int gz) { /* tsdf_volume.cu:115-159 from a global voxel index */
+  int B = t->o.block_size;
+  i3 blk = {fdiv(gx, B), fdiv(gy, B), fdiv(gz, B)};
+  int ptr = find_entry(t, blk);
+  Voxel v;
+  if (ptr < 0) { memset(&v, 0, sizeof v); return v; }
+  return t->voxels[(long)ptr * B * B * B + pmod(gx, B) * B * B + pmod(gy, B) * B + pmod(gz, B)];
+}
+
+/* mesh_extractor.cu:24-104 - false as soon as one of the eight voxels has weight 0; only the distance is consumed */
+static int mesh_trilinear(Tsdf* t, f3 p, float* dist_out) {
+  float s = t->o.voxel_size;
+  float h = s / 2.0f;
+  f3 pd = {p.x - h, p.y - h, p.z - h};
+  f3 vp = {p.x / s, p.y / s, p.z / s};
+  float wx = vp.x - floorf(vp.x), wy = vp.y - floorf(vp.y), wz = vp.z - floorf(vp.z);
+  static const int ox[8] = {0, 1, 0, 0, 1, 0, 1, 1}, oy[8] = {0, 0, 1, 0, 1, 1, 0, 1}, oz[8] = {0, 0, 0, 1, 0, 1, 1, 1};
+  float dist = 0.0f;
+  for (int k = 0; k < 8; ++k) {
+    f3 q = {pd.x + (ox[k] ? s : 0.0f), pd.y + (oy[k] ? s : 0.0f), pd.z + (oz[k] ? s : 0.0f)};
+    Voxel v = voxel_at(t, w2g1(q.x, s), w2g1(q.y, s), w2g1(q.z, s));
+    if (v.w == 0) return 0;
+    float W = ((ox[k] ? wx : 1.0f - wx) * (oy[k] ? wy : 1.0f - wy)) * (oz[k] ? wz : 1.0f - wz);
+    dist = fmaf(W, v.sdf, dist);
+  }
+  *dist_out = dist;
+  return 1;
+}
+
+/* cube corners in the reference's bit order (mesh_extractor.cu:188-196): 010,110,100,000,011,111,101,001 */
+static const int kCornerX[8] = {0, 1, 1, 0, 0, 1, 1, 0}, kCornerY[8] = {1, 1, 0, 0, 1, 1, 0, 0}, kCornerZ[8] = {0, 0, 0, 0, 1, 1, 1, 1};
+static const int kEdgeA[12] = {0, 1, 2, 3, 4, 5, 6, 7, 0, 1, 2, 3}, kEdgeB[12] = {1, 2, 3, 0, 5, 6, 7, 4, 4, 5, 6, 7}; /* :203-237 */
+
+static float lerp_axis(float mu, float a, float b) { return fmaf(mu, b - a, a); } /* mesh_extractor.cu:121-123 */
+
+/* vert/cols: xyz / rgb float triples per vertex (three vertices per triangle), cap in vertices. returns #vertices */
+long tsdf_oracle_extract_mesh(Tsdf* t, const float* lower, const float* upper, float* vert, float* cols, long cap) {
+  float s = t->o.voxel_size;
+  int n[3];
+  for (int a = 0; a < 3; ++a) n[a] = to_int_sat(fabsf(lower[a] - upper[a]) / s); /* :248-252 */
+  long nv = 0;
+  float h = s / 2.0f;
+  for (int iz = 0; iz < n[2]; ++iz)
+    for (int iy = 0; iy < n[1]; ++iy)
+      for (int ix = 0; ix < n[0]; ++ix) {
+        f3 pos = {fmaf((float)ix, s, lower[0]), fmaf((float)iy, s, lower[1]), fmaf((float)iz, s, lower[2])};
+        /* cheap reject first (result-neutral): the p000 sample's first voxel must exist (it is tested first, :146-149) */
+        f3 cp[8];
+        float d[8];
+        /* evaluation order of the reference: 000,100,010,001,110,011,101,111 -> our corner ids 3,2,0,7,1,4,6,5 */
+        static const int order[8] = {3, 2, 0, 7, 1, 4, 6, 5};
+        int ok = 1;
+        for (int k = 0; k < 8 && ok; ++k) {
+          int c = order[k];
+          cp[c].x = pos.x + (kCornerX[c] ? h : -h);
+          cp[c].y = pos.y + (kCornerY[c] ? h : -h);
+          cp[c].z = pos.z + (kCornerZ[c] ? h : -h);
+          ok = mesh_trilinear(t, cp[c], &d[c]);
+        }
+        if (!ok) continue;
+        int cube = 0;
+        for (int c = 0; c < 8; ++c) if (d[c] < 0.0f) cube |= 1 << c;
+        uint64_t tri = kMcTri[cube];
+        if ((tri & 0xF) == 0xF) continue; /* edgeTable[cubeindex] == 0 */
+        Voxel vc = voxel_at(t, w2g1(pos.x, s), w2g1(pos.y, s), w2g1(pos.z, s)); /* :200 */
+        float col[3] = {(float)vc.c[2] / 255.f, (float)vc.c[1] / 255.f, (float)vc.c[0] / 255.f}; /* GetMeshSync: z,y,x */
+        for (int k = 0; k < 15; ++k) {
+          int e = (int)((tri >> (4 * k)) & 0xF);
+          if (e == 0xF) break;
+          int a = kEdgeA[e], b = kEdgeB[e];
+          f3 p;
+          float d1 = d[a], d2 = d[b];
+          if (fabsf(0.0f - d1) < 0.00001f) p = cp[a];
+          else if (fabsf(0.0f - d2) < 0.00001f) p = cp[b];
+          else if (fabsf(d1 - d2) < 0.00001f) p = cp[a];
+          else {
+            float mu = (0.0f - d1) / (d2 - d1);
+            p.x = lerp_axis(mu, cp[a].x, cp[b].x); p.y = lerp_axis(mu, cp[a].y, cp[b].y); p.z = lerp_axis(mu, cp[a].z, cp[b].z);
+          }
+          if (nv < cap) {
+            vert[3 * nv] = p.x; vert[3 * nv + 1] = p.y; vert[3 * nv + 2] = p.z;
+            cols[3 * nv] = col[0]; cols[3 * nv + 1] = col[1]; cols[3 * nv + 2] = col[2];
+          }
+          nv++;
+        }
+      }
+  return nv;
+}

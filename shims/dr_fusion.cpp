@@ -49,31 +49,29 @@ void DrFusion::GetRenderResult(std::vector<unsigned char*>& bgr, std::vector<flo
   if (tdm_fusion_get_render_result(handle_, bgr.data(), depth.data(), n_render_) != TDM_OK) die("DrFusion::GetRenderResult");
 }
 
-void DrFusion::ExtractMeshAsync(float lower_corner[3], float upper_corner[3]) {
-  std::memcpy(mesh_lower_, lower_corner, 12);
-  std::memcpy(mesh_upper_, upper_corner, 12);
+void DrFusion::ExtractMeshAsync(float lower_corner[3], float upper_corner[3]) {   // dr_fusion.cpp:151-153
+  if (tdm_fusion_extract_mesh_async(handle_, lower_corner, upper_corner) != TDM_OK) die("DrFusion::ExtractMeshAsync");
 }
 
-void DrFusion::GetMeshSync() {
-  long long n = tdm_fusion_extract_mesh(handle_, mesh_lower_, mesh_upper_, dr_mesh_vert, dr_mesh_cols, dr_mesh_num_max);
+void DrFusion::GetMeshSync() {   // dr_fusion.cpp:155-157: fills dr_mesh_num / dr_mesh_vert / dr_mesh_cols
+  long long n = tdm_fusion_get_mesh(handle_, dr_mesh_vert, dr_mesh_cols, dr_mesh_num_max);
   if (n < 0) die("DrFusion::GetMeshSync");
   dr_mesh_num = (size_t)n;
 }
 
-struct DrMesh DrFusion::GetMesh(float lower_corner[3], float upper_corner[3]) {
-  ExtractMeshAsync(lower_corner, upper_corner);
-  GetMeshSync();
+struct DrMesh DrFusion::GetMesh(float lower_corner[3], float upper_corner[3]) {   // dr_fusion.cpp:95-149 (caller frees)
   DrMesh m;
-  m.num = dr_mesh_num;
-  m.vert = (float*)malloc(m.num * 3 * sizeof(float));
-  m.cols = (float*)malloc(m.num * 3 * sizeof(float));
-  std::memcpy(m.vert, dr_mesh_vert, m.num * 3 * sizeof(float));
-  std::memcpy(m.cols, dr_mesh_cols, m.num * 3 * sizeof(float));
+  long long n = tdm_fusion_extract_mesh(handle_, lower_corner, upper_corner, nullptr, nullptr, 0);   // count, mesh stays on the device
+  if (n < 0) die("DrFusion::GetMesh");
+  m.num = (size_t)n;
+  m.vert = (float*)malloc((m.num + 1) * 3 * sizeof(float));
+  m.cols = (float*)malloc((m.num + 1) * 3 * sizeof(float));
+  if (tdm_fusion_extract_mesh(handle_, lower_corner, upper_corner, m.vert, m.cols, m.num) < 0) die("DrFusion::GetMesh");
   return m;
 }
 
 void DrFusion::SaveMeshToFile(std::string const& filename, float lower_corner[3], float upper_corner[3]) {
-  DrMesh m = GetMesh(lower_corner, upper_corner);  // .obj with per-vertex colours, as mesh.cu:24-66
+  DrMesh m = GetMesh(lower_corner, upper_corner);  // .obj, one "v x y z r g b" line per vertex then the faces: Mesh::SaveToFile(bgr=true), mesh.cu:26-66
   std::ofstream f(filename);
   for (size_t i = 0; i < m.num; ++i)
     f << "v " << m.vert[3 * i] << " " << m.vert[3 * i + 1] << " " << m.vert[3 * i + 2] << " " << m.cols[3 * i] << " "

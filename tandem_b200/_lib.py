@@ -83,6 +83,11 @@ def _declare(l):
         "tdm_fusion_synchronize": (i, [vp]),
         "tdm_fusion_set_slab": (i, [vp, i, i]),
         "tdm_fusion_extract_mesh": (c.c_longlong, [vp, fp, fp, fp, fp, c.c_size_t]),
+        "tdm_fusion_extract_mesh_async": (i, [vp, fp, fp]),
+        "tdm_fusion_get_mesh": (c.c_longlong, [vp, fp, fp, c.c_size_t]),
+        "tdm_fusion_last_mesh_ms": (i, [vp, fp]),
+        "tdm_fusion_set_option": (i, [vp, cp, i]),
+        "tdm_fusion_last_alloc_ms": (i, [vp, fp]),
         "tdm_fusion_get_stats": (i, [vp, P(FusionStats)]),
         "tdm_fusion_dump_blocks": (c.c_longlong, [vp, ip, vp, c.c_size_t]),
         "tdm_fusion_run_resident": (i, [vp, i, fp, fp]),

@@ -61,8 +61,42 @@ long long tdm_fusion_extract_mesh(tdm_fusion* h, const float lower[3], const flo
                                   size_t max_vertices) {
   TDM_API_BEGIN
   TDM_CHECK(h && lower && upper, "null argument");
-  (void)vert; (void)cols; (void)max_vertices;
-  throw tdm::Error("tdm_fusion_extract_mesh: marching cubes (SURVEY.md §8f row n4, viewer output only) is not built yet");
+  if (!h->impl->mesh_pending()) h->impl->extract_mesh_async(lower, upper, false);
+  return h->impl->get_mesh(vert, cols, max_vertices, false, /*query_only=*/vert == nullptr && cols == nullptr);
+  TDM_API_END
+}
+int tdm_fusion_extract_mesh_async(tdm_fusion* h, const float lower[3], const float upper[3]) {
+  TDM_API_BEGIN
+  TDM_CHECK(h && lower && upper, "null argument");
+  h->impl->extract_mesh_async(lower, upper, true);
+  return TDM_OK;
+  TDM_API_END
+}
+long long tdm_fusion_get_mesh(tdm_fusion* h, float* vert, float* cols, size_t max_vertices) {
+  TDM_API_BEGIN
+  TDM_CHECK(h, "null handle");
+  return h->impl->get_mesh(vert, cols, max_vertices, true, false);
+  TDM_API_END
+}
+int tdm_fusion_last_mesh_ms(tdm_fusion* h, float* ms) {
+  TDM_API_BEGIN
+  TDM_CHECK(h && ms, "null argument");
+  *ms = h->impl->last_mesh_ms();
+  return TDM_OK;
+  TDM_API_END
+}
+int tdm_fusion_set_option(tdm_fusion* h, const char* name, int value) {
+  TDM_API_BEGIN
+  TDM_CHECK(h && name, "null argument");
+  h->impl->set_option(name, value);
+  return TDM_OK;
+  TDM_API_END
+}
+int tdm_fusion_last_alloc_ms(tdm_fusion* h, float* ms) {
+  TDM_API_BEGIN
+  TDM_CHECK(h && ms, "null argument");
+  *ms = h->impl->last_alloc_ms();
+  return TDM_OK;
   TDM_API_END
 }
 int tdm_fusion_get_stats(tdm_fusion* h, tdm_fusion_stats* out) {

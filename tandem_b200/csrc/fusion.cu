@@ -17,7 +17,11 @@
 // the reference's; geometry that decides integers uses __f*_rn intrinsics so it is bit-identical to the CPU
 // oracle (oracle/tsdf_oracle.c) which evaluates the same expressions without FMA contraction.
 #include <algorithm>
+#include <cmath>
+#include <cstdlib>
 #include <cstring>
+#include <string>
+#include <type_traits>
 #include <vector>
 
 #include "fusion.h"
@@ -84,33 +88,49 @@ __device__ __forceinline__ long long hash_bucket(const tdm_fusion_options& o, in
   return (long long)r * o.bucket_size;
 }
 
-__device__ void insert_block(const FusionDev& d, int x, int y, int z) {
-  if (x <= -kKeyBias || x >= kKeyBias || y <= -kKeyBias || y >= kKeyBias || z <= -kKeyBias || z >= kKeyBias) return;
-  if (z < d.slab_lo || z >= d.slab_hi) return;   // another rank's Z-slab
+// returns true when the block is in the table after the call (found or inserted), false when it was rejected / dropped
+__device__ bool insert_block(const FusionDev& d, int x, int y, int z) {
+  if (x <= -kKeyBias || x >= kKeyBias || y <= -kKeyBias || y >= kKeyBias || z <= -kKeyBias || z >= kKeyBias) return false;
+  if (z < d.slab_lo || z >= d.slab_hi) return false;   // another rank's Z-slab
   const unsigned long long key = pack_key(x, y, z);
   const long long b = hash_bucket(d.o, x, y, z);
   for (int i = 0; i < d.o.bucket_size; ++i) {
     unsigned long long cur = d.keys[b + i];
-    if (cur == key) return;
+    if (cur == key) return true;
     if (cur == kEmptyKey) {
       cur = atomicCAS(&d.keys[b + i], kEmptyKey, key);
-      if (cur == key) return;           // somebody else inserted the same block
+      if (cur == key) return true;      // somebody else inserted the same block
       if (cur == kEmptyKey) {           // we own the slot: take a voxel block and publish it in the list
         const int ptr = atomicAdd(&d.counters[0], 1);
         if (ptr >= d.o.num_blocks) {    // heap exhausted (heap.cu:16-18 aborts; we drop and count)
           atomicAdd(&d.counters[1], 1);
           d.ptrs[b + i] = -1;
-          return;
+          return false;
         }
         d.ptrs[b + i] = ptr;
         d.list[ptr] = make_int4(x, y, z, ptr);
         atomicAdd(&d.counters[3], 1);
-        return;
+        return true;
       }
       // slot taken by a different block in the meantime: keep scanning
     }
   }
   atomicAdd(&d.counters[1], 1);  // bucket full: block dropped (hash_table.cu:103-115 returns without allocating)
+  return false;
+}
+
+// CTA-level filter in front of the table: the 128 rays of a CTA are neighbours and walk through the same few hundred blocks,
+// so most insert attempts are repeats.  Direct-mapped set of keys KNOWN to be in the table (only successful inserts / finds
+// are remembered, so drops are still counted per attempt as in the reference); races between threads are benign.
+constexpr int kAllocFilter = 1024;
+template <bool FILTER>
+__device__ __forceinline__ void insert_filtered(const FusionDev& d, unsigned long long* sfilter, int x, int y, int z) {
+  if (!FILTER) { insert_block(d, x, y, z); return; }
+  const unsigned long long key = pack_key(x, y, z);
+  const unsigned h = ((unsigned)x * 73856093u ^ (unsigned)y * 19349669u ^ (unsigned)z * 83492791u);
+  const int slot = (int)((h ^ (h >> 11)) & (kAllocFilter - 1));
+  if (sfilter[slot] == key) return;
+  if (insert_block(d, x, y, z)) sfilter[slot] = key;
 }
 
 __device__ __forceinline__ int find_block(const FusionDev& d, int x, int y, int z) {  // hash_table.cu:141-155
@@ -123,10 +143,16 @@ __device__ __forceinline__ int find_block(const FusionDev& d, int x, int y, int 
 }
 
 // ---------------------------------------------------------------------------------------------- K5
-__global__ void k_allocate(FusionDev d, const float* __restrict__ depth, Mat4 T) {
+template <bool FILTER>
+__global__ void __launch_bounds__(128) k_allocate(FusionDev d, const float* __restrict__ depth, Mat4 T) {
   const tdm_fusion_options& o = d.o;
   const int n = o.height * o.width;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  __shared__ unsigned long long sfilter[FILTER ? kAllocFilter : 1];
+  if (FILTER) {
+    for (int k = threadIdx.x; k < kAllocFilter; k += blockDim.x) sfilter[k] = kEmptyKey;
+    __syncthreads();
+  }
   if (i >= n) return;
   const float dz = depth[i];
   if (dz < o.min_sensor_depth || dz > o.max_sensor_depth) return;
@@ -154,8 +180,8 @@ __global__ void k_allocate(FusionDev d, const float* __restrict__ depth, Mat4 T)
   if (bp.x != be.x && dir.x < 0) { diff.x--; neg = true; }
   if (bp.y != be.y && dir.y < 0) { diff.y--; neg = true; }
   if (bp.z != be.z && dir.z < 0) { diff.z--; neg = true; }
-  insert_block(d, bp.x, bp.y, bp.z);
-  if (neg) { bp.x += diff.x; bp.y += diff.y; bp.z += diff.z; insert_block(d, bp.x, bp.y, bp.z); }
+  insert_filtered<FILTER>(d, sfilter, bp.x, bp.y, bp.z);
+  if (neg) { bp.x += diff.x; bp.y += diff.y; bp.z += diff.z; insert_filtered<FILTER>(d, sfilter, bp.x, bp.y, bp.z); }
   int guard = 0;
   while ((bp.x != be.x || bp.y != be.y || bp.z != be.z) && guard++ < 100000) {
     if (mt.x < mt.y) {
@@ -163,7 +189,7 @@ __global__ void k_allocate(FusionDev d, const float* __restrict__ depth, Mat4 T)
     } else {
       if (mt.y < mt.z) { bp.y += step.y; mt.y = add_(mt.y, dt.y); } else { bp.z += step.z; mt.z = add_(mt.z, dt.z); }
     }
-    insert_block(d, bp.x, bp.y, bp.z);
+    insert_filtered<FILTER>(d, sfilter, bp.x, bp.y, bp.z);
   }
 }
 
@@ -232,23 +258,52 @@ k_integrate(FusionDev d, const unsigned char* __restrict__ bgr, const float* __r
 }
 
 // ---------------------------------------------------------------------------------------------- K7
-struct BlockCache { int x, y, z, ptr; };
+// Per-ray block caches in front of the hash table.
+//  Cache1: the last block only.
+//  Cache8: eight entries, direct-mapped by the parity of the block coordinate (slot = x&1 | (y&1)<<1 | (z&1)<<2).  The nine
+//          voxel reads of one trilinear sample span at most two blocks per axis, which always land in different slots, so
+//          a sample never evicts what it still needs and a ray only probes the table when it ENTERS a block.
+//          Lives in shared memory (column per thread, conflict-free).
+struct Cache1 {
+  int x, y, z, ptr;
+  __device__ __forceinline__ void init() { x = y = z = INT_MIN; ptr = -1; }
+  __device__ __forceinline__ int find(const FusionDev& d, int bx, int by, int bz) {
+    if (bx != x || by != y || bz != z) { x = bx; y = by; z = bz; ptr = find_block(d, bx, by, bz); }
+    return ptr;
+  }
+};
+struct Cache8 {
+  unsigned long long* keys;   // [8][256] in shared memory, this thread's column
+  int* ptrs;
+  __device__ __forceinline__ void init() {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) keys[k * 256] = kEmptyKey;
+  }
+  __device__ __forceinline__ int find(const FusionDev& d, int bx, int by, int bz) {
+    if (bx <= -kKeyBias || bx >= kKeyBias || by <= -kKeyBias || by >= kKeyBias || bz <= -kKeyBias || bz >= kKeyBias) return -1;
+    const int slot = ((bx & 1) | ((by & 1) << 1) | ((bz & 1) << 2)) * 256;
+    const unsigned long long key = pack_key(bx, by, bz);
+    if (keys[slot] == key) return ptrs[slot];
+    const int p = find_block(d, bx, by, bz);
+    keys[slot] = key;
+    ptrs[slot] = p;
+    return p;
+  }
+};
 
-__device__ __forceinline__ uint2 get_voxel(const FusionDev& d, float3 p, BlockCache& bc) {  // tsdf_volume.cu:109-159
+template <class Cache>
+__device__ __forceinline__ uint2 get_voxel(const FusionDev& d, float3 p, Cache& bc) {  // tsdf_volume.cu:109-159
   const float s = d.o.voxel_size;
   const int gx = (int)add_(div_(p.x, s), mul_((float)sgn(p.x), 0.5f));
   const int gy = (int)add_(div_(p.y, s), mul_((float)sgn(p.y), 0.5f));
   const int gz = (int)add_(div_(p.z, s), mul_((float)sgn(p.z), 0.5f));
-  const int bx = gx >> 3, by = gy >> 3, bz = gz >> 3;  // floor division by the block size 8
-  if (bx != bc.x || by != bc.y || bz != bc.z) {
-    bc.x = bx; bc.y = by; bc.z = bz;
-    bc.ptr = find_block(d, bx, by, bz);
-  }
-  if (bc.ptr < 0) return make_uint2(0u, 0u);
-  return __ldg(d.voxels + (size_t)bc.ptr * 512 + (gx & 7) * 64 + (gy & 7) * 8 + (gz & 7));
+  const int ptr = bc.find(d, gx >> 3, gy >> 3, gz >> 3);  // floor division by the block size 8
+  if (ptr < 0) return make_uint2(0u, 0u);
+  return __ldg(d.voxels + (size_t)ptr * 512 + (gx & 7) * 64 + (gy & 7) * 8 + (gz & 7));
 }
 
-__device__ uint2 get_interpolated(const FusionDev& d, float3 p, BlockCache& bc) {  // tsdf_volume.cu:161-289
+template <class Cache>
+__device__ uint2 get_interpolated(const FusionDev& d, float3 p, Cache& bc) {  // tsdf_volume.cu:161-289
   const uint2 v0 = get_voxel(d, p, bc);
   if ((v0.y >> 24) == 0) return v0;
   const float s = d.o.voxel_size;
@@ -275,14 +330,19 @@ __device__ uint2 get_interpolated(const FusionDev& d, float3 p, BlockCache& bc) 
   return make_uint2(__float_as_uint(dist), col | (v0.y & 0xFF000000u));
 }
 
+template <bool CACHE8>
 __global__ void __launch_bounds__(256)
 k_raycast(FusionDev d, Mat4 T, unsigned char* __restrict__ bgr_out, float* __restrict__ depth_out) {
   const tdm_fusion_options& o = d.o;
+  __shared__ unsigned long long skeys[CACHE8 ? 8 * 256 : 1];
+  __shared__ int sptrs[CACHE8 ? 8 * 256 : 1];
   const int x = blockIdx.x * 16 + (threadIdx.x & 15);
   const int y = blockIdx.y * 16 + (threadIdx.x >> 4);
   if (x >= o.width || y >= o.height) return;
   const int i = y * o.width + x;
-  BlockCache bc = {INT_MIN, INT_MIN, INT_MIN, -1};
+  typename std::conditional<CACHE8, Cache8, Cache1>::type bc;
+  if constexpr (CACHE8) { bc.keys = skeys + threadIdx.x; bc.ptrs = sptrs + threadIdx.x; }
+  bc.init();
   float cur = 0.f;
   int guard = 0;
   while (cur < o.max_sensor_depth && guard++ < 100000) {
@@ -305,6 +365,59 @@ k_raycast(FusionDev d, Mat4 T, unsigned char* __restrict__ bgr_out, float* __res
 __global__ void k_fill_keys(unsigned long long* keys, int* ptrs, long long n) {
   long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (i < n) { keys[i] = kEmptyKey; ptrs[i] = -1; }
+}
+
+#include "mesh.cuh"
+
+// ---- host side of the mesh extractor: the per-axis tables (same fp32 expression sequence as the reference) ----
+inline int w2g1_host(float x, float s) {   // one axis of WorldToGlobalVoxel, tsdf_volume.cu:109-113
+  const float sg = (float)((x > 0) - (x < 0));
+  return (int)(x / s + sg * 0.5f);
+}
+inline int floor_div8(int v) { return v >> 3; }
+
+struct MeshAxisHost {
+  std::vector<MeshAxisCell> cells;
+  std::vector<int2> ranges;
+  int bmin = 0, nb = 0;
+};
+
+MeshAxisHost build_mesh_axis(float lower, float upper, float s) {
+  MeshAxisHost A;
+  const float ext = fabsf(lower - upper) / s;                 // mesh_extractor.cu:248-252
+  TDM_CHECK(ext == ext && ext < 4.0e6f && fabsf(lower) < 1.0e5f && fabsf(upper) < 1.0e5f, "mesh bounding box too large");
+  const int n = (int)ext;
+  if (n <= 0) return A;
+  const float h = s / 2.0f;
+  A.cells.resize(n);
+  for (int i = 0; i < n; ++i) {
+    MeshAxisCell c;
+    const float pos = std::fmaf((float)i, s, lower);          // mesh_extractor.cu:258-261 (contracted by the reference's nvcc)
+    c.cM = pos + (-h);                                        // :143-144 (M = -P)
+    c.cP = pos + h;
+    const float pdM = c.cM - h, pdP = c.cP - h;               // :28-30
+    const float vpM = c.cM / s, vpP = c.cP / s;               // :31
+    c.wM = vpM - floorf(vpM);                                 // :32-34
+    c.wP = vpP - floorf(vpP);
+    c.gMA = w2g1_host(pdM + 0.0f, s); c.gMB = w2g1_host(pdM + s, s);
+    c.gPA = w2g1_host(pdP + 0.0f, s); c.gPB = w2g1_host(pdP + s, s);
+    c.gC = w2g1_host(pos, s);
+    A.cells[i] = c;
+    const int blk = floor_div8(c.gMA);
+    const int lo = std::min(std::min(c.gMA, c.gMB), std::min(std::min(c.gPA, c.gPB), c.gC));
+    const int hi = std::max(std::max(c.gMA, c.gMB), std::max(std::max(c.gPA, c.gPB), c.gC));
+    TDM_CHECK(lo >= blk * 8 && hi < blk * 8 + kMeshTile, "mesh: voxel reach of a cell exceeds the staged tile");
+    TDM_CHECK(i == 0 || c.gMA >= A.cells[i - 1].gMA, "mesh: voxel index is not monotone in the cell index");
+  }
+  A.bmin = floor_div8(A.cells[0].gMA);
+  A.nb = floor_div8(A.cells[n - 1].gMA) - A.bmin + 1;
+  A.ranges.assign(A.nb, make_int2(0, 0));
+  for (int i = 0; i < n; ++i) {
+    int2& r = A.ranges[floor_div8(A.cells[i].gMA) - A.bmin];
+    if (r.y == 0) r.x = i;
+    r.y++;
+  }
+  return A;
 }
 
 }  // namespace
@@ -364,6 +477,10 @@ class FusionImpl final : public FusionIface {
     for (int half = 0; half < 2; ++half) { cudaFreeHost(h_bgr_out_[half]); cudaFreeHost(h_depth_out_[half]); }
     cudaFree(d_bgr_out_); cudaFree(d_depth_out_); cudaFreeHost(h_counters_);
     cudaEventDestroy(ev_int_); cudaEventDestroy(ev_render_);
+    cudaFree(d_mesh_tables_); cudaFree(d_mesh_counts_); cudaFree(d_mesh_offsets_); cudaFree(d_mesh_total_);
+    cudaFree(d_mesh_vert_); cudaFree(d_mesh_cols_); cudaFreeHost(h_mesh_total_);
+    if (ev_mesh0_) cudaEventDestroy(ev_mesh0_);
+    if (ev_mesh1_) cudaEventDestroy(ev_mesh1_);
     cudaStreamDestroy(stream_);
   }
 
@@ -453,6 +570,113 @@ class FusionImpl final : public FusionIface {
     return n;
   }
 
+  // ExtractMeshAsync, tsdf_volume.cu:759-779 (+ MeshExtractor::ExtractMesh, mesh_extractor.cu:267-282)
+  void extract_mesh_async(const float* lower, const float* upper, bool check_order) override {
+    if (check_order && next_ != kIntegrate)
+      throw Error("Please call this function after GetRenderResult (tsdf_volume.cu:760-763)");
+    if (mesh_pending_) throw Error("ExtractMeshAsync called twice without GetMeshSync (tsdf_volume.cu:769-772)");
+    TDM_CUDA(cudaSetDevice(device_));
+    const int nblk = d_.o.num_blocks;
+    if (!d_mesh_counts_) {
+      TDM_CUDA(cudaMalloc(&d_mesh_counts_, (size_t)nblk * sizeof(int)));
+      TDM_CUDA(cudaMalloc(&d_mesh_offsets_, (size_t)nblk * sizeof(int)));
+      TDM_CUDA(cudaMalloc(&d_mesh_total_, sizeof(int)));
+      TDM_CUDA(cudaMallocHost(&h_mesh_total_, sizeof(int)));
+      TDM_CUDA(cudaEventCreate(&ev_mesh0_));
+      TDM_CUDA(cudaEventCreate(&ev_mesh1_));
+    }
+    // per-axis tables -> one device buffer: [cells x | cells y | cells z | ranges x | ranges y | ranges z]
+    MeshAxisHost A[3];
+    size_t bytes = 0;
+    bool empty = false;
+    for (int a = 0; a < 3; ++a) {
+      A[a] = build_mesh_axis(lower[a], upper[a], d_.o.voxel_size);
+      empty = empty || A[a].cells.empty();
+      bytes += A[a].cells.size() * sizeof(MeshAxisCell) + A[a].ranges.size() * sizeof(int2) + 64;
+    }
+    mesh_empty_ = empty;
+    mesh_pending_ = true;
+    *h_mesh_total_ = 0;
+    if (empty) return;
+    if (bytes > mesh_tables_cap_) {
+      cudaFree(d_mesh_tables_);
+      d_mesh_tables_ = nullptr;
+      TDM_CUDA(cudaMalloc(&d_mesh_tables_, bytes));
+      mesh_tables_cap_ = bytes;
+    }
+    std::vector<char> host(bytes, 0);
+    size_t off = 0;
+    for (int a = 0; a < 3; ++a) {
+      const size_t nb = A[a].cells.size() * sizeof(MeshAxisCell);
+      std::memcpy(host.data() + off, A[a].cells.data(), nb);
+      mesh_axes_.cells[a] = reinterpret_cast<const MeshAxisCell*>(d_mesh_tables_ + off);
+      off += (nb + 15) / 16 * 16;
+    }
+    for (int a = 0; a < 3; ++a) {
+      const size_t nb = A[a].ranges.size() * sizeof(int2);
+      std::memcpy(host.data() + off, A[a].ranges.data(), nb);
+      mesh_axes_.brange[a] = reinterpret_cast<const int2*>(d_mesh_tables_ + off);
+      off += (nb + 15) / 16 * 16;
+      mesh_axes_.bmin[a] = A[a].bmin;
+      mesh_axes_.nb[a] = A[a].nb;
+    }
+    TDM_CUDA(cudaMemcpyAsync(d_mesh_tables_, host.data(), off, cudaMemcpyHostToDevice, stream_));  // pageable: staged before return
+    if (!d_mesh_vert_) {   // first estimate (72 B per triangle); GetMeshSync grows it when the count says so
+      const char* init = getenv("TDM_MESH_INIT_TRIS");
+      grow_mesh_buffers(init && atoll(init) > 0 ? atoll(init) : (1 << 20));
+    }
+    TDM_CUDA(cudaEventRecord(ev_mesh0_, stream_));
+    k_mesh<false><<<kMeshGrid, 256, 0, stream_>>>(d_, mesh_axes_, d_mesh_counts_, nullptr, 0, nullptr, nullptr);
+    TDM_CUDA(cudaGetLastError());
+    k_mesh_scan<<<1, 1024, 0, stream_>>>(d_mesh_counts_, d_mesh_offsets_, d_.counters, nblk, d_mesh_total_);
+    TDM_CUDA(cudaGetLastError());
+    launch_mesh_emit();
+    TDM_CUDA(cudaMemcpyAsync(h_mesh_total_, d_mesh_total_, sizeof(int), cudaMemcpyDeviceToHost, stream_));
+    TDM_CUDA(cudaEventRecord(ev_mesh1_, stream_));
+  }
+
+  // GetMeshSync, tsdf_volume.cu:781-839: vertices as xyz triples, colours as rgb triples, 3 per triangle
+  long long get_mesh(float* vert, float* cols, size_t max_vertices, bool check_order, bool query_only) override {
+    if (check_order && next_ != kIntegrate)
+      throw Error("Please call this function after GetRenderResult (tsdf_volume.cu:782-785)");
+    if (!mesh_pending_) throw Error("GetMeshSync without ExtractMeshAsync (tsdf_volume.cu:787-790)");
+    if (!query_only) mesh_pending_ = false;
+    if (mesh_empty_) { mesh_ms_ = 0.f; return 0; }
+    TDM_CUDA(cudaSetDevice(device_));
+    TDM_CUDA(cudaEventSynchronize(ev_mesh1_));
+    TDM_CUDA(cudaEventElapsedTime(&mesh_ms_, ev_mesh0_, ev_mesh1_));
+    const long long ntri = *h_mesh_total_;
+    if (query_only) return 3 * ntri;
+    if (ntri > mesh_cap_tris_) {   // first estimate too small: grow once and re-emit (counts / offsets are still valid)
+      grow_mesh_buffers(ntri + ntri / 4);
+      TDM_CUDA(cudaEventRecord(ev_mesh0_, stream_));
+      launch_mesh_emit();
+      TDM_CUDA(cudaEventRecord(ev_mesh1_, stream_));
+      TDM_CUDA(cudaEventSynchronize(ev_mesh1_));
+      float again = 0.f;
+      TDM_CUDA(cudaEventElapsedTime(&again, ev_mesh0_, ev_mesh1_));
+      mesh_ms_ += again;
+    }
+    const long long nv = 3 * ntri;
+    if ((unsigned long long)nv > (unsigned long long)max_vertices)
+      throw Error("Did not provide enough storage for mesh. (tsdf_volume.cu:796-799)");
+    if (nv > 0) {
+      TDM_CHECK(vert && cols, "null mesh output buffers");
+      TDM_CUDA(cudaMemcpy(vert, d_mesh_vert_, (size_t)nv * 3 * sizeof(float), cudaMemcpyDeviceToHost));
+      TDM_CUDA(cudaMemcpy(cols, d_mesh_cols_, (size_t)nv * 3 * sizeof(float), cudaMemcpyDeviceToHost));
+    }
+    return nv;
+  }
+  float last_mesh_ms() override { return mesh_ms_; }
+  float last_alloc_ms() override { return last_alloc_ms_; }
+  void set_option(const char* name, int value) override {
+    const std::string n(name);
+    if (n == "alloc_filter") alloc_filter_ = value != 0;
+    else if (n == "raycast_cache8") raycast_cache8_ = value != 0;
+    else throw Error("unknown fusion option " + n);
+  }
+  bool mesh_pending() override { return mesh_pending_; }
+
   const float* render_depth_device(int i, void** ready_event, int* device) override {
     TDM_CHECK(i >= 0 && i < n_rendered_, "render_depth_device: no such render");
     if (ready_event) *ready_event = (void*)ev_render_;
@@ -464,7 +688,8 @@ class FusionImpl final : public FusionIface {
     TDM_CUDA(cudaSetDevice(device_));
     cudaEvent_t e0, e1, e2;
     TDM_CUDA(cudaEventCreate(&e0)); TDM_CUDA(cudaEventCreate(&e1)); TDM_CUDA(cudaEventCreate(&e2));
-    float ti = 0, tr = 0;
+    TDM_CUDA(cudaEventCreate(&ev_split_));
+    float ti = 0, tr = 0, ta = 0;
     const int n = std::max(1, d_.o.num_render_streams);
     if (render_poses_.empty()) render_poses_.resize(1);
     for (int it = 0; it < iters; ++it) {
@@ -474,21 +699,27 @@ class FusionImpl final : public FusionIface {
       launch_render(n, false);
       TDM_CUDA(cudaEventRecord(e2, stream_));
       TDM_CUDA(cudaEventSynchronize(e2));
-      float a, b;
+      float a, b, c;
       TDM_CUDA(cudaEventElapsedTime(&a, e0, e1));
       TDM_CUDA(cudaEventElapsedTime(&b, e1, e2));
-      ti += a; tr += b;
+      TDM_CUDA(cudaEventElapsedTime(&c, e0, ev_split_));
+      ti += a; tr += b; ta += c;
     }
     cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
+    cudaEventDestroy(ev_split_);
+    ev_split_ = nullptr;
     *ms_int = ti; *ms_render = tr;
+    last_alloc_ms_ = ta / std::max(iters, 1);
   }
 
  private:
   void launch_integrate() {
     const int npx = d_.o.height * d_.o.width;
     TDM_CUDA(cudaMemsetAsync(d_.counters + 2, 0, 2 * sizeof(int), stream_));
-    k_allocate<<<cdiv(npx, 128), 128, 0, stream_>>>(d_, d_depth_in_, pose_);
+    if (alloc_filter_) k_allocate<true><<<cdiv(npx, 128), 128, 0, stream_>>>(d_, d_depth_in_, pose_);
+    else k_allocate<false><<<cdiv(npx, 128), 128, 0, stream_>>>(d_, d_depth_in_, pose_);
     TDM_CUDA(cudaGetLastError());
+    if (ev_split_) TDM_CUDA(cudaEventRecord(ev_split_, stream_));
     k_integrate<<<148 * 8, 256, 0, stream_>>>(d_, d_bgr_in_, d_depth_in_, pose_inv_);
     TDM_CUDA(cudaGetLastError());
   }
@@ -496,13 +727,27 @@ class FusionImpl final : public FusionIface {
     const size_t npx = (size_t)d_.o.height * d_.o.width;
     dim3 grid(cdiv(d_.o.width, 16), cdiv(d_.o.height, 16));
     for (int i = 0; i < n; ++i) {
-      k_raycast<<<grid, 256, 0, stream_>>>(d_, render_poses_[i], d_bgr_out_ + (size_t)i * npx * 3, d_depth_out_ + (size_t)i * npx);
+      if (raycast_cache8_) k_raycast<true><<<grid, 256, 0, stream_>>>(d_, render_poses_[i], d_bgr_out_ + (size_t)i * npx * 3, d_depth_out_ + (size_t)i * npx);
+      else k_raycast<false><<<grid, 256, 0, stream_>>>(d_, render_poses_[i], d_bgr_out_ + (size_t)i * npx * 3, d_depth_out_ + (size_t)i * npx);
       TDM_CUDA(cudaGetLastError());
     }
     if (copy_back) {
       TDM_CUDA(cudaMemcpyAsync(h_bgr_out_[free_half_], d_bgr_out_, npx * 3 * n, cudaMemcpyDeviceToHost, stream_));
       TDM_CUDA(cudaMemcpyAsync(h_depth_out_[free_half_], d_depth_out_, npx * 4 * n, cudaMemcpyDeviceToHost, stream_));
     }
+  }
+  static constexpr int kMeshGrid = 148 * 8;
+  void grow_mesh_buffers(long long tris) {
+    cudaFree(d_mesh_vert_); cudaFree(d_mesh_cols_);
+    d_mesh_vert_ = d_mesh_cols_ = nullptr;
+    mesh_cap_tris_ = 0;
+    TDM_CUDA(cudaMalloc(&d_mesh_vert_, (size_t)tris * 9 * sizeof(float)));
+    TDM_CUDA(cudaMalloc(&d_mesh_cols_, (size_t)tris * 9 * sizeof(float)));
+    mesh_cap_tris_ = (int)std::min<long long>(tris, INT_MAX);
+  }
+  void launch_mesh_emit() {
+    k_mesh<true><<<kMeshGrid, 256, 0, stream_>>>(d_, mesh_axes_, d_mesh_counts_, d_mesh_offsets_, mesh_cap_tris_, d_mesh_vert_, d_mesh_cols_);
+    TDM_CUDA(cudaGetLastError());
   }
   void fetch_counters() {
     TDM_CUDA(cudaSetDevice(device_));
@@ -529,6 +774,19 @@ class FusionImpl final : public FusionIface {
   int n_rendered_ = 0;
   bool have_scan_ = false;
   Next next_ = kIntegrate;
+  bool alloc_filter_ = true, raycast_cache8_ = true;   // tdm_fusion_set_option (A/B switches; results are identical)
+  cudaEvent_t ev_split_ = nullptr;
+  float last_alloc_ms_ = 0.f;
+  // mesh extraction state
+  char* d_mesh_tables_ = nullptr;
+  size_t mesh_tables_cap_ = 0;
+  MeshAxes mesh_axes_{};
+  int *d_mesh_counts_ = nullptr, *d_mesh_offsets_ = nullptr, *d_mesh_total_ = nullptr, *h_mesh_total_ = nullptr;
+  float *d_mesh_vert_ = nullptr, *d_mesh_cols_ = nullptr;
+  int mesh_cap_tris_ = 0;
+  cudaEvent_t ev_mesh0_ = nullptr, ev_mesh1_ = nullptr;
+  bool mesh_pending_ = false, mesh_empty_ = false;
+  float mesh_ms_ = 0.f;
 };
 
 FusionIface* make_fusion(const tdm_fusion_options& o, int device) { return new FusionImpl(o, device); }

@@ -19,6 +19,13 @@ class FusionIface {
   virtual void get_stats(tdm_fusion_stats* s) = 0;
   virtual long long dump_blocks(int* coords, void* voxels, size_t cap) = 0;
   virtual void run_resident(int iters, float* ms_int, float* ms_render) = 0;
+  // marching cubes (ExtractMeshAsync / GetMeshSync); check_order enforces the reference's call-order state machine
+  virtual void extract_mesh_async(const float* lower, const float* upper, bool check_order) = 0;
+  virtual long long get_mesh(float* vert, float* cols, size_t max_vertices, bool check_order, bool query_only) = 0;
+  virtual bool mesh_pending() = 0;
+  virtual float last_mesh_ms() = 0;
+  virtual float last_alloc_ms() = 0;   // k_allocate share of the last run_resident's integrate time (per iteration)
+  virtual void set_option(const char* name, int value) = 0;
   // device copy of the i-th depth map of the last RenderAsync + the event recorded behind it (tracker reference, n1)
   virtual const float* render_depth_device(int i, void** ready_event, int* device) = 0;
 };

@@ -85,6 +85,52 @@ class DrFusion:
             depths.append(d)
         return bgrs, depths
 
+    # ---- mesh (dr_fusion.h:56-68) ---------------------------------------------------------------
+    def ExtractMeshAsync(self, lower_corner, upper_corner):
+        fp = ctypes.POINTER(ctypes.c_float)
+        lo = np.ascontiguousarray(lower_corner, np.float32)
+        up = np.ascontiguousarray(upper_corner, np.float32)
+        check(lib().tdm_fusion_extract_mesh_async(self._h, lo.ctypes.data_as(fp), up.ctypes.data_as(fp)))
+
+    def GetMeshSync(self, max_vertices=60000000):
+        """-> (vert (n,3) f32, cols (n,3) f32 rgb in [0,1]); n = 3 * triangles (dr_mesh_num / dr_mesh_vert / dr_mesh_cols)."""
+        fp = ctypes.POINTER(ctypes.c_float)
+        # the reference copies into 60 M-vertex host arrays; size ours from a first query through the blocking entry
+        n = check(lib().tdm_fusion_extract_mesh(self._h, (ctypes.c_float * 3)(), (ctypes.c_float * 3)(), None, None, 0))
+        if n > max_vertices:
+            raise TandemError("Did not provide enough storage for mesh.")
+        vert = np.empty((n, 3), np.float32)
+        cols = np.empty((n, 3), np.float32)
+        n2 = check(lib().tdm_fusion_get_mesh(self._h, vert.ctypes.data_as(fp), cols.ctypes.data_as(fp), max(n, 1)))
+        assert n2 == n
+        self.dr_mesh_num, self.dr_mesh_vert, self.dr_mesh_cols = n, vert, cols
+        return vert, cols
+
+    def GetMesh(self, lower_corner, upper_corner):
+        """Blocking TsdfVolume::ExtractMesh (no call-order requirement) -> (vert, cols)."""
+        fp = ctypes.POINTER(ctypes.c_float)
+        lo = np.ascontiguousarray(lower_corner, np.float32)
+        up = np.ascontiguousarray(upper_corner, np.float32)
+        n = check(lib().tdm_fusion_extract_mesh(self._h, lo.ctypes.data_as(fp), up.ctypes.data_as(fp), None, None, 0))
+        vert = np.empty((n, 3), np.float32)
+        cols = np.empty((n, 3), np.float32)
+        check(lib().tdm_fusion_extract_mesh(self._h, lo.ctypes.data_as(fp), up.ctypes.data_as(fp), vert.ctypes.data_as(fp),
+                                            cols.ctypes.data_as(fp), max(n, 1)))
+        return vert, cols
+
+    def SaveMeshToFile(self, filename, lower_corner, upper_corner):
+        vert, cols = self.GetMesh(lower_corner, upper_corner)
+        with open(filename, "w") as f:
+            for v, c in zip(vert, cols):
+                f.write(f"v {v[0]:g} {v[1]:g} {v[2]:g} {c[0]:g} {c[1]:g} {c[2]:g}\n")
+            for i in range(0, len(vert) - 2, 3):
+                f.write(f"f {i + 1} {i + 2} {i + 3}\n")
+
+    def last_mesh_ms(self):
+        ms = ctypes.c_float()
+        check(lib().tdm_fusion_last_mesh_ms(self._h, ctypes.byref(ms)))
+        return ms.value
+
     def set_slab(self, z_block_lo, z_block_hi):
         """Multi-GPU extension: keep only voxel blocks with z_block_lo <= z < z_block_hi (see include/tandem_b200.h)."""
         check(lib().tdm_fusion_set_slab(self._h, int(z_block_lo), int(z_block_hi)))
@@ -106,6 +152,14 @@ class DrFusion:
         check(lib().tdm_fusion_dump_blocks(self._h, coords.ctypes.data_as(ctypes.POINTER(ctypes.c_int)),
                                            vox.ctypes.data if with_voxels else None, n))
         return coords, vox
+
+    def set_option(self, name, value):
+        check(lib().tdm_fusion_set_option(self._h, name.encode(), int(value)))
+
+    def last_alloc_ms(self):
+        ms = ctypes.c_float()
+        check(lib().tdm_fusion_last_alloc_ms(self._h, ctypes.byref(ms)))
+        return ms.value
 
     def run_resident(self, iters):
         a, b = ctypes.c_float(), ctypes.c_float()

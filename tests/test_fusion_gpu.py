@@ -194,3 +194,97 @@ def test_z_slab_partition_matches_single_volume():
     assert np.mean(hit_m != hit_f) < 5e-3
     both = hit_m & hit_f
     assert np.median(np.abs(dm[both] - fd[both])) < 1e-3 and np.quantile(np.abs(dm[both] - fd[both]), 0.99) < 0.02
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# marching cubes: DrFusion::ExtractMeshAsync / GetMeshSync / GetMesh vs the brute-force oracle
+def _sorted_tris(vert, cols):
+    """Triangle order is unspecified (the reference appends with atomicAdd): compare lexicographically sorted rows."""
+    t = np.concatenate([vert.reshape(-1, 9), cols.reshape(-1, 9)], axis=1)
+    return t[np.lexsort(t.T[::-1])]
+
+
+def _mesh_pair(n_frames=3, **kw):
+    poses, frames = _scene_frames(n_frames)
+    f, o = DrFusion(_opts(**kw)), TsdfOracle(_opts(**kw))
+    for (bgr, depth), pose in zip(frames, poses):
+        f.IntegrateScanAsync(bgr, depth, pose)
+        o.integrate(bgr, depth, pose)
+        f.RenderAsync([pose])
+        f.GetRenderResult()
+    return f, o
+
+
+@pytest.mark.parametrize("lower,upper", [
+    ((-1.28, -1.28, -1.28), (1.28, 1.28, 1.28)),          # voxel-aligned box, negative and positive coordinates
+    ((-1.2345, -0.777, -1.1111), (1.3, 0.9137, 1.2501)),  # arbitrary corners: per-axis rounding is whatever fp32 says
+    ((0.105, -0.4, 0.2), (0.9, 0.4, 1.0)),                # a sub-box that cuts through blocks
+])
+def test_mesh_matches_oracle_bit_exact(lower, upper):
+    f, o = _mesh_pair()
+    lo, up = np.float32(lower), np.float32(upper)
+    vo, co = o.extract_mesh(lo, up)
+    f.ExtractMeshAsync(lo, up)
+    vg, cg = f.GetMeshSync()
+    print(f"mesh {lower}..{upper}: {len(vg) // 3} triangles (oracle {len(vo) // 3}), device {f.last_mesh_ms():.3f} ms")
+    assert len(vo) > 3000, "scene produced no surface - test is vacuous"
+    assert len(vg) == len(vo), f"vertex count {len(vg)} vs oracle {len(vo)}"
+    assert np.array_equal(_sorted_tris(vg, cg), _sorted_tris(vo, co)), "triangle sets differ"
+    # blocking variant (TsdfVolume::ExtractMesh, no call-order requirement) gives the same set
+    v2, c2 = f.GetMesh(lo, up)
+    assert np.array_equal(_sorted_tris(v2, c2), _sorted_tris(vo, co))
+
+
+def test_mesh_call_order_capacity_and_regrow(monkeypatch):
+    monkeypatch.setenv("TDM_MESH_INIT_TRIS", "64")      # force the grow-and-re-emit path of GetMeshSync
+    f, o = _mesh_pair(2)
+    lo, up = np.float32([-1.28] * 3), np.float32([1.28] * 3)
+    with pytest.raises(Exception):
+        f.GetMeshSync()                                  # GetMeshSync without ExtractMeshAsync (tsdf_volume.cu:787-790)
+    f.ExtractMeshAsync(lo, up)
+    with pytest.raises(Exception):
+        f.ExtractMeshAsync(lo, up)                       # twice in a row (tsdf_volume.cu:769-772)
+    vg, cg = f.GetMeshSync()
+    vo, co = o.extract_mesh(lo, up)
+    assert len(vg) == len(vo) > 64 * 3
+    assert np.array_equal(_sorted_tris(vg, cg), _sorted_tris(vo, co))
+    # only legal where IntegrateScanAsync is legal (tsdf_volume.cu:760-763)
+    poses, frames = _scene_frames(1)
+    f.IntegrateScanAsync(frames[0][0], frames[0][1], poses[0])
+    with pytest.raises(Exception):
+        f.ExtractMeshAsync(lo, up)
+    f.RenderAsync([poses[0]]); f.GetRenderResult()
+    f.ExtractMeshAsync(lo, up)
+    import ctypes
+    from tandem_b200._lib import lib
+    fp = ctypes.POINTER(ctypes.c_float)
+    small = np.empty((30, 3), np.float32)
+    rc = lib().tdm_fusion_get_mesh(f._h, small.ctypes.data_as(fp), small.ctypes.data_as(fp), 30)
+    assert rc < 0 and b"enough storage" in lib().tdm_last_error()   # tsdf_volume.cu:796-799
+    # empty boxes
+    assert len(f.GetMesh(np.float32([5, 5, 5]), np.float32([5.5, 5.5, 5.5]))[0]) == 0
+    assert len(f.GetMesh(lo, np.float32([lo[0], 1, 1]))[0]) == 0
+
+
+def test_mesh_full_size_properties():
+    """640x480 scan into the initDr-sized map, the 10 m box of tandem_backend.cpp:80-81: every vertex lies within a voxel and
+    a half of the analytic surface it was fused from; the same call twice gives the same triangle set."""
+    scene = RoomScene()
+    f = DrFusion(DrFusionOptions())
+    for eye in ((0.3, 0.0, -0.2), (0.35, 0.02, -0.15)):
+        pose = look_at_pose(eye, (2.5, 0.2, 0.5))
+        bgr, depth = scene.render(pose, 480, 640, 320.0, 320.0, 319.5, 239.5)
+        f.IntegrateScanAsync(bgr, depth, pose)
+        f.RenderAsync([pose]); f.GetRenderResult()
+    lo, up = np.float32([-5, -5, -5]), np.float32([5, 5, 5])
+    f.ExtractMeshAsync(lo, up)
+    v1, c1 = f.GetMeshSync()
+    ms = f.last_mesh_ms()
+    v2, c2 = f.GetMesh(lo, up)
+    print(f"full-size mesh: {len(v1) // 3} triangles from {f.stats()['allocated_blocks']} blocks in {ms:.3f} ms (device)")
+    assert len(v1) > 100000 and len(v1) % 3 == 0
+    assert np.array_equal(_sorted_tris(v1, c1), _sorted_tris(v2, c2))
+    d_walls = np.min(np.abs(np.abs(v1) - scene.half), axis=1)
+    d_sph = np.min([np.abs(np.linalg.norm(v1 - np.float32(s[:3]), axis=1) - s[3]) for s in scene.spheres], axis=0)
+    assert np.quantile(np.minimum(d_walls, d_sph), 0.995) < 0.015
+    assert (c1 >= 0).all() and (c1 <= 1).all()

@@ -159,3 +159,45 @@ def test_lm_driver_converges_with_oracle_tracker():
     E = se3_exp([0.1, -0.2, 0.3, 0.02, -0.01, 0.03])
     assert np.allclose(E[:3, :3] @ E[:3, :3].T, np.eye(3), atol=1e-12) and abs(np.linalg.det(E[:3, :3]) - 1) < 1e-12
     assert np.allclose(se3_exp(np.zeros(6)), np.eye(4))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# marching cubes oracle: properties on the CPU (the reference has no mesh test or golden)
+def _mesh_scene():
+    from oracle.cpu import TsdfOracle
+    from tandem_b200 import DrFusionOptions
+    from tandem_b200.synthetic import RoomScene, look_at_pose
+    H, W = 60, 80
+    intr = dict(fx=40.0, fy=40.0, cx=39.5, cy=29.5)
+    scene = RoomScene(half=0.6, spheres=((0.0, 0.0, 0.35, 0.15),))
+    o = TsdfOracle(DrFusionOptions(height=H, width=W, num_buckets=50021, bucket_size=10, num_blocks=30000, **intr))
+    for eye in ((0.0, 0.0, -0.3), (0.05, 0.02, -0.28), (-0.04, -0.03, -0.31)):
+        pose = look_at_pose(eye, (0.0, 0.0, 0.6))
+        bgr, depth = scene.render(pose, H, W, **intr)
+        o.integrate(bgr, depth, pose)
+    return o
+
+
+def test_mesh_oracle_properties():
+    o = _mesh_scene()
+    lo, up = np.float32([-0.64, -0.64, -0.64]), np.float32([0.64, 0.64, 0.64])
+    vert, cols = o.extract_mesh(lo, up)
+    assert len(vert) % 3 == 0 and len(vert) > 3000
+    assert np.isfinite(vert).all() and (cols >= 0).all() and (cols <= 1).all()
+    assert (vert >= lo - 0.011).all() and (vert <= up + 0.011).all()
+    # every vertex lies on the true surface (sphere r=0.15 at (0,0,0.35) or the z=+0.6 wall / side walls) within ~1.5 voxels
+    d_sphere = np.abs(np.linalg.norm(vert - np.float32([0, 0, 0.35]), axis=1) - 0.15)
+    d_walls = np.min(np.abs(np.abs(vert) - 0.6), axis=1)
+    assert np.quantile(np.minimum(d_sphere, d_walls), 0.99) < 0.015
+    # triangles are small (one cell) and non-degenerate on the whole
+    tri = vert.reshape(-1, 3, 3)
+    assert np.max(np.linalg.norm(tri[:, 0] - tri[:, 1], axis=1)) < 0.02
+    # cell locality: the box split at a cell boundary yields exactly the two halves (same cells, same arithmetic)
+    mid = np.float32(lo[0] + np.float32(64) * np.float32(0.01))
+    va, _ = o.extract_mesh(lo, np.float32([mid, up[1], up[2]]))
+    assert len(va) > 0
+    whole_left = vert.reshape(-1, 9)[(vert.reshape(-1, 3, 3)[:, :, 0].max(1) <= mid + 0.0051)]
+    assert abs(len(va) // 3 - len(whole_left)) <= 0.02 * len(whole_left) + 8
+    # an empty / inverted-size box gives nothing; zero-extent axis gives nothing
+    assert len(o.extract_mesh(lo, np.float32([lo[0], up[1], up[2]]))[0]) == 0
+    assert len(o.extract_mesh(np.float32([3, 3, 3]), np.float32([3.5, 3.5, 3.5]))[0]) == 0

@@ -36,13 +36,33 @@ for (bgr, depth), pose in zip(frames, poses):
 f.Synchronize()
 e2e_ms = (time.perf_counter() - t0) * 1e3 / n_frames
 st = f.stats()
-mi, mr = f.run_resident(20)
 vis = st["visible_blocks"]
 alg = vis * 512 * 16 + 7 * H * W
+res = {}
+for name, opts in (("default", {}), ("no_alloc_filter", {"alloc_filter": 0}), ("raycast_cache1", {"raycast_cache8": 0})):
+    for k in ("alloc_filter", "raycast_cache8"):
+        f.set_option(k, opts.get(k, 1))
+    f.run_resident(3)
+    mi, mr = f.run_resident(20)
+    res[name] = {"allocate_ms": f.last_alloc_ms(), "allocate+integrate_ms": mi / 20, "raycast_ms": mr / 20}
+for k in ("alloc_filter", "raycast_cache8"):
+    f.set_option(k, 1)
+mi = res["default"]["allocate+integrate_ms"] * 20
+mr = res["default"]["raycast_ms"] * 20
 print(json.dumps({"what": "tsdf ours", "frames": n_frames, "allocated_blocks": st["allocated_blocks"], "visible_blocks_last": vis,
                   "e2e_ms_per_frame(integrate+render+copies)": e2e_ms, "resident_allocate+integrate_ms": mi / 20,
+                  "resident_allocate_ms": res["default"]["allocate_ms"],
                   "resident_raycast_ms": mr / 20, "integrate_algorithmic_GB": alg / 1e9,
-                  "integrate_GBps": alg / (mi / 20 * 1e-3) / 1e9}))
+                  "integrate_GBps": alg / (mi / 20 * 1e-3) / 1e9, "ab": res}))
+# marching cubes over the 10 m box of tandem_backend.cpp:80-81 (shifted with the scene)
+lo = np.float32([0.12, 0.12, 0.12]); up = np.float32([10.12, 10.12, 10.12])
+f.ExtractMeshAsync(lo, up)
+t0 = time.perf_counter()
+mv, mc = f.GetMeshSync()
+wall = (time.perf_counter() - t0) * 1e3
+f.ExtractMeshAsync(lo, up); f.GetMeshSync()
+print(json.dumps({"what": "mesh ours (block-sparse marching cubes, 1000^3-cell box)", "triangles": len(mv) // 3,
+                  "blocks": st["allocated_blocks"], "device_ms(classify+scan+emit)": f.last_mesh_ms(), "GetMeshSync_wall_ms(first call, incl. D2H)": wall}))
 
 ref_lib = os.path.join(ROOT, "oracle", "_ref", "libdr_fusion_ref.so")
 if os.path.exists(ref_lib):
@@ -62,8 +82,13 @@ if os.path.exists(ref_lib):
         t2 = time.perf_counter()
         ti += t1 - t0
         tr += t2 - t1
+    l.ref_fusion_get_mesh.restype = ctypes.c_longlong
+    t0 = time.perf_counter()
+    nm = l.ref_fusion_get_mesh(r, lo.ctypes.data_as(_fp), up.ctypes.data_as(_fp), None, None, ctypes.c_longlong(0))
+    tm = (time.perf_counter() - t0) * 1e3
     print(json.dumps({"what": "tsdf reference dr_fusion (unmodified, sm_100a)", "frames": nref,
-                      "integrate_ms_per_frame(wall)": ti * 1e3 / nref, "render_ms_per_frame(wall)": tr * 1e3 / nref}))
+                      "integrate_ms_per_frame(wall)": ti * 1e3 / nref, "render_ms_per_frame(wall)": tr * 1e3 / nref,
+                      "GetMesh_wall_ms(10 m box)": tm, "mesh_triangles": nm // 3}))
     l.ref_fusion_destroy(r)
 
 c = tracker_case()
