@@ -184,7 +184,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default="mixed16", choices=["mixed16", "fp32", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--inflight", type=int, default=4, choices=[1, 2, 3, 4, 5, 6, 7, 8],
+    ap.add_argument("--inflight", type=int, default=8, choices=[1, 2, 3, 4, 5, 6, 7, 8],
                     help="independent windows in flight per GPU (n DrMvsnet handles, one stream each, used round-robin) in both legs")
     ap.add_argument("--tc", type=int, default=-1, help="1/0: force the tcgen05 conv path on/off (default: engine default)")
     a = ap.parse_args()

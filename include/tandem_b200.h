@@ -123,6 +123,12 @@ int tdm_fusion_synchronize(tdm_fusion* h);
  * reads never cross ranks). Every rank integrates the same (broadcast) scans; renders are combined by a per-pixel
  * nearest-hit reduction (tandem_b200/parallel.py: reduce_nearest_hit). Call before the first scan. */
 int tdm_fusion_set_slab(tdm_fusion* h, int z_block_lo, int z_block_hi);
+/* The one exchange step of the slab-partitioned ray-cast, on the device: tdm_fusion_render_keys_device packs render
+ * `render_index` of the last RenderAsync into height*width int64 keys (depth bits << 24 | b | g<<8 | r<<16; miss = +inf) in a
+ * DEVICE buffer owned by the handle (stream synchronised on return) - the caller all-reduces it with MIN over the ranks
+ * (NCCL, in place) - tdm_fusion_unpack_keys turns reduced keys back into a depth map and a bgr image in HOST buffers. */
+int tdm_fusion_render_keys_device(tdm_fusion* h, int render_index, long long** keys_dev);
+int tdm_fusion_unpack_keys(tdm_fusion* h, const long long* keys_dev, float* depth_out, unsigned char* bgr_out);
 /* Mesh (dr_fusion.h:56-68; TsdfVolume::ExtractMeshAsync / GetMeshSync / ExtractMesh, tsdf_volume.cu:739-839; kernel
  * marching_cubes/mesh_extractor.cu:244-265): marching cubes over the cells of the box [lower, upper) at voxel spacing.
  * Output layout of GetMeshSync: vertices as xyz float triples, colours as rgb float triples in [0,1], 3 consecutive
@@ -130,7 +136,7 @@ int tdm_fusion_set_slab(tdm_fusion* h, int z_block_lo, int z_block_hi);
  *   tdm_fusion_extract_mesh_async = ExtractMeshAsync: launches the extraction on the fusion stream and returns; only legal
  *     where IntegrateScanAsync is legal (tsdf_volume.cu:760-763) and not twice in a row (:769-772);
  *   tdm_fusion_get_mesh = GetMeshSync: waits, copies 3*triangles vertices out, returns the vertex count (error if it exceeds
- *     max_vertices, :796-799);
+ *     max_vertices, :796-799); with vert == cols == NULL it waits and returns the count only, the mesh stays pending;
  *   tdm_fusion_extract_mesh = TsdfVolume::ExtractMesh (blocking, no call-order check; DrFusion::GetMesh / SaveMeshToFile);
  *     with vert == cols == NULL it only returns the vertex count and keeps the mesh on the device, so that the next call
  *     (with buffers of that size) copies it out without extracting again. */
@@ -156,7 +162,8 @@ long long tdm_fusion_dump_blocks(tdm_fusion* h, int* coords, void* voxels, size_
 int tdm_fusion_run_resident(tdm_fusion* h, int iters, float* ms_integrate, float* ms_render);
 int tdm_fusion_last_alloc_ms(tdm_fusion* h, float* ms);
 /* A/B switches for measurements (results are bit-identical either way): "alloc_filter" (CTA-level shared-memory filter in
- * front of the hash table during allocation, default 1), "raycast_cache8" (8-entry per-ray block cache, default 1). */
+ * front of the hash table during allocation), "raycast_cache8" (8-entry per-ray block cache); both default to 0 - measured
+ * on B200 they do not pay (the table probes are L2 hits behind other latency). */
 int tdm_fusion_set_option(tdm_fusion* h, const char* name, int value);
 
 /* ------------------------------------------------------------------------------------------------

@@ -86,6 +86,8 @@ def _declare(l):
         "tdm_fusion_extract_mesh_async": (i, [vp, fp, fp]),
         "tdm_fusion_get_mesh": (c.c_longlong, [vp, fp, fp, c.c_size_t]),
         "tdm_fusion_last_mesh_ms": (i, [vp, fp]),
+        "tdm_fusion_render_keys_device": (i, [vp, i, P(vp)]),
+        "tdm_fusion_unpack_keys": (i, [vp, vp, fp, vp]),
         "tdm_fusion_set_option": (i, [vp, cp, i]),
         "tdm_fusion_last_alloc_ms": (i, [vp, fp]),
         "tdm_fusion_get_stats": (i, [vp, P(FusionStats)]),

@@ -75,13 +75,27 @@ int tdm_fusion_extract_mesh_async(tdm_fusion* h, const float lower[3], const flo
 long long tdm_fusion_get_mesh(tdm_fusion* h, float* vert, float* cols, size_t max_vertices) {
   TDM_API_BEGIN
   TDM_CHECK(h, "null handle");
-  return h->impl->get_mesh(vert, cols, max_vertices, true, false);
+  return h->impl->get_mesh(vert, cols, max_vertices, true, /*query_only=*/vert == nullptr && cols == nullptr);
   TDM_API_END
 }
 int tdm_fusion_last_mesh_ms(tdm_fusion* h, float* ms) {
   TDM_API_BEGIN
   TDM_CHECK(h && ms, "null argument");
   *ms = h->impl->last_mesh_ms();
+  return TDM_OK;
+  TDM_API_END
+}
+int tdm_fusion_render_keys_device(tdm_fusion* h, int render_index, long long** keys_dev) {
+  TDM_API_BEGIN
+  TDM_CHECK(h && keys_dev, "null argument");
+  *keys_dev = h->impl->render_keys_device(render_index);
+  return TDM_OK;
+  TDM_API_END
+}
+int tdm_fusion_unpack_keys(tdm_fusion* h, const long long* keys_dev, float* depth_out, unsigned char* bgr_out) {
+  TDM_API_BEGIN
+  TDM_CHECK(h && keys_dev && depth_out && bgr_out, "null argument");
+  h->impl->unpack_keys(keys_dev, depth_out, bgr_out);
   return TDM_OK;
   TDM_API_END
 }

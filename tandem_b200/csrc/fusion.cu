@@ -362,6 +362,27 @@ k_raycast(FusionDev d, Mat4 T, unsigned char* __restrict__ bgr_out, float* __res
   }
 }
 
+// Slab-partitioned ray-cast: per-pixel key = depth bits << 24 | b | g << 8 | r << 16, a miss = +inf, so that the
+// per-pixel MIN over ranks (one NCCL all-reduce on these device buffers) keeps the nearest hit and its colour.
+__global__ void k_pack_hits(const float* __restrict__ depth, const unsigned char* __restrict__ bgr, long long* __restrict__ keys, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float d = depth[i];
+  const long long bits = d > 0.f ? (long long)__float_as_uint(d) : 0x7F800000ll;
+  keys[i] = (bits << 24) | (long long)bgr[3 * i] | ((long long)bgr[3 * i + 1] << 8) | ((long long)bgr[3 * i + 2] << 16);
+}
+__global__ void k_unpack_hits(const long long* __restrict__ keys, float* __restrict__ depth, unsigned char* __restrict__ bgr, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const long long k = keys[i];
+  const unsigned bits = (unsigned)(k >> 24);
+  const bool miss = bits == 0x7F800000u;
+  depth[i] = miss ? 0.f : __uint_as_float(bits);
+  bgr[3 * i] = miss ? 0 : (unsigned char)(k & 0xFF);
+  bgr[3 * i + 1] = miss ? 0 : (unsigned char)((k >> 8) & 0xFF);
+  bgr[3 * i + 2] = miss ? 0 : (unsigned char)((k >> 16) & 0xFF);
+}
+
 __global__ void k_fill_keys(unsigned long long* keys, int* ptrs, long long n) {
   long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (i < n) { keys[i] = kEmptyKey; ptrs[i] = -1; }
@@ -477,6 +498,7 @@ class FusionImpl final : public FusionIface {
     for (int half = 0; half < 2; ++half) { cudaFreeHost(h_bgr_out_[half]); cudaFreeHost(h_depth_out_[half]); }
     cudaFree(d_bgr_out_); cudaFree(d_depth_out_); cudaFreeHost(h_counters_);
     cudaEventDestroy(ev_int_); cudaEventDestroy(ev_render_);
+    cudaFree(d_hit_keys_); cudaFree(d_unpack_depth_); cudaFree(d_unpack_bgr_);
     cudaFree(d_mesh_tables_); cudaFree(d_mesh_counts_); cudaFree(d_mesh_offsets_); cudaFree(d_mesh_total_);
     cudaFree(d_mesh_vert_); cudaFree(d_mesh_cols_); cudaFreeHost(h_mesh_total_);
     if (ev_mesh0_) cudaEventDestroy(ev_mesh0_);
@@ -683,6 +705,30 @@ class FusionImpl final : public FusionIface {
     if (device) *device = device_;
     return d_depth_out_ + (size_t)i * d_.o.height * d_.o.width;
   }
+  // slab exchange step: device buffer of packed nearest-hit keys of render i (valid until the next call), stream synchronised
+  long long* render_keys_device(int i) override {
+    TDM_CHECK(i >= 0 && i < n_rendered_, "render_keys_device: no such render");
+    TDM_CUDA(cudaSetDevice(device_));
+    const int npx = d_.o.height * d_.o.width;
+    if (!d_hit_keys_) TDM_CUDA(cudaMalloc(&d_hit_keys_, (size_t)npx * sizeof(long long)));
+    k_pack_hits<<<cdiv(npx, 256), 256, 0, stream_>>>(d_depth_out_ + (size_t)i * npx, d_bgr_out_ + (size_t)i * npx * 3, d_hit_keys_, npx);
+    TDM_CUDA(cudaGetLastError());
+    TDM_CUDA(cudaStreamSynchronize(stream_));
+    return d_hit_keys_;
+  }
+  void unpack_keys(const long long* keys_dev, float* depth_out, unsigned char* bgr_out) override {
+    TDM_CUDA(cudaSetDevice(device_));
+    const int npx = d_.o.height * d_.o.width;
+    if (!d_unpack_depth_) {
+      TDM_CUDA(cudaMalloc(&d_unpack_depth_, (size_t)npx * 4));
+      TDM_CUDA(cudaMalloc(&d_unpack_bgr_, (size_t)npx * 3));
+    }
+    k_unpack_hits<<<cdiv(npx, 256), 256, 0, stream_>>>(keys_dev, d_unpack_depth_, d_unpack_bgr_, npx);
+    TDM_CUDA(cudaGetLastError());
+    TDM_CUDA(cudaMemcpyAsync(depth_out, d_unpack_depth_, (size_t)npx * 4, cudaMemcpyDeviceToHost, stream_));
+    TDM_CUDA(cudaMemcpyAsync(bgr_out, d_unpack_bgr_, (size_t)npx * 3, cudaMemcpyDeviceToHost, stream_));
+    TDM_CUDA(cudaStreamSynchronize(stream_));
+  }
   void run_resident(int iters, float* ms_int, float* ms_render) override {
     TDM_CHECK(have_scan_, "run_resident: no scan submitted yet");
     TDM_CUDA(cudaSetDevice(device_));
@@ -774,9 +820,12 @@ class FusionImpl final : public FusionIface {
   int n_rendered_ = 0;
   bool have_scan_ = false;
   Next next_ = kIntegrate;
-  bool alloc_filter_ = true, raycast_cache8_ = true;   // tdm_fusion_set_option (A/B switches; results are identical)
+  bool alloc_filter_ = false, raycast_cache8_ = false;   // tdm_fusion_set_option: measured on B200 (profiles/r01_fusion_tracker.txt), neither pays: 0.071 vs 0.065 ms, 0.87 vs 0.82 ms
   cudaEvent_t ev_split_ = nullptr;
   float last_alloc_ms_ = 0.f;
+  long long* d_hit_keys_ = nullptr;
+  float* d_unpack_depth_ = nullptr;
+  unsigned char* d_unpack_bgr_ = nullptr;
   // mesh extraction state
   char* d_mesh_tables_ = nullptr;
   size_t mesh_tables_cap_ = 0;

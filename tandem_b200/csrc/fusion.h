@@ -23,6 +23,8 @@ class FusionIface {
   virtual void extract_mesh_async(const float* lower, const float* upper, bool check_order) = 0;
   virtual long long get_mesh(float* vert, float* cols, size_t max_vertices, bool check_order, bool query_only) = 0;
   virtual bool mesh_pending() = 0;
+  virtual long long* render_keys_device(int i) = 0;
+  virtual void unpack_keys(const long long* keys_dev, float* depth_out, unsigned char* bgr_out) = 0;
   virtual float last_mesh_ms() = 0;
   virtual float last_alloc_ms() = 0;   // k_allocate share of the last run_resident's integrate time (per iteration)
   virtual void set_option(const char* name, int value) = 0;

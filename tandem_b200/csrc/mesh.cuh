@@ -109,12 +109,21 @@ k_mesh(FusionDev d, MeshAxes ax, int* __restrict__ counts, const int* __restrict
     __syncthreads();   // the previous block's tile is no longer read
     if (tid < 8) sptr[tid] = tid == 0 ? e.w : find_block(d, e.x + (tid >> 2), e.y + ((tid >> 1) & 1), e.z + (tid & 1));
     __syncthreads();
+    int neg = 0;
     for (int t = tid; t < kMeshTileVox; t += 256) {
       const int tx = t / (kMeshTile * kMeshTile), ty = (t / kMeshTile) % kMeshTile, tz = t % kMeshTile;
       const int ptr = sptr[(tx >> 3) * 4 + (ty >> 3) * 2 + (tz >> 3)];
-      tile[t] = ptr < 0 ? make_uint2(0u, 0u) : __ldg(d.voxels + (size_t)ptr * 512 + (tx & 7) * 64 + (ty & 7) * 8 + (tz & 7));
+      const uint2 v = ptr < 0 ? make_uint2(0u, 0u) : __ldg(d.voxels + (size_t)ptr * 512 + (tx & 7) * 64 + (ty & 7) * 8 + (tz & 7));
+      tile[t] = v;
+      neg |= (v.y >> 24) != 0 && __uint_as_float(v.x) < 0.0f;
     }
-    __syncthreads();
+    // Every corner distance is a chain of fma(W, sdf, acc) with W >= 0: if no observed voxel of the neighbourhood is negative,
+    // every distance is >= +0, the cube index is 0 and the block emits nothing - skip it (most blocks of the viewing frustum
+    // are free space with sdf = +truncation).  The all-negative case is NOT skipped (a -0 sum would read as "not below").
+    if (!__syncthreads_or(neg)) {
+      if (!EMIT && tid == 0) counts[b] = 0;
+      continue;
+    }
     const int t0x = e.x * 8, t0y = e.y * 8, t0z = e.z * 8;
     int running = EMIT ? offsets[b] : 0;   // EMIT: first triangle slot of this round; COUNT: per-thread sum
     for (int base = 0; base < ncell; base += 256) {

@@ -95,8 +95,8 @@ class DrFusion:
     def GetMeshSync(self, max_vertices=60000000):
         """-> (vert (n,3) f32, cols (n,3) f32 rgb in [0,1]); n = 3 * triangles (dr_mesh_num / dr_mesh_vert / dr_mesh_cols)."""
         fp = ctypes.POINTER(ctypes.c_float)
-        # the reference copies into 60 M-vertex host arrays; size ours from a first query through the blocking entry
-        n = check(lib().tdm_fusion_extract_mesh(self._h, (ctypes.c_float * 3)(), (ctypes.c_float * 3)(), None, None, 0))
+        # the reference copies into 60 M-vertex host arrays; size ours from a first count-only query
+        n = check(lib().tdm_fusion_get_mesh(self._h, None, None, 0))
         if n > max_vertices:
             raise TandemError("Did not provide enough storage for mesh.")
         vert = np.empty((n, 3), np.float32)
@@ -134,6 +134,20 @@ class DrFusion:
     def set_slab(self, z_block_lo, z_block_hi):
         """Multi-GPU extension: keep only voxel blocks with z_block_lo <= z < z_block_hi (see include/tandem_b200.h)."""
         check(lib().tdm_fusion_set_slab(self._h, int(z_block_lo), int(z_block_hi)))
+
+    def render_keys_device(self, render_index=0):
+        """Device pointer (int) of the packed nearest-hit keys of a render + element count (see include/tandem_b200.h)."""
+        ptr = ctypes.c_void_p()
+        check(lib().tdm_fusion_render_keys_device(self._h, int(render_index), ctypes.byref(ptr)))
+        return ptr.value, self.options.height * self.options.width
+
+    def unpack_keys(self, keys_dev_ptr):
+        o = self.options
+        depth = np.empty((o.height, o.width), np.float32)
+        bgr = np.empty((o.height, o.width, 3), np.uint8)
+        check(lib().tdm_fusion_unpack_keys(self._h, ctypes.c_void_p(keys_dev_ptr), depth.ctypes.data_as(ctypes.POINTER(ctypes.c_float)),
+                                           bgr.ctypes.data))
+        return depth, bgr
 
     def Synchronize(self):
         check(lib().tdm_fusion_synchronize(self._h))

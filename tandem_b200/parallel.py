@@ -81,3 +81,23 @@ def reduce_nearest_hit(dist, depth, bgr, device="cpu"):
     t = torch.from_numpy(keys).to(device)
     dist.all_reduce(t, op=dist.ReduceOp.MIN)
     return unpack_hits(t.cpu().numpy())
+
+
+class _DeviceInt64:
+    """__cuda_array_interface__ view of a device buffer owned by the C library (no copy)."""
+
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<i8", "data": (int(ptr), False), "version": 2}
+
+
+def reduce_nearest_hit_device(dist, fusion, render_index=0, device="cuda:0"):
+    """Same exchange as reduce_nearest_hit but without the host round trip: the keys are packed by a kernel into a device
+    buffer of the DrFusion handle, all-reduced in place with MIN over the ranks (NCCL over NVLink) and unpacked by a kernel.
+    Returns (depth, bgr) of the combined render on the host."""
+    ptr, n = fusion.render_keys_device(render_index)
+    if dist is not None:
+        import torch
+        t = torch.as_tensor(_DeviceInt64(ptr, n), device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        torch.cuda.synchronize(device)
+    return fusion.unpack_keys(ptr)

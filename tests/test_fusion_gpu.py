@@ -218,7 +218,8 @@ def _mesh_pair(n_frames=3, **kw):
 @pytest.mark.parametrize("lower,upper", [
     ((-1.28, -1.28, -1.28), (1.28, 1.28, 1.28)),          # voxel-aligned box, negative and positive coordinates
     ((-1.2345, -0.777, -1.1111), (1.3, 0.9137, 1.2501)),  # arbitrary corners: per-axis rounding is whatever fp32 says
-    ((0.105, -0.4, 0.2), (0.9, 0.4, 1.0)),                # a sub-box that cuts through blocks
+    ((0.105, -0.4, -0.3), (1.3, 0.4, 0.7)),               # sub-boxes that cut through blocks
+    ((-0.9, -0.6, 0.3), (0.3, 0.5, 1.25)),
 ])
 def test_mesh_matches_oracle_bit_exact(lower, upper):
     f, o = _mesh_pair()
@@ -288,3 +289,21 @@ def test_mesh_full_size_properties():
     d_sph = np.min([np.abs(np.linalg.norm(v1 - np.float32(s[:3]), axis=1) - s[3]) for s in scene.spheres], axis=0)
     assert np.quantile(np.minimum(d_walls, d_sph), 0.995) < 0.015
     assert (c1 >= 0).all() and (c1 <= 1).all()
+
+
+def test_nearest_hit_keys_roundtrip_on_device():
+    """The slab exchange buffers: packing a render into int64 keys on the device and unpacking them again is
+    the identity, and the device keys equal the host-side packing used by the gloo test (tandem_b200.parallel.pack_hits)."""
+    import torch
+    from tandem_b200.parallel import _DeviceInt64, pack_hits, reduce_nearest_hit_device
+    poses, frames = _scene_frames(2)
+    f = DrFusion(_opts())
+    for (bgr, depth), pose in zip(frames, poses):
+        f.IntegrateScanAsync(bgr, depth, pose)
+        f.RenderAsync([poses[0]])
+        (rb,), (rd,) = f.GetRenderResult()
+    ptr, n = f.render_keys_device(0)
+    keys = torch.as_tensor(_DeviceInt64(ptr, n), device="cuda:0").cpu().numpy().reshape(H, W)
+    assert np.array_equal(keys, pack_hits(rd, rb))
+    dm, bm = reduce_nearest_hit_device(None, f, 0)
+    assert np.array_equal(dm, rd) and np.array_equal(bm[rd > 0], rb[rd > 0]) and (rd == 0).any() and (rd > 0).any()
