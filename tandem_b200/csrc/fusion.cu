@@ -257,6 +257,73 @@ k_integrate(FusionDev d, const unsigned char* __restrict__ bgr, const float* __r
   }
 }
 
+// K6, two-step form: only ~10 % of the allocated blocks are in view of a scan, and the map grows with every keyframe, so the
+// visibility test runs once per block in its own kernel (thread per block, warp-aggregated append to a compact list) and the
+// voxel update visits the visible blocks only.  Same expressions as k_integrate -> bit-identical voxels.
+__global__ void __launch_bounds__(256) k_visible(FusionDev d, Mat4 Ti, int* __restrict__ vis_list) {
+  const tdm_fusion_options& o = d.o;
+  const int nblocks = min(d.counters[0], o.num_blocks);
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  bool vis = false;
+  if (b < nblocks) {
+    const int4 e = d.list[b];
+    const float vs = o.voxel_size;
+    const float3 pos = make_float3(mul_(mul_((float)e.x, vs), 8.0f), mul_(mul_((float)e.y, vs), 8.0f), mul_(mul_((float)e.z, vs), 8.0f));
+    const float3 pc = xform(Ti, pos);
+    if (!(pc.z < 0)) {
+      const double half = 0.5 * (double)vs * 8.0;  // double as written in the reference (tsdf_volume.cu:460-463)
+      const float3 ctr = make_float3((float)((double)pc.x + half), (float)((double)pc.y + half), (float)((double)pc.z + half));
+      const int2 px = project(o, ctr);
+      vis = px.x >= 0 && px.y >= 0 && px.x < o.width && px.y < o.height;
+    }
+  }
+  const unsigned m = __ballot_sync(0xffffffffu, vis);
+  if (m) {
+    const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
+    int base = 0;
+    if (lane == leader) base = atomicAdd(&d.counters[2], __popc(m));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (vis) vis_list[base + __popc(m & ((1u << lane) - 1u))] = b;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+k_integrate_list(FusionDev d, const unsigned char* __restrict__ bgr, const float* __restrict__ depth, Mat4 Ti, const int* __restrict__ vis_list) {
+  const tdm_fusion_options& o = d.o;
+  const int nvis = d.counters[2];
+  const float vs = o.voxel_size, tau = o.truncation_distance;
+  for (int k = blockIdx.x; k < nvis; k += gridDim.x) {
+    const int4 e = d.list[vis_list[k]];
+    const float3 pos = make_float3(mul_(mul_((float)e.x, vs), 8.0f), mul_(mul_((float)e.y, vs), 8.0f), mul_(mul_((float)e.z, vs), 8.0f));
+    const int t = threadIdx.x;
+    const int bx = t >> 5, by = (t >> 2) & 7, bz0 = (t & 3) * 2;
+    uint4* vp = reinterpret_cast<uint4*>(d.voxels + (size_t)e.w * 512 + bx * 64 + by * 8 + bz0);
+    uint4 raw = *vp;
+    uint2 vox[2] = {make_uint2(raw.x, raw.y), make_uint2(raw.z, raw.w)};
+    bool dirty = false;
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const float3 vw = make_float3(add_(pos.x, mul_((float)bx, vs)), add_(pos.y, mul_((float)by, vs)),
+                                    add_(pos.z, mul_((float)(bz0 + q), vs)));
+      const float3 vc = xform(Ti, vw);
+      if (vc.z == 0.0f) continue;
+      const int2 px = project(o, vc);
+      if (!(px.x >= 0 && px.y >= 0 && px.x < o.width && px.y < o.height)) continue;
+      const int idx = px.y * o.width + px.x;
+      const float dz = depth[idx];
+      if (dz <= 0 || dz < o.min_sensor_depth || dz > o.max_sensor_depth) continue;
+      const float sd = norm3(get_point3d(o, idx, dz)), vd = norm3(vc);
+      float nsdf;
+      if (vd > sub_(sd, tau) && vd < add_(sd, tau) && dz < o.max_sensor_depth) nsdf = sub_(sd, vd);
+      else if (vd < sub_(sd, tau)) nsdf = tau;
+      else continue;
+      vox[q] = combine(vox[q], nsdf, bgr + 3 * (size_t)idx, o.max_sdf_weight);
+      dirty = true;
+    }
+    if (dirty) *vp = make_uint4(vox[0].x, vox[0].y, vox[1].x, vox[1].y);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------- K7
 // Per-ray block caches in front of the hash table.
 //  Cache1: the last block only.
@@ -359,6 +426,65 @@ k_raycast(FusionDev d, Mat4 T, unsigned char* __restrict__ bgr_out, float* __res
   } else {
     bgr_out[3 * i] = bgr_out[3 * i + 1] = bgr_out[3 * i + 2] = 0;
     depth_out[i] = 0.f;
+  }
+}
+
+// K7, persistent form.  Rays differ a lot in length (a few steps next to the camera's near surfaces, > 100 through free space),
+// so with one ray per thread a CTA - and every lane of a warp - idles until its slowest ray is done (ncu on B200: 38 % warps
+// active, 22 of 32 lanes executing).  Here a fixed grid of warps pulls rays from a global counter: every trip of the warp's
+// loop first refills the lanes whose ray has finished (one warp-aggregated atomicAdd), then advances every lane's ray by ONE
+// sphere-tracing step.  Rays are numbered in 8x4 pixel tiles so a warp's 32 rays stay neighbours.  Per-ray arithmetic is the
+// same expression sequence as k_raycast, so the output is bit-identical.
+__global__ void __launch_bounds__(256)
+k_raycast_persistent(FusionDev d, Mat4 T, unsigned char* __restrict__ bgr_out, float* __restrict__ depth_out, int* __restrict__ ray_counter) {
+  const tdm_fusion_options& o = d.o;
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const int tiles_x = (o.width + 7) >> 3, tiles_y = (o.height + 3) >> 2;
+  const int n_padded = tiles_x * tiles_y * 32;
+  Cache1 bc;
+  bc.init();
+  int i = 0, steps = 0;
+  float cur = 0.f;
+  bool have = false, exhausted = false;   // exhausted: the counter has passed the last ray (warp-uniform)
+  for (;;) {
+    if (!exhausted) {
+      const unsigned need = __ballot_sync(full, !have);
+      if (need) {
+        const int leader = __ffs(need) - 1;
+        int base = 0;
+        if (lane == leader) base = atomicAdd(ray_counter, __popc(need));
+        base = __shfl_sync(full, base, leader);
+        if (!have) {
+          const int idx = base + __popc(need & ((1u << lane) - 1u));
+          if (idx < n_padded) {
+            const int tile = idx >> 5, within = idx & 31;
+            const int x = (tile % tiles_x) * 8 + (within & 7), y = (tile / tiles_x) * 4 + (within >> 3);
+            if (x < o.width && y < o.height) { i = y * o.width + x; cur = 0.f; steps = 0; have = true; }
+          }
+        }
+        exhausted = base + __popc(need) >= n_padded;
+      }
+    }
+    if (exhausted && !__any_sync(full, have)) break;
+    if (have) {
+      const uint2 v = get_interpolated(d, xform(T, get_point3d(o, i, cur)), bc);
+      const unsigned w = v.y >> 24;
+      const float sdf = __uint_as_float(v.x);
+      cur = add_(cur, w == 0 ? o.truncation_distance : sdf);
+      ++steps;
+      if ((w != 0 && sdf < o.voxel_size) || !(cur < o.max_sensor_depth) || steps >= 100000) {
+        if (cur < o.max_sensor_depth) {
+          const uint2 c = get_interpolated(d, xform(T, get_point3d(o, i, cur)), bc);
+          bgr_out[3 * i] = c.y & 0xFF; bgr_out[3 * i + 1] = (c.y >> 8) & 0xFF; bgr_out[3 * i + 2] = (c.y >> 16) & 0xFF;
+          depth_out[i] = cur;
+        } else {
+          bgr_out[3 * i] = bgr_out[3 * i + 1] = bgr_out[3 * i + 2] = 0;
+          depth_out[i] = 0.f;
+        }
+        have = false;
+      }
+    }
   }
 }
 
@@ -467,6 +593,13 @@ class FusionImpl final : public FusionIface {
     TDM_CUDA(cudaMalloc(&d_.voxels, (size_t)o.num_blocks * 512 * 8));
     TDM_CUDA(cudaMalloc(&d_.list, (size_t)o.num_blocks * sizeof(int4)));
     TDM_CUDA(cudaMalloc(&d_.counters, 8 * sizeof(int)));
+    TDM_CUDA(cudaMalloc(&d_vis_list_, (size_t)o.num_blocks * sizeof(int)));
+    {
+      int per_sm = 0, sms = 0;
+      TDM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_raycast_persistent, 256, 0));
+      TDM_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device_));
+      raycast_grid_ = std::max(1, per_sm) * std::max(1, sms);
+    }
     TDM_CUDA(cudaMemsetAsync(d_.voxels, 0, (size_t)o.num_blocks * 512 * 8, stream_));
     TDM_CUDA(cudaMemsetAsync(d_.counters, 0, 8 * sizeof(int), stream_));
     k_fill_keys<<<cdiv(n_entries_, 256), 256, 0, stream_>>>(d_.keys, d_.ptrs, n_entries_);
@@ -493,7 +626,7 @@ class FusionImpl final : public FusionIface {
   ~FusionImpl() override {
     cudaSetDevice(device_);
     cudaStreamSynchronize(stream_);
-    cudaFree(d_.keys); cudaFree(d_.ptrs); cudaFree(d_.voxels); cudaFree(d_.list); cudaFree(d_.counters);
+    cudaFree(d_.keys); cudaFree(d_.ptrs); cudaFree(d_.voxels); cudaFree(d_.list); cudaFree(d_.counters); cudaFree(d_vis_list_);
     cudaFreeHost(h_bgr_in_); cudaFreeHost(h_depth_in_); cudaFree(d_bgr_in_); cudaFree(d_depth_in_);
     for (int half = 0; half < 2; ++half) { cudaFreeHost(h_bgr_out_[half]); cudaFreeHost(h_depth_out_[half]); }
     cudaFree(d_bgr_out_); cudaFree(d_depth_out_); cudaFreeHost(h_counters_);
@@ -695,6 +828,8 @@ class FusionImpl final : public FusionIface {
     const std::string n(name);
     if (n == "alloc_filter") alloc_filter_ = value != 0;
     else if (n == "raycast_cache8") raycast_cache8_ = value != 0;
+    else if (n == "raycast_persistent") raycast_persistent_ = value != 0;
+    else if (n == "integrate_compact") integrate_compact_ = value != 0;
     else throw Error("unknown fusion option " + n);
   }
   bool mesh_pending() override { return mesh_pending_; }
@@ -766,14 +901,24 @@ class FusionImpl final : public FusionIface {
     else k_allocate<false><<<cdiv(npx, 128), 128, 0, stream_>>>(d_, d_depth_in_, pose_);
     TDM_CUDA(cudaGetLastError());
     if (ev_split_) TDM_CUDA(cudaEventRecord(ev_split_, stream_));
-    k_integrate<<<148 * 8, 256, 0, stream_>>>(d_, d_bgr_in_, d_depth_in_, pose_inv_);
+    if (integrate_compact_) {
+      k_visible<<<cdiv(d_.o.num_blocks, 256), 256, 0, stream_>>>(d_, pose_inv_, d_vis_list_);
+      TDM_CUDA(cudaGetLastError());
+      k_integrate_list<<<148 * 8, 256, 0, stream_>>>(d_, d_bgr_in_, d_depth_in_, pose_inv_, d_vis_list_);
+    } else {
+      k_integrate<<<148 * 8, 256, 0, stream_>>>(d_, d_bgr_in_, d_depth_in_, pose_inv_);
+    }
     TDM_CUDA(cudaGetLastError());
   }
   void launch_render(int n, bool copy_back) {
     const size_t npx = (size_t)d_.o.height * d_.o.width;
     dim3 grid(cdiv(d_.o.width, 16), cdiv(d_.o.height, 16));
     for (int i = 0; i < n; ++i) {
-      if (raycast_cache8_) k_raycast<true><<<grid, 256, 0, stream_>>>(d_, render_poses_[i], d_bgr_out_ + (size_t)i * npx * 3, d_depth_out_ + (size_t)i * npx);
+      if (raycast_persistent_) {
+        TDM_CUDA(cudaMemsetAsync(d_.counters + 4, 0, sizeof(int), stream_));
+        k_raycast_persistent<<<raycast_grid_, 256, 0, stream_>>>(d_, render_poses_[i], d_bgr_out_ + (size_t)i * npx * 3,
+                                                                 d_depth_out_ + (size_t)i * npx, d_.counters + 4);
+      } else if (raycast_cache8_) k_raycast<true><<<grid, 256, 0, stream_>>>(d_, render_poses_[i], d_bgr_out_ + (size_t)i * npx * 3, d_depth_out_ + (size_t)i * npx);
       else k_raycast<false><<<grid, 256, 0, stream_>>>(d_, render_poses_[i], d_bgr_out_ + (size_t)i * npx * 3, d_depth_out_ + (size_t)i * npx);
       TDM_CUDA(cudaGetLastError());
     }
@@ -821,6 +966,9 @@ class FusionImpl final : public FusionIface {
   bool have_scan_ = false;
   Next next_ = kIntegrate;
   bool alloc_filter_ = false, raycast_cache8_ = false;   // tdm_fusion_set_option: measured on B200 (profiles/r01_fusion_tracker.txt), neither pays: 0.071 vs 0.065 ms, 0.87 vs 0.82 ms
+  bool raycast_persistent_ = true, integrate_compact_ = true;
+  int* d_vis_list_ = nullptr;
+  int raycast_grid_ = 148;
   cudaEvent_t ev_split_ = nullptr;
   float last_alloc_ms_ = 0.f;
   long long* d_hit_keys_ = nullptr;

@@ -39,14 +39,16 @@ st = f.stats()
 vis = st["visible_blocks"]
 alg = vis * 512 * 16 + 7 * H * W
 res = {}
-for name, opts in (("default", {}), ("alloc_filter", {"alloc_filter": 1}), ("raycast_cache8", {"raycast_cache8": 1})):
-    for k in ("alloc_filter", "raycast_cache8"):
-        f.set_option(k, opts.get(k, 0))
+DEFAULTS = {"alloc_filter": 0, "raycast_cache8": 0, "raycast_persistent": 1, "integrate_compact": 1}
+for name, opts in (("default", {}), ("alloc_filter", {"alloc_filter": 1}), ("raycast_one_ray_per_thread", {"raycast_persistent": 0}),
+                   ("raycast_one_ray_per_thread_cache8", {"raycast_persistent": 0, "raycast_cache8": 1}), ("integrate_full_scan", {"integrate_compact": 0})):
+    for k, dv in DEFAULTS.items():
+        f.set_option(k, opts.get(k, dv))
     f.run_resident(3)
     mi, mr = f.run_resident(20)
     res[name] = {"allocate_ms": f.last_alloc_ms(), "allocate+integrate_ms": mi / 20, "raycast_ms": mr / 20}
-for k in ("alloc_filter", "raycast_cache8"):
-    f.set_option(k, 0)
+for k, dv in DEFAULTS.items():
+    f.set_option(k, dv)
 mi = res["default"]["allocate+integrate_ms"] * 20
 mr = res["default"]["raycast_ms"] * 20
 print(json.dumps({"what": "tsdf ours", "frames": n_frames, "allocated_blocks": st["allocated_blocks"], "visible_blocks_last": vis,
