@@ -966,7 +966,7 @@ class FusionImpl final : public FusionIface {
   bool have_scan_ = false;
   Next next_ = kIntegrate;
   bool alloc_filter_ = false, raycast_cache8_ = false;   // tdm_fusion_set_option: measured on B200 (profiles/r01_fusion_tracker.txt), neither pays: 0.071 vs 0.065 ms, 0.87 vs 0.82 ms
-  bool raycast_persistent_ = true, integrate_compact_ = true;
+  bool raycast_persistent_ = false, integrate_compact_ = true;   // measured: persistent 0.875 ms vs 0.820 ms (instruction-bound, not imbalance-bound)
   int* d_vis_list_ = nullptr;
   int raycast_grid_ = 148;
   cudaEvent_t ev_split_ = nullptr;
