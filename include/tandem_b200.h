@@ -164,7 +164,8 @@ int tdm_fusion_last_alloc_ms(tdm_fusion* h, float* ms);
 /* A/B switches for measurements (results are bit-identical either way): "alloc_filter" (CTA-level shared-memory filter in
  * front of the hash table during allocation), "raycast_cache8" (8-entry per-ray block cache); both default to 0 - measured
  * on B200 they do not pay (the table probes are L2 hits behind other latency); "raycast_persistent" (warps pull rays from a
- * counter and refill finished lanes; default 0 = one ray per thread, which measured faster: 0.82 vs 0.875 ms), "integrate_compact" (visibility pass + update of the
+ * counter and refill finished lanes; default 0 = one ray per thread, which measured faster: 0.82 vs 0.875 ms), "raycast_shared" (index arithmetic shared between the nine voxel reads of a sample, one block lookup when they sit in one
+ * block; default 1), "integrate_compact" (visibility pass + update of the
  * visible blocks only, default 1; 0 = every CTA scans the whole block list). */
 int tdm_fusion_set_option(tdm_fusion* h, const char* name, int value);
 

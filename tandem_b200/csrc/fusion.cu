@@ -397,6 +397,98 @@ __device__ uint2 get_interpolated(const FusionDev& d, float3 p, Cache& bc) {  //
   return make_uint2(__float_as_uint(dist), col | (v0.y & 0xFF000000u));
 }
 
+// get_interpolated with the index arithmetic shared between the nine voxel reads (same values, same order of the fp32
+// operations that produce the result -> bit-identical).  WorldToGlobalVoxel is separable per axis, so a sample needs three
+// divisions per axis (the sample itself, and the two dual-cell corners) instead of three per voxel read; and when the eight
+// corners are index-adjacent and sit inside one voxel block (two thirds of all samples) they are read from ONE block lookup at
+// constant offsets.  ncu on the one-lookup-per-voxel form: 502 M warp instructions per 640x480 render, 18 % of them FP32.
+__device__ __forceinline__ int w2g_axis(float q /* = x / s */, float x) {   // tsdf_volume.cu:109-113, division hoisted
+  return (int)add_(q, mul_((float)sgn(x), 0.5f));
+}
+template <class Cache>
+__device__ __forceinline__ uint2 voxel_at(const FusionDev& d, int gx, int gy, int gz, Cache& bc) {
+  const int ptr = bc.find(d, gx >> 3, gy >> 3, gz >> 3);
+  if (ptr < 0) return make_uint2(0u, 0u);
+  return __ldg(d.voxels + (size_t)ptr * 512 + (gx & 7) * 64 + (gy & 7) * 8 + (gz & 7));
+}
+template <class Cache>
+__device__ uint2 get_interpolated_shared(const FusionDev& d, float3 p, Cache& bc) {
+  const float s = d.o.voxel_size;
+  const float3 vp = make_float3(div_(p.x, s), div_(p.y, s), div_(p.z, s));
+  const uint2 v0 = voxel_at(d, w2g_axis(vp.x, p.x), w2g_axis(vp.y, p.y), w2g_axis(vp.z, p.z), bc);
+  if ((v0.y >> 24) == 0) return v0;
+  const float hs = div_(s, 2.0f);
+  const float3 pd = make_float3(sub_(p.x, hs), sub_(p.y, hs), sub_(p.z, hs));
+  const float wx = sub_(vp.x, floorf(vp.x)), wy = sub_(vp.y, floorf(vp.y)), wz = sub_(vp.z, floorf(vp.z));
+  const float ux = sub_(1.f, wx), uy = sub_(1.f, wy), uz = sub_(1.f, wz);
+  // the two voxel indices per axis that the corners pd + {0, s} round to
+  const float ax0 = add_(pd.x, 0.f), ax1 = add_(pd.x, s), ay0 = add_(pd.y, 0.f), ay1 = add_(pd.y, s), az0 = add_(pd.z, 0.f), az1 = add_(pd.z, s);
+  const int gx0 = w2g_axis(div_(ax0, s), ax0), gx1 = w2g_axis(div_(ax1, s), ax1);
+  const int gy0 = w2g_axis(div_(ay0, s), ay0), gy1 = w2g_axis(div_(ay1, s), ay1);
+  const int gz0 = w2g_axis(div_(az0, s), az0), gz1 = w2g_axis(div_(az1, s), az1);
+  uint2 c[8];   // corner order of the reference: 000,100,010,001,110,011,101,111
+  const bool one_block = gx1 == gx0 + 1 && gy1 == gy0 + 1 && gz1 == gz0 + 1 && (gx0 & 7) != 7 && (gy0 & 7) != 7 && (gz0 & 7) != 7;
+  if (one_block) {
+    const int ptr = bc.find(d, gx0 >> 3, gy0 >> 3, gz0 >> 3);
+    if (ptr < 0) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) c[k] = make_uint2(0u, 0u);
+    } else {
+      const uint2* b = d.voxels + (size_t)ptr * 512 + (gx0 & 7) * 64 + (gy0 & 7) * 8 + (gz0 & 7);
+      c[0] = __ldg(b); c[1] = __ldg(b + 64); c[2] = __ldg(b + 8); c[3] = __ldg(b + 1);
+      c[4] = __ldg(b + 72); c[5] = __ldg(b + 9); c[6] = __ldg(b + 65); c[7] = __ldg(b + 73);
+    }
+  } else {
+    c[0] = voxel_at(d, gx0, gy0, gz0, bc); c[1] = voxel_at(d, gx1, gy0, gz0, bc); c[2] = voxel_at(d, gx0, gy1, gz0, bc);
+    c[3] = voxel_at(d, gx0, gy0, gz1, bc); c[4] = voxel_at(d, gx1, gy1, gz0, bc); c[5] = voxel_at(d, gx0, gy1, gz1, bc);
+    c[6] = voxel_at(d, gx1, gy0, gz1, bc); c[7] = voxel_at(d, gx1, gy1, gz1, bc);
+  }
+  float dist = 0.f, cf[3] = {0.f, 0.f, 0.f};
+  const int ox[8] = {0, 1, 0, 0, 1, 0, 1, 1}, oy[8] = {0, 0, 1, 0, 1, 1, 0, 1}, oz[8] = {0, 0, 0, 1, 0, 1, 1, 1};
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    uint2 v = c[k];
+    if ((v.y >> 24) == 0) v = v0;
+    const float w = mul_(mul_(ox[k] ? wx : ux, oy[k] ? wy : uy), oz[k] ? wz : uz);
+    dist = add_(dist, mul_(w, __uint_as_float(v.x)));
+#pragma unroll
+    for (int q = 0; q < 3; ++q) cf[q] = add_(cf[q], mul_(w, (float)((v.y >> (8 * q)) & 0xFF)));
+  }
+  unsigned col = 0;
+#pragma unroll
+  for (int q = 0; q < 3; ++q) col |= ((unsigned)cf[q] & 0xFF) << (8 * q);
+  return make_uint2(__float_as_uint(dist), col | (v0.y & 0xFF000000u));
+}
+
+// one ray per thread, shared-index sampling (the default ray-cast)
+__global__ void __launch_bounds__(256)
+k_raycast_shared(FusionDev d, Mat4 T, unsigned char* __restrict__ bgr_out, float* __restrict__ depth_out) {
+  const tdm_fusion_options& o = d.o;
+  const int x = blockIdx.x * 16 + (threadIdx.x & 15);
+  const int y = blockIdx.y * 16 + (threadIdx.x >> 4);
+  if (x >= o.width || y >= o.height) return;
+  const int i = y * o.width + x;
+  Cache1 bc;
+  bc.init();
+  float cur = 0.f;
+  int guard = 0;
+  while (cur < o.max_sensor_depth && guard++ < 100000) {
+    const uint2 v = get_interpolated_shared(d, xform(T, get_point3d(o, i, cur)), bc);
+    const unsigned w = v.y >> 24;
+    const float sdf = __uint_as_float(v.x);
+    cur = add_(cur, w == 0 ? o.truncation_distance : sdf);
+    if (w != 0 && sdf < o.voxel_size) break;
+  }
+  if (cur < o.max_sensor_depth) {
+    const uint2 v = get_interpolated_shared(d, xform(T, get_point3d(o, i, cur)), bc);
+    bgr_out[3 * i] = v.y & 0xFF; bgr_out[3 * i + 1] = (v.y >> 8) & 0xFF; bgr_out[3 * i + 2] = (v.y >> 16) & 0xFF;
+    depth_out[i] = cur;
+  } else {
+    bgr_out[3 * i] = bgr_out[3 * i + 1] = bgr_out[3 * i + 2] = 0;
+    depth_out[i] = 0.f;
+  }
+}
+
 template <bool CACHE8>
 __global__ void __launch_bounds__(256)
 k_raycast(FusionDev d, Mat4 T, unsigned char* __restrict__ bgr_out, float* __restrict__ depth_out) {
@@ -829,6 +921,7 @@ class FusionImpl final : public FusionIface {
     if (n == "alloc_filter") alloc_filter_ = value != 0;
     else if (n == "raycast_cache8") raycast_cache8_ = value != 0;
     else if (n == "raycast_persistent") raycast_persistent_ = value != 0;
+    else if (n == "raycast_shared") raycast_shared_ = value != 0;
     else if (n == "integrate_compact") integrate_compact_ = value != 0;
     else throw Error("unknown fusion option " + n);
   }
@@ -914,7 +1007,9 @@ class FusionImpl final : public FusionIface {
     const size_t npx = (size_t)d_.o.height * d_.o.width;
     dim3 grid(cdiv(d_.o.width, 16), cdiv(d_.o.height, 16));
     for (int i = 0; i < n; ++i) {
-      if (raycast_persistent_) {
+      if (raycast_shared_ && !raycast_persistent_ && !raycast_cache8_) {
+        k_raycast_shared<<<grid, 256, 0, stream_>>>(d_, render_poses_[i], d_bgr_out_ + (size_t)i * npx * 3, d_depth_out_ + (size_t)i * npx);
+      } else if (raycast_persistent_) {
         TDM_CUDA(cudaMemsetAsync(d_.counters + 4, 0, sizeof(int), stream_));
         k_raycast_persistent<<<raycast_grid_, 256, 0, stream_>>>(d_, render_poses_[i], d_bgr_out_ + (size_t)i * npx * 3,
                                                                  d_depth_out_ + (size_t)i * npx, d_.counters + 4);
@@ -966,6 +1061,7 @@ class FusionImpl final : public FusionIface {
   bool have_scan_ = false;
   Next next_ = kIntegrate;
   bool alloc_filter_ = false, raycast_cache8_ = false;   // tdm_fusion_set_option: measured on B200 (profiles/r01_fusion_tracker.txt), neither pays: 0.071 vs 0.065 ms, 0.87 vs 0.82 ms
+  bool raycast_shared_ = true;
   bool raycast_persistent_ = false, integrate_compact_ = true;   // measured: persistent 0.875 ms vs 0.820 ms (instruction-bound, not imbalance-bound)
   int* d_vis_list_ = nullptr;
   int raycast_grid_ = 148;
