@@ -460,12 +460,15 @@ __device__ uint2 get_interpolated_shared(const FusionDev& d, float3 p, Cache& bc
   return make_uint2(__float_as_uint(dist), col | (v0.y & 0xFF000000u));
 }
 
-// one ray per thread, shared-index sampling (the default ray-cast)
-__global__ void __launch_bounds__(256)
+// one ray per thread, shared-index sampling (the default ray-cast).  The kernel is latency-bound (a step is one long dependent
+// chain: divide -> convert -> address -> load -> interpolate -> next t) and rays differ a lot in length, so small CTAs (8x8
+// pixels) at high residency balance better than 16x16 ones: TW x TH pixel tiles, MINB CTAs per SM requested.
+template <int TW, int TH, int MINB>
+__global__ void __launch_bounds__(TW * TH, MINB)
 k_raycast_shared(FusionDev d, Mat4 T, unsigned char* __restrict__ bgr_out, float* __restrict__ depth_out) {
   const tdm_fusion_options& o = d.o;
-  const int x = blockIdx.x * 16 + (threadIdx.x & 15);
-  const int y = blockIdx.y * 16 + (threadIdx.x >> 4);
+  const int x = blockIdx.x * TW + (threadIdx.x % TW);
+  const int y = blockIdx.y * TH + (threadIdx.x / TW);
   if (x >= o.width || y >= o.height) return;
   const int i = y * o.width + x;
   Cache1 bc;
@@ -922,6 +925,7 @@ class FusionImpl final : public FusionIface {
     else if (n == "raycast_cache8") raycast_cache8_ = value != 0;
     else if (n == "raycast_persistent") raycast_persistent_ = value != 0;
     else if (n == "raycast_shared") raycast_shared_ = value != 0;
+    else if (n == "raycast_tile") raycast_tile_ = value;
     else if (n == "integrate_compact") integrate_compact_ = value != 0;
     else throw Error("unknown fusion option " + n);
   }
@@ -1008,7 +1012,12 @@ class FusionImpl final : public FusionIface {
     dim3 grid(cdiv(d_.o.width, 16), cdiv(d_.o.height, 16));
     for (int i = 0; i < n; ++i) {
       if (raycast_shared_ && !raycast_persistent_ && !raycast_cache8_) {
-        k_raycast_shared<<<grid, 256, 0, stream_>>>(d_, render_poses_[i], d_bgr_out_ + (size_t)i * npx * 3, d_depth_out_ + (size_t)i * npx);
+        unsigned char* bo = d_bgr_out_ + (size_t)i * npx * 3;
+        float* dout_i = d_depth_out_ + (size_t)i * npx;
+        if (raycast_tile_ == 0) k_raycast_shared<16, 16, 5><<<grid, 256, 0, stream_>>>(d_, render_poses_[i], bo, dout_i);
+        else if (raycast_tile_ == 1) k_raycast_shared<8, 8, 24><<<dim3(cdiv(d_.o.width, 8), cdiv(d_.o.height, 8)), 64, 0, stream_>>>(d_, render_poses_[i], bo, dout_i);
+        else if (raycast_tile_ == 2) k_raycast_shared<8, 4, 48><<<dim3(cdiv(d_.o.width, 8), cdiv(d_.o.height, 4)), 32, 0, stream_>>>(d_, render_poses_[i], bo, dout_i);
+        else k_raycast_shared<16, 8, 12><<<dim3(cdiv(d_.o.width, 16), cdiv(d_.o.height, 8)), 128, 0, stream_>>>(d_, render_poses_[i], bo, dout_i);
       } else if (raycast_persistent_) {
         TDM_CUDA(cudaMemsetAsync(d_.counters + 4, 0, sizeof(int), stream_));
         k_raycast_persistent<<<raycast_grid_, 256, 0, stream_>>>(d_, render_poses_[i], d_bgr_out_ + (size_t)i * npx * 3,
@@ -1062,6 +1071,7 @@ class FusionImpl final : public FusionIface {
   Next next_ = kIntegrate;
   bool alloc_filter_ = false, raycast_cache8_ = false;   // tdm_fusion_set_option: measured on B200 (profiles/r01_fusion_tracker.txt), neither pays: 0.071 vs 0.065 ms, 0.87 vs 0.82 ms
   bool raycast_shared_ = true;
+  int raycast_tile_ = 1;   // 0: 16x16 px CTAs, 1: 8x8, 2: 8x4 (one warp), 3: 16x8
   bool raycast_persistent_ = false, integrate_compact_ = true;   // measured: persistent 0.875 ms vs 0.820 ms (instruction-bound, not imbalance-bound)
   int* d_vis_list_ = nullptr;
   int raycast_grid_ = 148;
