@@ -17,4 +17,9 @@ timeout 300 ncu --set full --clock-control none --import-source on -k regex:k_co
     python tools/quick_profile.py mixed16 > gpurun_out/${R}_ncu_cv.log 2>&1
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:k_conv_tc_is -c 6 -f -o gpurun_out/${R}_conv_tc_is \
     python tools/quick_profile.py mixed16 > gpurun_out/${R}_ncu_is.log 2>&1
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:"k_raycast_shared|k_integrate_list|k_visible|k_allocate" --launch-skip 140 --launch-count 4 \
+    -f -o gpurun_out/${R}_tsdf python tools/bench_fusion_tracker.py 36 > gpurun_out/${R}_ncu_tsdf.log 2>&1
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:k_mesh --launch-count 3 -f -o gpurun_out/${R}_mesh \
+    python tools/bench_fusion_tracker.py 36 > gpurun_out/${R}_ncu_mesh.log 2>&1
+timeout 400 python tools/bench_config3.py --frames 1000 > gpurun_out/${R}_config3.txt 2>&1
 ls -la gpurun_out | grep ${R}_

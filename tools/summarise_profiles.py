@@ -123,7 +123,18 @@ def main():
     traffic.update(summarise_rep("conv_tc_is", "the input-stationary tcgen05 3-D convolution (k_conv_tc_is)",
                                  "Launch order: stage-1 CostRegNet conv0 first. Shared-memory operand streaming of the small-N MMAs is the "
                                  "limiter (L1/TEX throughput includes shared memory), see DESIGN.md section 5."))
-    json.dump(traffic, open(os.path.join(P, f"{R}_ncu_traffic.json"), "w"), indent=1)
+    traffic.update(summarise_rep("tsdf", "the TSDF kernels at the 36th frame of tools/bench_fusion_tracker.py (K5 allocate, K6 visibility + update, K7 ray-cast)",
+                                 "640x480 scan into the initDr-sized map (90 k blocks allocated, 8 k in view). k_allocate / k_raycast_shared are "
+                                 "latency-bound chains of dependent table / voxel reads (L2 hits), k_integrate_list streams 16 B per voxel of the "
+                                 "visible blocks; see DESIGN.md section 5."))
+    traffic.update(summarise_rep("mesh", "marching cubes (k_mesh<count>, k_mesh_scan, k_mesh<emit>) over the 10 m box of tandem_backend.cpp:80-81",
+                                 "Block-sparse two-pass extraction (DESIGN.md section 5): one CTA per allocated block, 12^3 voxel tile in shared memory."))
+    tj = os.path.join(P, f"{R}_ncu_traffic.json")
+    if os.path.exists(tj):      # keep the entries of captures that are not in gpurun_out/ any more
+        old = json.load(open(tj))
+        old.update(traffic)
+        traffic = old
+    json.dump(traffic, open(tj, "w"), indent=1)
     summarise_launches()
     for f in ("bench.json", "bench_reference.json", "kernels.txt", "fusion_tracker.txt", "loop.txt", "pytest_gpu.log"):
         s = os.path.join(G, f"{R}_{f}")
