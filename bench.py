@@ -154,7 +154,19 @@ def dist_setup(n):
     import torch.distributed as dist
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
-    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    # NCCL announces its version on stdout when the communicator is created (NCCL_DEBUG=VERSION in this image); stdout is
+    # reserved for the ONE JSON line, so fd 1 points at stderr until the communicator exists.
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        dist.barrier()
+        torch.cuda.synchronize(local)
+    finally:
+        sys.stdout.flush()
+        os.dup2(saved, 1)
+        os.close(saved)
     return rank, world, local, dist
 
 

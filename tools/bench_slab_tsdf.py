@@ -33,7 +33,15 @@ def main():
     torch.cuda.set_device(local)
     if world > 1:
         import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)          # NCCL's version banner goes to stderr, stdout carries the JSON line only
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            dist.barrier()
+        finally:
+            os.dup2(saved, 1)
+            os.close(saved)
     H, W = 480, 640
     intr = dict(fx=320.0, fy=320.0, cx=319.5, cy=239.5)
     half = 5.0                                   # 10 m room inside the 10.24 m (1024^3 voxels at 1 cm) cube
