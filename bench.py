@@ -199,6 +199,7 @@ def main():
     ap.add_argument("--inflight", type=int, default=8, choices=[1, 2, 3, 4, 5, 6, 7, 8],
                     help="independent windows in flight per GPU (n DrMvsnet handles, one stream each, used round-robin) in both legs")
     ap.add_argument("--tc", type=int, default=-1, help="1/0: force the tcgen05 conv path on/off (default: engine default)")
+    ap.add_argument("--opt", action="append", default=[], help="engine option key=int for A/B runs, e.g. --opt fork_fpn=0")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3) if a.impl == "ours" else a.warmup
 
@@ -232,6 +233,10 @@ def main():
     if a.tc >= 0:
         for h in [m] + extra:
             h.set_option("use_tc", a.tc)
+    for kv in a.opt:
+        k, v = kv.split("=")
+        for h in [m] + extra:
+            h.set_option(k, int(v))
 
     def call():
         m.CallAsync(win["H"], win["W"], win["V"], win["ref_index"], win["bgrs"], win["K"], win["c2ws"], win["dmin"],

@@ -137,6 +137,9 @@ class MvsnetEngine final : public MvsnetIface {
     int lo, hi;
     TDM_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
     TDM_CUDA(cudaStreamCreateWithPriority(&stream_, cudaStreamNonBlocking, lo));
+    TDM_CUDA(cudaStreamCreateWithPriority(&side_stream_, cudaStreamNonBlocking, lo));
+    TDM_CUDA(cudaEventCreateWithFlags(&ev_fork_, cudaEventDisableTiming));
+    TDM_CUDA(cudaEventCreateWithFlags(&ev_join_, cudaEventDisableTiming));
     slot_ = acquire_slot();
     for (auto& e : ev_out_) TDM_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     upload_weights();
@@ -160,6 +163,9 @@ class MvsnetEngine final : public MvsnetIface {
     if (h_params_) cudaFreeHost(h_params_);
     if (d_params_) cudaFree(d_params_);
     for (auto& e : ev_out_) if (e) cudaEventDestroy(e);
+    if (ev_fork_) cudaEventDestroy(ev_fork_);
+    if (ev_join_) cudaEventDestroy(ev_join_);
+    if (side_stream_) cudaStreamDestroy(side_stream_);
     if (stream_) cudaStreamDestroy(stream_);
   }
 
@@ -182,6 +188,7 @@ class MvsnetEngine final : public MvsnetIface {
     else if (key == "keep_intermediates") keep_ = value != 0;
     else if (key == "use_tc") use_tc_ = value != 0;
     else if (key == "use_is") use_is_ = value != 0;
+    else if (key == "fork_fpn") fork_fpn_ = value != 0;
     else throw Error("unknown option " + key);
   }
 
@@ -1154,7 +1161,23 @@ class MvsnetEngine final : public MvsnetIface {
     conv("f.conv2.0", "f.c2", "f.c2_0", 1, 2, 2, true);
     conv("f.conv2.1", "f.c2_0", "f.c2_1", 1, 1, 1, true);
     conv("f.conv2.2", "f.c2_1", "f.c1", 1, 1, 1, true);
-    conv("f.out1", "f.c1", "feat1", 1, 1, 1, false);
+    // The pyramid's upper outputs (feat2, feat3) are only read by stages 2 and 3, while stage 1 needs feat1 alone and its
+    // coarse U-Net levels leave most SMs idle: the FPN tail runs on a second stream, forked here and joined before the
+    // stage-2 cost volume (inside the captured graph these are two parallel branches).  Not while profiling: the per-kernel
+    // events assume one stream.
+    const bool fork = fork_fpn_ && !profiling;
+    struct SwapBack {   // an exception inside the branch must not leave the engine on the side stream
+      cudaStream_t &a, &b; bool on;
+      ~SwapBack() { if (on) std::swap(a, b); }
+    } side{stream_, side_stream_, false};
+    if (fork) {
+      TDM_CUDA(cudaEventRecord(ev_fork_, stream_));
+      TDM_CUDA(cudaStreamWaitEvent(side_stream_, ev_fork_, 0));
+      std::swap(stream_, side_stream_);
+      side.on = true;
+    } else {
+      conv("f.out1", "f.c1", "feat1", 1, 1, 1, false);
+    }
     if (fused_fpn_ && use_tc_) {
       conv("f.skip2", "f.c2", "f.i2", 1, 1, 1, false, 2, "f.c1", "f.i2b", d_bs3_);
       conv("f.out2", "f.i2", "feat2", 1, 1, 1, false);
@@ -1166,11 +1189,18 @@ class MvsnetEngine final : public MvsnetIface {
       conv("f.skip3", "f.c3", "f.i3", 1, 1, 1, false, 2, "f.i2");
       conv("f.out3", "f.i3", "feat3", 1, 1, 1, false);
     }
+    if (fork) {
+      TDM_CUDA(cudaEventRecord(ev_join_, stream_));      // stream_ is the side stream here
+      std::swap(stream_, side_stream_);
+      side.on = false;
+      conv("f.out1", "f.c1", "feat1", 1, 1, 1, false);
+    }
 
     for (int s = 1; s <= 3; ++s) {
       const std::string k = "s" + std::to_string(s) + ".";
       const HypSpec hs = hyp_spec(s);
       const DevBuf& dd = bufs_.at(k + "depth_dense");
+      if (s == 2 && fork) TDM_CUDA(cudaStreamWaitEvent(stream_, ev_join_, 0));
       if (s > 1) {
         const DevBuf& pd = bufs_.at("s" + std::to_string(s - 1) + ".depth_dense");
         rec_begin(k + "adaptive_dmin", 4.0 * (pd.H * pd.W + dd.H * dd.W), 0);
@@ -1274,6 +1304,9 @@ class MvsnetEngine final : public MvsnetIface {
   int tc_smem_kb_ = 225;   // shared-memory budget of the tile planner (<= 113 lets two CTAs share an SM)
   bool use_is_ = true;   // input-stationary kernel for the 3-D stride-1 convs
   bool fused_fpn_ = false;
+  bool fork_fpn_ = true;      // FPN tail on a second stream / graph branch (A/B: set_option("fork_fpn", 0))
+  cudaStream_t side_stream_ = nullptr;
+  cudaEvent_t ev_fork_ = nullptr, ev_join_ = nullptr;
   bool filter_all_ = false, keep_ = true, use_tc_ = (sizeof(TA) == 2);  // tcgen05 convs are the default on 16-bit engines
   bool profiling_ = false;
   int launch_count_ = 0, launches_per_forward_ = 0;
