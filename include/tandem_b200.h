@@ -144,6 +144,10 @@ long long tdm_fusion_extract_mesh(tdm_fusion* h, const float lower[3], const flo
                                   float* vert, float* cols, size_t max_vertices);
 int tdm_fusion_extract_mesh_async(tdm_fusion* h, const float lower[3], const float upper[3]);
 long long tdm_fusion_get_mesh(tdm_fusion* h, float* vert, float* cols, size_t max_vertices);
+/* Host-only introspection (no GPU needed): the per-axis cell table the mesh extractor uploads for one axis of a box - per cell
+ * the voxel indices {gMA, gMB, gPA, gPB, gC} (ints5), {wM, wP, cM, cP} (floats4), and per voxel block {first cell, #cells}
+ * (ranges2, bmin_nb = {first block, #blocks}). Returns the number of cells (mesh_extractor.cu:248-261 arithmetic). */
+int tdm_debug_mesh_axis_table(float lower, float upper, float voxel_size, int* ints5, float* floats4, int* ranges2, int* bmin_nb, int capacity);
 /* Device time (CUDA events) of the last extraction: classify + scan + emit. */
 int tdm_fusion_last_mesh_ms(tdm_fusion* h, float* ms);
 /* Introspection for parity tests and the roofline: counters of the last integrate / render. */

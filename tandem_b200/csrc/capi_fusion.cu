@@ -99,6 +99,12 @@ int tdm_fusion_unpack_keys(tdm_fusion* h, const long long* keys_dev, float* dept
   return TDM_OK;
   TDM_API_END
 }
+int tdm_debug_mesh_axis_table(float lower, float upper, float voxel_size, int* ints5, float* floats4, int* ranges2, int* bmin_nb, int capacity) {
+  TDM_API_BEGIN
+  TDM_CHECK(ints5 && floats4 && ranges2 && bmin_nb && capacity > 0, "null argument");
+  return tdm::mesh_axis_table(lower, upper, voxel_size, ints5, floats4, ranges2, bmin_nb, capacity);
+  TDM_API_END
+}
 int tdm_fusion_set_option(tdm_fusion* h, const char* name, int value) {
   TDM_API_BEGIN
   TDM_CHECK(h && name, "null argument");

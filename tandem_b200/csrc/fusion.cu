@@ -1094,4 +1094,18 @@ class FusionImpl final : public FusionIface {
 
 FusionIface* make_fusion(const tdm_fusion_options& o, int device) { return new FusionImpl(o, device); }
 
+// host-only view of the mesh extractor's per-axis table (no GPU involved; used by the CPU test-suite)
+int mesh_axis_table(float lower, float upper, float voxel_size, int* ints5, float* floats4, int* ranges2, int* bmin, int cap) {
+  const MeshAxisHost A = build_mesh_axis(lower, upper, voxel_size);
+  const int n = (int)A.cells.size();
+  for (int i = 0; i < n && i < cap; ++i) {
+    const MeshAxisCell& c = A.cells[i];
+    ints5[5 * i] = c.gMA; ints5[5 * i + 1] = c.gMB; ints5[5 * i + 2] = c.gPA; ints5[5 * i + 3] = c.gPB; ints5[5 * i + 4] = c.gC;
+    floats4[4 * i] = c.wM; floats4[4 * i + 1] = c.wP; floats4[4 * i + 2] = c.cM; floats4[4 * i + 3] = c.cP;
+  }
+  for (int b = 0; b < A.nb && b < cap; ++b) { ranges2[2 * b] = A.ranges[b].x; ranges2[2 * b + 1] = A.ranges[b].y; }
+  if (bmin) { bmin[0] = A.bmin; bmin[1] = A.nb; }
+  return n;
+}
+
 }  // namespace tdm

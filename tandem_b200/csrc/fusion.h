@@ -33,5 +33,6 @@ class FusionIface {
 };
 
 FusionIface* make_fusion(const tdm_fusion_options& o, int device);
+int mesh_axis_table(float lower, float upper, float voxel_size, int* ints5, float* floats4, int* ranges2, int* bmin, int cap);
 
 }  // namespace tdm

@@ -52,3 +52,53 @@ def test_product_does_not_import_oracle():
                 code = "\n".join(l for l in src.splitlines() if not l.strip().startswith(("//", "#", "*", '"""')))
                 assert not re.search(r"^\s*(from|import)\s+oracle", code, re.M), f"{f} imports the oracle"
                 assert "oracle/_build" not in code and "libtsdf_oracle" not in code, f
+
+
+def test_mesh_axis_tables_match_a_float32_restatement():
+    """Host logic of the mesh extractor (no GPU): the per-axis cell table equals an independent float32 restatement of
+    mesh_extractor.cu:248-261 + TrilinearInterpolation's index arithmetic (:28-34) + WorldToGlobalVoxel (tsdf_volume.cu:109-113),
+    and every cell is owned by exactly one voxel block whose 12-voxel tile contains all its reads."""
+    f32 = np.float32
+    l = lib()
+    for lower, upper, s in [(-1.28, 1.28, 0.01), (-1.2345, 1.3, 0.01), (0.105, 0.9, 0.01), (-5.0, 5.0, 0.01), (3.3, -0.7, 0.02)]:
+        cap = 4096
+        ints = np.zeros((cap, 5), np.int32); flts = np.zeros((cap, 4), np.float32); rng = np.zeros((cap, 2), np.int32)
+        bm = np.zeros(2, np.int32)
+        ip, fp = ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_float)
+        n = l.tdm_debug_mesh_axis_table(lower, upper, s, ints.ctypes.data_as(ip), flts.ctypes.data_as(fp), rng.ctypes.data_as(ip),
+                                        bm.ctypes.data_as(ip), cap)
+        lo, up, vs = f32(lower), f32(upper), f32(s)
+        assert n == int(f32(abs(lo - up)) / vs) and 0 < n <= cap
+        h = vs / f32(2)
+
+        def w2g(x):
+            x = f32(x)
+            sg = f32(int(x > 0) - int(x < 0))
+            return int(f32(f32(x / vs) + f32(sg * f32(0.5))))
+
+        for i in list(range(0, n, max(1, n // 97))) + [n - 1]:
+            # fp32 fma: product and sum are exact in 80-bit extended precision (12 + 24 bits, then one add), one rounding to fp32
+            pos = f32(np.longdouble(i) * np.longdouble(vs) + np.longdouble(lo))
+            cM, cP = f32(pos + (-h)), f32(pos + h)
+            exp = []
+            for c in (cM, cP):
+                pd = f32(c - h)
+                exp += [w2g(f32(pd + f32(0))), w2g(f32(pd + vs))]
+            exp.append(w2g(pos))
+            assert list(ints[i]) == exp, (lower, upper, i, list(ints[i]), exp)
+            vpM, vpP = f32(cM / vs), f32(cP / vs)
+            assert flts[i, 0] == f32(vpM - np.floor(vpM)) and flts[i, 1] == f32(vpP - np.floor(vpP))
+            assert flts[i, 2] == cM and flts[i, 3] == cP
+        # ownership: contiguous, disjoint cell ranges per block, every read inside the 12-voxel tile of the owner
+        first, nb = int(bm[0]), int(bm[1])
+        covered = 0
+        for b in range(nb):
+            a, c = int(rng[b, 0]), int(rng[b, 1])
+            if c == 0:
+                continue
+            assert a == covered
+            covered += c
+            blk = first + b
+            g = ints[a:a + c]
+            assert (g[:, 0] >> 3 == blk).all() and g.min() >= 8 * blk and g.max() < 8 * blk + 12
+        assert covered == n
