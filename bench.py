@@ -32,6 +32,23 @@ WORKLOAD = "CVA-MVSNet 640x480, 7 views, 3-stage cascade (48/32/8), view aggrega
 WEIGHTS = "abl03_view_aggregation"
 
 
+def tune_host_malloc():
+    """Keep freed result buffers inside the process.  DrMvsnet::GetResult hands every keyframe's four maps (4.9 MB) to the caller
+    in freshly allocated memory (dr_mvsnet.h:12-34: four malloc'd arrays per output, ownership transferred).  With glibc's
+    defaults such blocks are mmap'd and unmapped every time, and the kernel's page faults + zeroing for them (~0.9 ms per
+    keyframe, measured) cost about as much as the whole forward (1.2 ms).  Raising the mmap / trim thresholds - an
+    application-level allocator setting, equivalent to MALLOC_MMAP_THRESHOLD_ / MALLOC_TRIM_THRESHOLD_ in the environment -
+    lets malloc recycle them.  Applied to both arms."""
+    import ctypes
+    try:
+        libc = ctypes.CDLL("libc.so.6")
+        M_TRIM_THRESHOLD, M_MMAP_THRESHOLD = -1, -3
+        ok = libc.mallopt(M_MMAP_THRESHOLD, 1 << 30) and libc.mallopt(M_TRIM_THRESHOLD, 1 << 30)
+        return "mallopt(M_MMAP_THRESHOLD, M_TRIM_THRESHOLD) raised: freed result buffers are recycled" if ok else "mallopt refused"
+    except OSError:
+        return "libc not found: allocator defaults"
+
+
 def load_window(rank=0):
     g = np.load(os.path.join(ROOT, "tests", "golden", "sample_640x480.npz"))
     bgr = g["bgr"].copy()
@@ -202,6 +219,7 @@ def main():
     ap.add_argument("--opt", action="append", default=[], help="engine option key=int for A/B runs, e.g. --opt fork_fpn=0")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3) if a.impl == "ours" else a.warmup
+    host_malloc = tune_host_malloc()
 
     if a.impl == "reference":
         rank = int(os.environ.get("RANK", 0))
@@ -335,7 +353,8 @@ def main():
             "e2e": {"value": e2e, "unit": "keyframes/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e / a.steps, "windows_in_flight_per_gpu": a.inflight,
                     "serial_value": world * a.steps / (ms_e2e_serial / 1e3), "serial_ms_per_step": ms_e2e_serial / a.steps,
-                    "note": "CallAsync -> GetResult with host buffers; serial_* = one window at a time (latency bound)"},
+                    "note": "CallAsync -> GetResult with host buffers; serial_* = one window at a time (latency bound)",
+                    "host_malloc": host_malloc},
             "gpu_launches": launches * a.steps, "launches_per_step": launches,
             "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
         }
