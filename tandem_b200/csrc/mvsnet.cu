@@ -189,6 +189,7 @@ class MvsnetEngine final : public MvsnetIface {
     else if (key == "use_tc") use_tc_ = value != 0;
     else if (key == "use_is") use_is_ = value != 0;
     else if (key == "fork_fpn") fork_fpn_ = value != 0;
+    else if (key == "prob_direct") prob_direct_ = value != 0;
     else throw Error("unknown option " + key);
   }
 
@@ -371,6 +372,11 @@ class MvsnetEngine final : public MvsnetIface {
     if (!fc.bias.empty()) {
       TDM_CUDA(cudaMalloc(&dc.bias, fc.bias.size() * 4));
       TDM_CUDA(cudaMemcpy(dc.bias, fc.bias.data(), fc.bias.size() * 4, cudaMemcpyHostToDevice));
+    }
+    if (key.size() == 7 && key.compare(2, 5, ".prob") == 0 && key[0] == 's' && fc.w.size() == 216) {
+      TDM_CHECK(fc.cin == 8 && fc.cout == 1 && fc.kd == 3 && fc.kh == 3 && fc.kw == 3, "unexpected prob layer shape");
+      std::memcpy(prob_w_[key[1] - '1'].w, fc.w.data(), 216 * sizeof(float));   // [tap][cin][1] == [kd][kh][kw][cin]
+      have_prob_w_ = true;
     }
     if constexpr (sizeof(TA) == 2) {
       const bool vol_in = key.size() > 6 && key.compare(key.size() - 6, 6, ".conv0") == 0 && key[0] == 's';
@@ -940,6 +946,17 @@ class MvsnetEngine final : public MvsnetIface {
     const double macs = c.transposed ? (double)bi.D * bi.H * bi.W * taps * c.cin * c.cout : opos * taps * c.cin * c.cout;
     const double bytes = (double)bi.alg_bytes + (double)bo.alg_bytes + (res_mode ? (double)bufs_.at(res).alg_bytes : 0.0);
     const DevBuf* rp = res_mode ? &bufs_.at(res) : nullptr;
+    if constexpr (std::is_same<TA, __half>::value) {
+      if (prob_direct_ && have_prob_w_ && bo.f32 && c.cin == 8 && c.cout == 1 && c.kd == 3 && bi.kind == 1 && bi.pd == 1 && bi.W % 4 == 0 &&
+          wkey.size() == 7 && wkey.compare(2, 5, ".prob") == 0) {
+        rec_begin(wkey + "[direct]", bytes, 2.0 * macs);
+        const long long nthr = (long long)bi.D * bi.H * (bi.W / 4);
+        k_prob_direct<4><<<cdiv(nthr, 128), 128, 0, stream_>>>(p8<const __half>(bi), (float*)bo.p, prob_w_[wkey[1] - '1']);
+        TDM_CUDA(cudaGetLastError());
+        rec_end();
+        return;
+      }
+    }
     if (use_tc_ && c.tc_ok && res_mode != 2 && (c.tc_deconv ? (sd == 2 && sh == 2 && sw == 2) : (sd == 1 && sh == 1 && sw == 1))) {
       rec_begin(wkey + "[tc]", bytes, 2.0 * macs);
       if (conv_tc_dispatch(wkey, bi, c, rp, bo, relu)) {
@@ -1304,6 +1321,9 @@ class MvsnetEngine final : public MvsnetIface {
   int tc_smem_kb_ = 225;   // shared-memory budget of the tile planner (<= 113 lets two CTAs share an SM)
   bool use_is_ = true;   // input-stationary kernel for the 3-D stride-1 convs
   bool fused_fpn_ = false;
+  bool prob_direct_ = true;   // `prob` (8 -> 1 channels) on the FMA pipes instead of a 1/16-utilised tensor-core tile
+  bool have_prob_w_ = false;
+  ProbWeights prob_w_[3] = {};
   bool fork_fpn_ = true;      // FPN tail on a second stream / graph branch (A/B: set_option("fork_fpn", 0))
   cudaStream_t side_stream_ = nullptr;
   cudaEvent_t ev_fork_ = nullptr, ev_join_ = nullptr;

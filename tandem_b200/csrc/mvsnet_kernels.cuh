@@ -183,6 +183,69 @@ k_conv_direct(const P8<const TIn> in, const float* __restrict__ wgt /*[taps][CIN
 }
 
 // ------------------------------------------------------------------------------------------------
+// a7 tail: the `prob` layer (Conv3d 8 -> 1, 3x3x3, no bias / BN, module.py:577-600) as a direct fp32 convolution.
+// With one output channel a tensor-core tile spends 15 of its 16 N columns on padding while streaming the same A operand,
+// so this layer is cheaper on the FMA pipes: one thread owns PX consecutive outputs of a row, loads the PX+2 input vectors
+// (8 fp16 channels = 16 B each) of each of the 9 (kd, kh) rows once with 128-bit loads (zero halos: no bounds tests), and
+// multiplies them with weights that arrive as a __grid_constant__ kernel parameter, i.e. as constant-bank operands of the
+// FFMAs (no weight loads at all).  fp32 accumulation with the fp32 BN-free weights of the checkpoint.
+// ------------------------------------------------------------------------------------------------
+struct ProbWeights {
+  float w[27 * 8];   // [kd][kh][kw][cin]
+};
+
+template <int PX>
+__global__ void __launch_bounds__(128)
+k_prob_direct(P8<const __half> in, float* __restrict__ logits /*[D][H][W]*/, const __grid_constant__ ProbWeights Wt) {
+  const int S = in.W / PX;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int s = idx % S;
+  const int t = idx / S;
+  const int h = t % in.H, d = t / in.H;
+  if (d >= in.D) return;
+  float acc[PX];
+#pragma unroll
+  for (int i = 0; i < PX; ++i) acc[i] = 0.f;
+  // element offset of (d-1, h-1, w0-1); every tap row is a constant shift from it
+  const unsigned base = (unsigned)((((d + in.pd - 1) * in.Hp + h) * in.Wp + s * PX) * 8);
+  const unsigned plane = (unsigned)(in.Hp * in.Wp * 8), row = (unsigned)(in.Wp * 8);
+#pragma unroll
+  for (int kd = 0; kd < 3; ++kd) {
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh) {
+      const uint4* rp = reinterpret_cast<const uint4*>(in.p + base + kd * plane + kh * row);
+      float x[PX + 2][8];
+#pragma unroll
+      for (int q = 0; q < PX + 2; ++q) {
+        const uint4 v = __ldg(rp + q);
+        const __half2* hv = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 f = __half22float2(hv[j]);
+          x[q][2 * j] = f.x;
+          x[q][2 * j + 1] = f.y;
+        }
+      }
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw)
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const float wv = Wt.w[((kd * 3 + kh) * 3 + kw) * 8 + c];
+#pragma unroll
+          for (int i = 0; i < PX; ++i) acc[i] = fmaf(x[i + kw][c], wv, acc[i]);
+        }
+    }
+  }
+  float* op = logits + ((size_t)d * in.H + h) * in.W + s * PX;
+  if constexpr (PX == 4) {
+    *reinterpret_cast<float4*>(op) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+  } else {
+#pragma unroll
+    for (int i = 0; i < PX; ++i) op[i] = acc[i];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // a3/a4: depth hypotheses.  Stage 1: d_j = dmin + interval*j.  Later stages: per-pixel dmin map from
 // the bilinear (align_corners=False) x2 up-sampling of the previous stage's dense depth.
 // ------------------------------------------------------------------------------------------------

@@ -186,6 +186,28 @@ def test_tcgen05_convs_match_direct_kernels(golden_small, weights):
     assert _absrel(od.depth_dense, ot.depth_dense) < 4e-4
 
 
+@pytest.mark.parametrize("weights", ["abl03_view_aggregation", "abl04_fewer_depth_planes"])
+def test_prob_direct_kernel_matches_tensor_core_prob(golden_small, weights):
+    """The `prob` layer (8 -> 1 channels) on the FMA pipes (k_prob_direct, fp32 weights, fp32 accumulate) against the tcgen05
+    path (hi/lo 16-bit weights) on the same fp16 input: the stage-1 logits see identical inputs, later stages identical
+    kernels upstream but hypotheses that depend on the previous stage's depth; and the fork of the FPN tail changes nothing."""
+    ma, oa = _run_opts(golden_small, weights, "mixed16", prob_direct=0, fork_fpn=0)
+    mb, ob = _run_opts(golden_small, weights, "mixed16", prob_direct=1, fork_fpn=1)
+    names = [r[0] for r in mb.profile()]
+    assert sum(n.endswith("prob[direct]") for n in names) == 3, names
+    assert np.array_equal(ma.debug_tensor("s1.x11"), mb.debug_tensor("s1.x11")), "inputs of the stage-1 prob layer differ"
+    la, lb = ma.debug_tensor("s1.logits"), mb.debug_tensor("s1.logits")
+    scale = float(np.abs(la).max())
+    e = np.abs(la - lb)
+    print(f"s1.logits: max|d| {e.max():.3e} mean|d| {e.mean():.3e} (scale {scale:.3e})")
+    assert e.max() <= 2e-3 * scale and e.mean() <= 2e-4 * scale
+    for s in (2, 3):
+        e = np.abs(ma.debug_tensor(f"s{s}.logits") - mb.debug_tensor(f"s{s}.logits"))
+        assert np.quantile(e, 0.999) <= 2e-2 * scale, s
+    assert _absrel(oa.depth_dense, ob.depth_dense) < 1e-4
+    assert np.mean(np.abs(oa.confidence_dense - ob.confidence_dense)) < 1e-3
+
+
 def test_tcgen05_benchmark_config_abs_rel(golden_full):
     g = golden_full
     m, out = _run_opts(g, "abl03_view_aggregation", "mixed16", use_tc=1)
