@@ -1321,7 +1321,7 @@ class MvsnetEngine final : public MvsnetIface {
   int tc_smem_kb_ = 225;   // shared-memory budget of the tile planner (<= 113 lets two CTAs share an SM)
   bool use_is_ = true;   // input-stationary kernel for the 3-D stride-1 convs
   bool fused_fpn_ = false;
-  bool prob_direct_ = true;   // `prob` (8 -> 1 channels) on the FMA pipes instead of a 1/16-utilised tensor-core tile
+  bool prob_direct_ = false;  // `prob` (8 -> 1 channels) on the FMA pipes (k_prob_direct): measured SLOWER than the 1/16-utilised tensor-core tile (0.181 vs 0.143 ms over the three stages, 812 vs 850 keyframes/s); kept as an A/B option
   bool have_prob_w_ = false;
   ProbWeights prob_w_[3] = {};
   bool fork_fpn_ = true;      // FPN tail on a second stream / graph branch (A/B: set_option("fork_fpn", 0))

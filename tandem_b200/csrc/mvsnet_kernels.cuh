@@ -189,6 +189,9 @@ k_conv_direct(const P8<const TIn> in, const float* __restrict__ wgt /*[taps][CIN
 // (8 fp16 channels = 16 B each) of each of the 9 (kd, kh) rows once with 128-bit loads (zero halos: no bounds tests), and
 // multiplies them with weights that arrive as a __grid_constant__ kernel parameter, i.e. as constant-bank operands of the
 // FFMAs (no weight loads at all).  fp32 accumulation with the fp32 BN-free weights of the checkpoint.
+// MEASURED on B200 (round 1): 0.035 / 0.072 / 0.074 ms for the three stages against 0.027 / 0.052 / 0.064 ms of the tcgen05
+// kernel, logits equal to 8e-5 (scale 1e2) - the 864 FFMA + 432 conversions per thread do not beat the tensor-core tile even
+// at 1/16 utilisation, so this kernel is OFF by default (set_option("prob_direct", 1)) and serves as an independent check.
 // ------------------------------------------------------------------------------------------------
 struct ProbWeights {
   float w[27 * 8];   // [kd][kh][kw][cin]
