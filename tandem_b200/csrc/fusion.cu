@@ -844,10 +844,11 @@ class FusionImpl final : public FusionIface {
       empty = empty || A[a].cells.empty();
       bytes += A[a].cells.size() * sizeof(MeshAxisCell) + A[a].ranges.size() * sizeof(int2) + 64;
     }
+    TDM_CHECK(d_.slab_lo == INT_MIN && d_.slab_hi == INT_MAX,
+              "mesh extraction of a Z-slab-partitioned volume is not supported (cells at slab faces would be emitted by two ranks)");
     mesh_empty_ = empty;
-    mesh_pending_ = true;
     *h_mesh_total_ = 0;
-    if (empty) return;
+    if (empty) { mesh_pending_ = true; return; }
     if (bytes > mesh_tables_cap_) {
       cudaFree(d_mesh_tables_);
       d_mesh_tables_ = nullptr;
@@ -883,6 +884,7 @@ class FusionImpl final : public FusionIface {
     launch_mesh_emit();
     TDM_CUDA(cudaMemcpyAsync(h_mesh_total_, d_mesh_total_, sizeof(int), cudaMemcpyDeviceToHost, stream_));
     TDM_CUDA(cudaEventRecord(ev_mesh1_, stream_));
+    mesh_pending_ = true;   // only once everything is enqueued: a failed call leaves no half-started extraction behind
   }
 
   // GetMeshSync, tsdf_volume.cu:781-839: vertices as xyz triples, colours as rgb triples, 3 per triangle
