@@ -201,3 +201,35 @@ def test_mesh_oracle_properties():
     # an empty / inverted-size box gives nothing; zero-extent axis gives nothing
     assert len(o.extract_mesh(lo, np.float32([lo[0], up[1], up[2]]))[0]) == 0
     assert len(o.extract_mesh(np.float32([3, 3, 3]), np.float32([3.5, 3.5, 3.5]))[0]) == 0
+
+
+def test_marching_cubes_tables_are_consistent():
+    """The committed nibble-packed case tables (product copy and oracle copy) are identical and internally consistent: the
+    edges a case triangulates are exactly the edges whose two corners lie on different sides (so the crossed-edge mask the
+    reference stores as `edgeTable` is implied), complementary cases use the same edges, at most five triangles per case."""
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+    def load(path):
+        words = re.findall(r"0x([0-9a-f]{16})ull", open(path).read())
+        assert len(words) == 256, path
+        return [int(w, 16) for w in words]
+
+    a = load(os.path.join(root, "tandem_b200", "csrc", "mc_tables.h"))
+    b = load(os.path.join(root, "oracle", "mc_tables.h"))
+    assert a == b
+    ends = [(0, 1), (1, 2), (2, 3), (3, 0), (4, 5), (5, 6), (6, 7), (7, 4), (0, 4), (1, 5), (2, 6), (3, 7)]
+    masks = []
+    for case, w in enumerate(a):
+        nib = [(w >> (4 * k)) & 0xF for k in range(16)]
+        n = nib.index(0xF)
+        assert n % 3 == 0 and n <= 15 and all(x == 0xF for x in nib[n:]) and all(x < 12 for x in nib[:n])
+        used = 0
+        for e in nib[:n]:
+            used |= 1 << e
+        topo = sum(1 << e for e, (p, q) in enumerate(ends) if ((case >> p) & 1) != ((case >> q) & 1))
+        assert used == topo, case
+        for t in range(0, n, 3):
+            assert len({nib[t], nib[t + 1], nib[t + 2]}) == 3, case       # no degenerate triangle in the table
+        masks.append(used)
+    assert all(masks[c] == masks[255 - c] for c in range(256)) and masks[0] == 0 and masks[255] == 0
