@@ -7,7 +7,7 @@
  *   calcG     cuda_coarse_tracker_private.cu:261-394, host scaling cuda_coarse_tracker.cpp:277-356,
  *             CPU twin CoarseTracker.cpp:378-481
  *   affLL     cuda_coarse_tracker.cpp:42-52 ; bilinear (I,dx,dy) fetch cuda_coarse_tracker_private.cu:22-38
- * PARITY UNPINNED: the only tracker golden in the reference (main.cu:185-189) needs cct_data/*.npy inputs
+ * PARITY UNPINNED: the only tracker golden in the reference (main.cu:185-189) needs the cct_data .npy dumps as inputs
  * that are not shipped, and neither the host wrapper (Eigen, Sophus, cnpy) nor CoarseTracker.cpp (Eigen)
  * compiles in the build container.  Per-point arithmetic is fp32 as in the kernels; the reductions are done
  * in double here (the reference uses fp32 block reductions + float atomics, which are run-to-run
