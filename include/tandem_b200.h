@@ -84,6 +84,12 @@ int tdm_mvsnet_run_resident(tdm_mvsnet* h, int iters, float* ms_total, int* laun
 /* Same clock over n handles of one device: iters_total forwards issued round-robin, each handle on its own stream (the
  * windows are independent, so their kernels may overlap on the GPU); ms_total spans first launch .. last completion. */
 int tdm_mvsnet_run_resident_multi(tdm_mvsnet* const* hs, int n, int iters_total, float* ms_total, int* launches);
+/* Host-only introspection (no GPU needed): the tile plan the tcgen05 convolution planner picks for a layer - cin, N columns of
+ * the MMA (npad, doubled for hi/lo weights), kd (1: 2-D over planes, 3: 3-D, 2: transposed-as-GEMM), the grid D x H x W the
+ * tiles live on, pd (D halo), mode (0 stride-1, 1 transposed, 3 up2, 4 input-stationary), shared-memory budget in KB.
+ * out12 = {ring slots, tile rows, tile cols, pitch, planes per tile, 128-row chunks per plane, slot positions, tiles_w,
+ * tiles_h, tiles_d, grid, shared-memory bytes}. */
+int tdm_debug_conv_plan(int cin, int npad, int kd, int D, int H, int W, int pd, int mode, int smem_kb, long long* out12);
 /* Per-kernel CUDA-event timing of one resident forward: writes lines "name ms algorithmic_bytes flops\n"
  * into buf (NUL terminated). Returns bytes written or <0. */
 long long tdm_mvsnet_profile(tdm_mvsnet* h, char* buf, size_t capacity);

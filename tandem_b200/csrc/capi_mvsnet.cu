@@ -27,6 +27,14 @@ int tdm_device_count(void) {
   return n;
 }
 
+int tdm_debug_conv_plan(int cin, int npad, int kd, int D, int H, int W, int pd, int mode, int smem_kb, long long* out12) {
+  TDM_API_BEGIN
+  TDM_CHECK(out12 && cin >= 8 && npad >= 8 && (kd == 1 || kd == 2 || kd == 3) && D > 0 && H > 0 && W > 0, "bad argument");
+  tdm::debug_conv_plan(cin, npad, kd, D, H, W, pd, mode, smem_kb, out12);
+  return TDM_OK;
+  TDM_API_END
+}
+
 int tdm_mvsnet_create(const char* weights_path, int precision, int device, tdm_mvsnet** out) {
   TDM_API_BEGIN
   TDM_CHECK(weights_path && out, "null argument");

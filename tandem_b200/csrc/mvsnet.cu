@@ -1354,4 +1354,14 @@ MvsnetIface* make_mvsnet(const std::string& path, int precision, int device) {
   throw Error("unknown precision");
 }
 
+
+// host-only view of the tcgen05 tile planner (no GPU involved; used by the CPU test-suite): out12 = {S, R, TW, P, DR, nch,
+// slot_pos, tiles_w, tiles_h, tiles_d, grid, smem_bytes}
+void debug_conv_plan(int cin, int npad, int kd, int D, int H, int W, int pd, int mode, int smem_kb, long long* out12) {
+  const tc::Plan p = tc::make_plan(cin, npad, kd, D, H, W, pd, mode, (size_t)smem_kb * 1024);
+  const tc::Geom& g = p.g;
+  const long long v[12] = {g.S, g.R, g.TW, g.P, g.DR, g.nch, g.slot_pos, g.tiles_w, g.tiles_h, g.tiles_d, p.grid, (long long)p.smem};
+  for (int i = 0; i < 12; ++i) out12[i] = v[i];
+}
+
 }  // namespace tdm

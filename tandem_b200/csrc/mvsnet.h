@@ -25,5 +25,6 @@ class MvsnetIface {
 };
 
 MvsnetIface* make_mvsnet(const std::string& weights_path, int precision, int device);
+void debug_conv_plan(int cin, int npad, int kd, int D, int H, int W, int pd, int mode, int smem_kb, long long* out12);
 
 }  // namespace tdm

@@ -102,3 +102,39 @@ def test_mesh_axis_tables_match_a_float32_restatement():
             g = ints[a:a + c]
             assert (g[:, 0] >> 3 == blk).all() and g.min() >= 8 * blk and g.max() < 8 * blk + 12
         assert covered == n
+
+
+def test_tcgen05_tile_planner_invariants():
+    """Host logic of the tensor-core convolutions (no GPU): for every layer shape of the benchmark config (640x480, 7 views,
+    (48,32,8)) and of the small config-1 windows the planner returns a tiling that covers the grid, fits 225 KB of shared
+    memory, 512 TMEM columns and the TMA box limit."""
+    l = lib()
+    out = (ctypes.c_longlong * 12)()
+    shapes = []
+    for (H, W, V, Ds) in [(480, 640, 7, (48, 32, 8)), (256, 320, 4, (32, 32, 8)), (96, 128, 2, (32, 8, 8))]:
+        # FeatureNet: 2-D convs over V planes (kd = 1, pd = 0)
+        for cin, npad, sc in [(8, 32, 1), (16, 32, 2), (32, 64, 4), (32, 32, 2), (32, 32, 1)]:
+            shapes.append((cin, npad, 1, V, H // sc, W // sc, 0, 0))
+        for s, D in enumerate(Ds):
+            sc = 4 >> s
+            h, w = H // sc, W // sc
+            c0 = (32, 16, 8)[s]
+            shapes.append((c0, 48, 3, D, h, w, 1, 4))                       # conv0, input-stationary, hi/lo, 3 kd
+            shapes.append((8, 48, 3, D, h, w, 1, 4))                        # prob
+            for lvl, (cin, npad) in enumerate([(16, 32), (32, 32), (64, 32)]):
+                d2, h2, w2 = max(D >> (lvl + 1), 1), h >> (lvl + 1), w >> (lvl + 1)
+                shapes.append((cin, npad, 3, d2, h2, w2, 1, 0))             # conv2 / conv4 / conv6
+            for lvl, (cin, npad) in enumerate([(16, 64), (32, 128), (64, 64)]):
+                d2, h2, w2 = max(D >> (lvl + 1), 1), h >> (lvl + 1), w >> (lvl + 1)
+                shapes.append((cin, npad, 2, d2, h2, w2, 1, 1))             # conv11 / conv9 / conv7 (transposed as GEMM)
+    assert len(shapes) > 40
+    for (cin, npad, kd, D, H, W, pd, mode) in shapes:
+        rc = l.tdm_debug_conv_plan(cin, npad, kd, D, H, W, pd, mode, 225, out)
+        assert rc == 0, (cin, npad, kd, D, H, W, mode, l.tdm_last_error())
+        S, R, TW, P, DR, nch, slot_pos, tw, th, td, grid, smem = [int(x) for x in out]
+        key = (cin, npad, kd, D, H, W, mode)
+        assert P == TW + 2 and P <= 256 and R >= 1 and DR >= 1 and 2 <= S <= 4, key
+        assert tw * TW >= W and (tw - 1) * TW < W and th * R >= H and (th - 1) * R < H and td * DR >= D and (td - 1) * DR < D, key
+        assert grid == tw * th * td and grid >= 1, key
+        assert nch == (R * P + 127) // 128 and (4 if mode == 4 else 2) * nch * npad <= 512, key      # TMEM columns
+        assert smem <= 225 * 1024 and slot_pos % 8 == 0 and slot_pos >= (R + 2) * P, key
