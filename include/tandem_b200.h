@@ -84,6 +84,11 @@ int tdm_mvsnet_run_resident(tdm_mvsnet* h, int iters, float* ms_total, int* laun
 /* Same clock over n handles of one device: iters_total forwards issued round-robin, each handle on its own stream (the
  * windows are independent, so their kernels may overlap on the GPU); ms_total spans first launch .. last completion. */
 int tdm_mvsnet_run_resident_multi(tdm_mvsnet* const* hs, int n, int iters_total, float* ms_total, int* launches);
+/* Host-only introspection (no GPU needed): the plane-sweep homography of one source view as the cost-volume kernel receives it
+ * (homo_warping, cva_mvsnet/models/module.py:795-808): M = K [R|t]_src^-1 (K [R|t]_ref^-1)^-1, rot = M[:3,:3], trans = M[:3,3];
+ * a reference pixel (x, y) at depth d lands at rot (x, y, 1)^T d + trans in the source image. K row-major 3x3, poses row-major
+ * 4x4 cam->world. */
+int tdm_debug_homography(const float* K3x3, const float* c2w_ref, const float* c2w_src, float* rot9, float* trans3);
 /* Host-only introspection (no GPU needed): the tile plan the tcgen05 convolution planner picks for a layer - cin, N columns of
  * the MMA (npad, doubled for hi/lo weights), kd (1: 2-D over planes, 3: 3-D, 2: transposed-as-GEMM), the grid D x H x W the
  * tiles live on, pd (D halo), mode (0 stride-1, 1 transposed, 3 up2, 4 input-stationary), shared-memory budget in KB.

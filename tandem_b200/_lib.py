@@ -74,6 +74,7 @@ def _declare(l):
         "tdm_mvsnet_debug_tensor": (c.c_longlong, [vp, cp, fp, c.c_size_t, ip]),
         "tdm_mvsnet_run_resident": (i, [vp, i, fp, ip]),
         "tdm_mvsnet_run_resident_multi": (i, [P(vp), i, i, fp, ip]),
+        "tdm_debug_homography": (i, [fp, fp, fp, fp, fp]),
         "tdm_debug_conv_plan": (i, [i, i, i, i, i, i, i, i, i, P(c.c_longlong)]),
         "tdm_mvsnet_profile": (c.c_longlong, [vp, cp, c.c_size_t]),
         "tdm_fusion_create": (i, [P(FusionOptions), i, P(vp)]),

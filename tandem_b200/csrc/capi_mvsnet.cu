@@ -27,6 +27,14 @@ int tdm_device_count(void) {
   return n;
 }
 
+int tdm_debug_homography(const float* K3x3, const float* c2w_ref, const float* c2w_src, float* rot9, float* trans3) {
+  TDM_API_BEGIN
+  TDM_CHECK(K3x3 && c2w_ref && c2w_src && rot9 && trans3, "null argument");
+  tdm::debug_homography(K3x3, c2w_ref, c2w_src, rot9, trans3);
+  return TDM_OK;
+  TDM_API_END
+}
+
 int tdm_debug_conv_plan(int cin, int npad, int kd, int D, int H, int W, int pd, int mode, int smem_kb, long long* out12) {
   TDM_API_BEGIN
   TDM_CHECK(out12 && cin >= 8 && npad >= 8 && (kd == 1 || kd == 2 || kd == 3) && D > 0 && H > 0 && W > 0, "bad argument");

@@ -1355,6 +1355,19 @@ MvsnetIface* make_mvsnet(const std::string& path, int precision, int device) {
 }
 
 
+// host-only: the plane-sweep homography of one source view exactly as fill_cv_params computes it (module.py:795-808)
+void debug_homography(const float* K3x3, const float* c2w_ref, const float* c2w_src, float* rot9, float* trans3) {
+  double Pr[16], Pri[16], Ps[16], M[16];
+  world_to_pixel(K3x3, c2w_ref, Pr);
+  if (!mat4_inv(Pr, Pri)) throw Error("reference projection is singular");
+  world_to_pixel(K3x3, c2w_src, Ps);
+  mat4_mul(Ps, Pri, M);
+  for (int i = 0; i < 3; ++i) {
+    for (int j = 0; j < 3; ++j) rot9[i * 3 + j] = (float)M[i * 4 + j];
+    trans3[i] = (float)M[i * 4 + 3];
+  }
+}
+
 // host-only view of the tcgen05 tile planner (no GPU involved; used by the CPU test-suite): out12 = {S, R, TW, P, DR, nch,
 // slot_pos, tiles_w, tiles_h, tiles_d, grid, smem_bytes}
 void debug_conv_plan(int cin, int npad, int kd, int D, int H, int W, int pd, int mode, int smem_kb, long long* out12) {

@@ -233,3 +233,34 @@ def test_marching_cubes_tables_are_consistent():
             assert len({nib[t], nib[t + 1], nib[t + 2]}) == 3, case       # no degenerate triangle in the table
         masks.append(used)
     assert all(masks[c] == masks[255 - c] for c in range(256)) and masks[0] == 0 and masks[255] == 0
+
+
+def test_host_homography_matches_oracle_and_reference_formula(golden_full):
+    """Host logic of the cost-volume path (no GPU): the per-view homography the library uploads (double precision on the host,
+    rounded to fp32) against the oracle's fp32 restatement of homo_warping (module.py:795-808) on the golden window's poses
+    and intrinsics - they must agree to fp32 noise, and projecting a point through the homography must equal projecting it
+    through the two cameras."""
+    import ctypes
+    from tandem_b200._lib import lib
+    g = golden_full
+    fp = ctypes.POINTER(ctypes.c_float)
+    V = g["c2w"].shape[0]
+    order = [int(g["ref_index"])] + [v for v in range(V) if v != int(g["ref_index"])]
+    for s in (1, 2, 3):
+        K = np.ascontiguousarray(g[f"K{s}"], np.float32)
+        ref = np.ascontiguousarray(g["c2w"][order[0]], np.float32)
+        for v in order[1:]:
+            src = np.ascontiguousarray(g["c2w"][v], np.float32)
+            rot = np.zeros(9, np.float32); tr = np.zeros(3, np.float32)
+            assert lib().tdm_debug_homography(K.ctypes.data_as(fp), ref.ctypes.data_as(fp), src.ctypes.data_as(fp),
+                                              rot.ctypes.data_as(fp), tr.ctypes.data_as(fp)) == 0
+            M = O.homography(torch.from_numpy(K), torch.from_numpy(ref), torch.from_numpy(K), torch.from_numpy(src)).numpy()
+            assert np.abs(rot.reshape(3, 3) - M[:3, :3]).max() < 2e-4 * max(1.0, np.abs(M[:3, :3]).max())
+            assert np.abs(tr - M[:3, 3]).max() < 2e-3 * max(1.0, np.abs(M[:3, 3]).max())
+            # geometric meaning, in double: a reference pixel at depth d, lifted to the world and projected into the source
+            Kd, Rd, Sd = K.astype(np.float64), ref.astype(np.float64), src.astype(np.float64)
+            x, y, d = 37.0, 21.0, 1.7
+            Xw = Rd @ np.append(np.linalg.inv(Kd) @ np.array([x, y, 1.0]) * d, 1.0)
+            q = Kd @ (np.linalg.inv(Sd) @ Xw)[:3]
+            qh = rot.reshape(3, 3).astype(np.float64) @ np.array([x, y, 1.0]) * d + tr.astype(np.float64)
+            assert np.abs(q - qh).max() < 1e-3 * max(1.0, np.abs(q).max())
