@@ -202,3 +202,56 @@ class FrontOracle:
             None if id0 is None else id0.ctypes.data_as(_fp), rg.ctypes.data_as(_fp), arrs[0].ctypes.data_as(_fp),
             arrs[1].ctypes.data_as(_fp), arrs[2].ctypes.data_as(_fp), arrs[3].ctypes.data_as(_fp), proj.ctypes.data_as(_fp))
         return n, [a[:n + 1] for a in arrs], proj.reshape(h, w)
+
+
+class FrontRef:
+    """oracle/_ref/libfront_ref.so: the REFERENCE's own makeImages / setCoarseTrackingRef bodies (HessianBlocks.cpp:128-191,
+    CoarseTracker.cpp:655-725) compiled from where they lie by oracle/ref_build.mk (build container only). Pins FrontOracle."""
+
+    PATH = os.path.join(_HERE, "_ref", "libfront_ref.so")
+
+    @classmethod
+    def available(cls):
+        return os.path.exists(cls.PATH)
+
+    def __init__(self):
+        self._l = ctypes.CDLL(self.PATH)
+        self._l.ref_front_make_images.restype = ctypes.c_int
+        self._l.ref_front_dense_reference.restype = ctypes.c_int
+
+    def make_images(self, gray, levels):
+        g = np.ascontiguousarray(gray, np.float32)
+        h, w = g.shape
+        tot = sum((w >> l) * (h >> l) for l in range(levels))
+        dI = np.zeros(3 * tot, np.float32)
+        ag = np.zeros(tot, np.float32)
+        rc = self._l.ref_front_make_images(g.ctypes.data_as(_fp), w, h, levels, dI.ctypes.data_as(_fp), ag.ctypes.data_as(_fp))
+        assert rc == 0
+        out, off = [], 0
+        for l in range(levels):
+            wl, hl = w >> l, h >> l
+            out.append((dI[3 * off:3 * (off + wl * hl)].reshape(hl, wl, 3), ag[off:off + wl * hl].reshape(hl, wl)))
+            off += wl * hl
+        return out
+
+    def dense_reference(self, depth, c2w_depth, c2w_ref, K4, step, dense_only, sparse, idepth0, ref_gray):
+        """Same contract as FrontOracle.dense_reference, but takes the two camera poses (the reference derives
+        T_dense_depth_to_last itself, CoarseTracker.cpp:673); also returns that transform (4x4 double)."""
+        d = np.ascontiguousarray(depth, np.float32)
+        h, w = d.shape
+        nb = 0 if sparse is None else len(sparse[0]) - 1
+        arrs = [np.zeros(nb + 1 + w * h, np.float32) for _ in range(4)]
+        if sparse is not None:
+            for a, s in zip(arrs, sparse):
+                a[:nb + 1] = s
+        id0 = None if idepth0 is None else np.ascontiguousarray(idepth0, np.float32)
+        rg = np.ascontiguousarray(ref_gray, np.float32)
+        cd = np.ascontiguousarray(c2w_depth, np.float32)
+        cr = np.ascontiguousarray(c2w_ref, np.float64)
+        T = np.zeros(16, np.float64)
+        n = self._l.ref_front_dense_reference(
+            d.ctypes.data_as(_fp), w, h, int(step), cd.ctypes.data_as(_fp), cr.ctypes.data_as(_dp), ctypes.c_float(K4[0]),
+            ctypes.c_float(K4[1]), ctypes.c_float(K4[2]), ctypes.c_float(K4[3]), int(bool(dense_only)), nb,
+            None if id0 is None else id0.ctypes.data_as(_fp), rg.ctypes.data_as(_fp), arrs[0].ctypes.data_as(_fp),
+            arrs[1].ctypes.data_as(_fp), arrs[2].ctypes.data_as(_fp), arrs[3].ctypes.data_as(_fp), T.ctypes.data_as(_dp))
+        return n, [a[:n + 1] for a in arrs], T.reshape(4, 4)

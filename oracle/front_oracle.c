@@ -10,9 +10,14 @@
  *                    (forward-warp of the rendered dense depth into the reference keyframe with a nearest-depth
  *                    test, then raster-order append behind the sparse points, INCLUDING the pre-increment quirk of
  *                    :717-722: slot n_before keeps its stale content and the last appended point is not counted)
- * PARITY UNPINNED: the reference ships no test or golden for either function and CoarseTracker.cpp /
- * HessianBlocks.cpp need Eigen + Sophus, which are absent from the build container.  Both functions are a few lines
- * of fp32 arithmetic, restated operation by operation.  Deliberate, documented deviations:
+ * PINNED (round 2): the reference ships no test or golden for either function and CoarseTracker.cpp / HessianBlocks.cpp
+ * as a whole need Eigen + Sophus (absent from the build container), but the two function BODIES only touch Eigen as
+ * 3-vectors / 3x3 matrices.  oracle/ref_build.mk cuts them out of the files where they lie (HessianBlocks.cpp:128-191,
+ * CoarseTracker.cpp:655-725) and compiles them, unmodified, against a stand-in Eigen (tests/cpp/eigen_stub) and the harness
+ * oracle/ref_wrap_front.cpp into oracle/_ref/libfront_ref.so; tests/test_oracle_cpu.py::test_front_oracle_*_pinned_* compare
+ * this restatement with that library bit for bit (pyramid incl. a non-finite pixel; pc_n and all four point arrays for
+ * steps 1-3, with and without sparse points, up to 640x480).  Without /root/reference (fresh clone) those tests skip and
+ * the oracle is "parity unpinned".  Deliberate, documented deviations:
  *   * rows 0 and h-1 of (dx, dy, absSquaredGrad) are uninitialised memory in the reference (`new Eigen::Vector3f[]`);
  *     here they are 0.  The tracker never reads them (2 < Kv < h-3).
  *   * a warped depth <= 0 (point behind the reference camera) is ignored; in the reference its effect depends on the

@@ -22,3 +22,18 @@ $(OUT)/libtracker_ref.so: ref_wrap_tracker.cu
 	@mkdir -p $(OUT)
 	$(NVCC) -O2 -std=c++17 $(ARCH) -Xcompiler -fPIC -w -Iref_shim -I$(TRK)/include/private -shared -cudart static \
 	    -o $@ $(TRK)/src/cuda_coarse_tracker_private.cu ref_wrap_tracker.cu
+
+# n1 / n2 pins: two function bodies of tandem/src/FullSystem, cut out of the files where they lie (line ranges
+# as cited in oracle/front_oracle.c) into _ref/gen/ (build output, git-ignored - nothing is copied into the repo) and
+# compiled, unmodified, against the stand-in Eigen of tests/cpp/eigen_stub and the harness ref_wrap_front.cpp.  CPU only.
+FS := /root/reference/tandem/src/FullSystem
+CXX ?= g++
+all: $(OUT)/libfront_ref.so
+$(OUT)/gen/make_images.inc: $(FS)/HessianBlocks.cpp
+	@mkdir -p $(OUT)/gen
+	sed -n '128,191p' $< > $@
+$(OUT)/gen/dense_ref.inc: $(FS)/CoarseTracker.cpp
+	@mkdir -p $(OUT)/gen
+	sed -n '655,725p' $< > $@
+$(OUT)/libfront_ref.so: ref_wrap_front.cpp $(OUT)/gen/make_images.inc $(OUT)/gen/dense_ref.inc ../tests/cpp/eigen_stub/Eigen/Dense
+	$(CXX) -O2 -std=c++14 -fPIC -shared -ffp-contract=off -fno-fast-math -w -I. -I../tests/cpp/eigen_stub -o $@ ref_wrap_front.cpp

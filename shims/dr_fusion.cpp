@@ -19,7 +19,7 @@ DrFusion::DrFusion(struct DrFusionOptions const& o) {
   static_assert(sizeof(DrFusionOptions) == sizeof(tdm_fusion_options), "DrFusionOptions must match tdm_fusion_options");
   tdm_fusion_options t;
   std::memcpy(&t, &o, sizeof(t));
-  if (tdm_fusion_create(&t, 0, &handle_) != TDM_OK) die("DrFusion::DrFusion");
+  if (tdm_fusion_create(&t, getenv("TDM_DEVICE") ? atoi(getenv("TDM_DEVICE")) : 0, &handle_)   /* TDM_DEVICE: CUDA ordinal, default 0 */ != TDM_OK) die("DrFusion::DrFusion");
   dr_mesh_vert = (float*)malloc(sizeof(float) * dr_mesh_num_max * 3);  // dr_fusion.cpp:36-37
   dr_mesh_cols = (float*)malloc(sizeof(float) * dr_mesh_num_max * 3);
 }

@@ -6,6 +6,7 @@
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <fstream>
 #include <iostream>
@@ -24,9 +25,25 @@ static void die(const char* where) {
   exit(EXIT_FAILURE);
 }
 
+// The reference constructor has no precision / device argument (dr_mvsnet.h:38), so the two choices a deployment may want
+// come from the environment: TDM_PRECISION = mixed16 (default; benchmark precision) | fp32 (parity engine, Abs Rel 2e-6 vs
+// the reference's fp32 model) | bf16, and TDM_DEVICE = CUDA ordinal (default 0).  Documented in INTEGRATION.md.
+static int env_precision() {
+  const char* p = getenv("TDM_PRECISION");
+  if (!p || !*p || !strcmp(p, "mixed16")) return TDM_PRECISION_MIXED16;
+  if (!strcmp(p, "fp32")) return TDM_PRECISION_FP32;
+  if (!strcmp(p, "bf16")) return TDM_PRECISION_BF16;
+  std::cerr << "ERROR: DrMvsnet: TDM_PRECISION must be mixed16, fp32 or bf16 (got '" << p << "')" << std::endl;
+  exit(EXIT_FAILURE);
+}
+static int env_device() {
+  const char* d = getenv("TDM_DEVICE");
+  return d && *d ? atoi(d) : 0;
+}
+
 DrMvsnet::DrMvsnet(char const* filename) {
   impl = new DrMvsnetImpl();
-  if (tdm_mvsnet_create(filename, TDM_PRECISION_MIXED16, 0, &impl->h) != TDM_OK) die("DrMvsnet::DrMvsnet");
+  if (tdm_mvsnet_create(filename, env_precision(), env_device(), &impl->h) != TDM_OK) die("DrMvsnet::DrMvsnet");
 }
 
 DrMvsnet::~DrMvsnet() {

@@ -61,8 +61,7 @@ long long tdm_fusion_extract_mesh(tdm_fusion* h, const float lower[3], const flo
                                   size_t max_vertices) {
   TDM_API_BEGIN
   TDM_CHECK(h && lower && upper, "null argument");
-  if (!h->impl->mesh_pending()) h->impl->extract_mesh_async(lower, upper, false);
-  return h->impl->get_mesh(vert, cols, max_vertices, false, /*query_only=*/vert == nullptr && cols == nullptr);
+  return h->impl->extract_mesh_blocking(lower, upper, vert, cols, max_vertices);
   TDM_API_END
 }
 int tdm_fusion_extract_mesh_async(tdm_fusion* h, const float lower[3], const float upper[3]) {

@@ -750,6 +750,7 @@ class FusionImpl final : public FusionIface {
     launch_integrate();
     TDM_CUDA(cudaEventRecord(ev_int_, stream_));
     have_scan_ = true;
+    ++volume_epoch_;   // a pending mesh extracted before this scan no longer describes the volume
     next_ = d_.o.num_render_streams > 0 ? kRender : kRender;
   }
 
@@ -824,99 +825,39 @@ class FusionImpl final : public FusionIface {
   void extract_mesh_async(const float* lower, const float* upper, bool check_order) override {
     if (check_order && next_ != kIntegrate)
       throw Error("Please call this function after GetRenderResult (tsdf_volume.cu:760-763)");
-    if (mesh_pending_) throw Error("ExtractMeshAsync called twice without GetMeshSync (tsdf_volume.cu:769-772)");
-    TDM_CUDA(cudaSetDevice(device_));
-    const int nblk = d_.o.num_blocks;
-    if (!d_mesh_counts_) {
-      TDM_CUDA(cudaMalloc(&d_mesh_counts_, (size_t)nblk * sizeof(int)));
-      TDM_CUDA(cudaMalloc(&d_mesh_offsets_, (size_t)nblk * sizeof(int)));
-      TDM_CUDA(cudaMalloc(&d_mesh_total_, sizeof(int)));
-      TDM_CUDA(cudaMallocHost(&h_mesh_total_, sizeof(int)));
-      TDM_CUDA(cudaEventCreate(&ev_mesh0_));
-      TDM_CUDA(cudaEventCreate(&ev_mesh1_));
-    }
-    // per-axis tables -> one device buffer: [cells x | cells y | cells z | ranges x | ranges y | ranges z]
-    MeshAxisHost A[3];
-    size_t bytes = 0;
-    bool empty = false;
-    for (int a = 0; a < 3; ++a) {
-      A[a] = build_mesh_axis(lower[a], upper[a], d_.o.voxel_size);
-      empty = empty || A[a].cells.empty();
-      bytes += A[a].cells.size() * sizeof(MeshAxisCell) + A[a].ranges.size() * sizeof(int2) + 64;
-    }
-    TDM_CHECK(d_.slab_lo == INT_MIN && d_.slab_hi == INT_MAX,
-              "mesh extraction of a Z-slab-partitioned volume is not supported (cells at slab faces would be emitted by two ranks)");
-    mesh_empty_ = empty;
-    *h_mesh_total_ = 0;
-    if (empty) { mesh_pending_ = true; return; }
-    if (bytes > mesh_tables_cap_) {
-      cudaFree(d_mesh_tables_);
-      d_mesh_tables_ = nullptr;
-      TDM_CUDA(cudaMalloc(&d_mesh_tables_, bytes));
-      mesh_tables_cap_ = bytes;
-    }
-    std::vector<char> host(bytes, 0);
-    size_t off = 0;
-    for (int a = 0; a < 3; ++a) {
-      const size_t nb = A[a].cells.size() * sizeof(MeshAxisCell);
-      std::memcpy(host.data() + off, A[a].cells.data(), nb);
-      mesh_axes_.cells[a] = reinterpret_cast<const MeshAxisCell*>(d_mesh_tables_ + off);
-      off += (nb + 15) / 16 * 16;
-    }
-    for (int a = 0; a < 3; ++a) {
-      const size_t nb = A[a].ranges.size() * sizeof(int2);
-      std::memcpy(host.data() + off, A[a].ranges.data(), nb);
-      mesh_axes_.brange[a] = reinterpret_cast<const int2*>(d_mesh_tables_ + off);
-      off += (nb + 15) / 16 * 16;
-      mesh_axes_.bmin[a] = A[a].bmin;
-      mesh_axes_.nb[a] = A[a].nb;
-    }
-    TDM_CUDA(cudaMemcpyAsync(d_mesh_tables_, host.data(), off, cudaMemcpyHostToDevice, stream_));  // pageable: staged before return
-    if (!d_mesh_vert_) {   // first estimate (72 B per triangle); GetMeshSync grows it when the count says so
-      const char* init = getenv("TDM_MESH_INIT_TRIS");
-      grow_mesh_buffers(init && atoll(init) > 0 ? atoll(init) : (1 << 20));
-    }
-    TDM_CUDA(cudaEventRecord(ev_mesh0_, stream_));
-    k_mesh<false><<<kMeshGrid, 256, 0, stream_>>>(d_, mesh_axes_, d_mesh_counts_, nullptr, 0, nullptr, nullptr);
-    TDM_CUDA(cudaGetLastError());
-    k_mesh_scan<<<1, 1024, 0, stream_>>>(d_mesh_counts_, d_mesh_offsets_, d_.counters, nblk, d_mesh_total_);
-    TDM_CUDA(cudaGetLastError());
-    launch_mesh_emit();
-    TDM_CUDA(cudaMemcpyAsync(h_mesh_total_, d_mesh_total_, sizeof(int), cudaMemcpyDeviceToHost, stream_));
-    TDM_CUDA(cudaEventRecord(ev_mesh1_, stream_));
-    mesh_pending_ = true;   // only once everything is enqueued: a failed call leaves no half-started extraction behind
+    if (mesh_kind_ == kMeshAsync) throw Error("ExtractMeshAsync called twice without GetMeshSync (tsdf_volume.cu:769-772)");
+    start_mesh(lower, upper);
+    mesh_kind_ = kMeshAsync;   // only once everything is enqueued: a failed call leaves no half-started extraction behind
   }
 
   // GetMeshSync, tsdf_volume.cu:781-839: vertices as xyz triples, colours as rgb triples, 3 per triangle
   long long get_mesh(float* vert, float* cols, size_t max_vertices, bool check_order, bool query_only) override {
     if (check_order && next_ != kIntegrate)
       throw Error("Please call this function after GetRenderResult (tsdf_volume.cu:782-785)");
-    if (!mesh_pending_) throw Error("GetMeshSync without ExtractMeshAsync (tsdf_volume.cu:787-790)");
-    if (!query_only) mesh_pending_ = false;
-    if (mesh_empty_) { mesh_ms_ = 0.f; return 0; }
-    TDM_CUDA(cudaSetDevice(device_));
-    TDM_CUDA(cudaEventSynchronize(ev_mesh1_));
-    TDM_CUDA(cudaEventElapsedTime(&mesh_ms_, ev_mesh0_, ev_mesh1_));
-    const long long ntri = *h_mesh_total_;
-    if (query_only) return 3 * ntri;
-    if (ntri > mesh_cap_tris_) {   // first estimate too small: grow once and re-emit (counts / offsets are still valid)
-      grow_mesh_buffers(ntri + ntri / 4);
-      TDM_CUDA(cudaEventRecord(ev_mesh0_, stream_));
-      launch_mesh_emit();
-      TDM_CUDA(cudaEventRecord(ev_mesh1_, stream_));
-      TDM_CUDA(cudaEventSynchronize(ev_mesh1_));
-      float again = 0.f;
-      TDM_CUDA(cudaEventElapsedTime(&again, ev_mesh0_, ev_mesh1_));
-      mesh_ms_ += again;
+    if (mesh_kind_ != kMeshAsync) throw Error("GetMeshSync without ExtractMeshAsync (tsdf_volume.cu:787-790)");
+    const long long nv = finish_mesh(vert, cols, max_vertices, query_only);
+    if (!query_only) mesh_kind_ = kMeshNone;
+    return nv;
+  }
+
+  // TsdfVolume::ExtractMesh (blocking, tsdf_volume.cu:739-757).  The reference runs it on an extractor of its own, so it
+  // never disturbs an ExtractMeshAsync/GetMeshSync pair; here both share the device buffers, hence a blocking call while an
+  // asynchronous result is un-fetched is rejected instead of silently consuming it.  A count-only query (vert == cols ==
+  // nullptr) keeps the mesh on the device; it is re-used by the following copy call only for the identical box and an
+  // unchanged volume, anything else extracts again.
+  long long extract_mesh_blocking(const float* lower, const float* upper, float* vert, float* cols, size_t max_vertices) override {
+    if (mesh_kind_ == kMeshAsync)
+      throw Error("ExtractMesh (GetMesh / SaveMeshToFile) while an ExtractMeshAsync result is pending: call GetMeshSync first");
+    const bool query_only = vert == nullptr && cols == nullptr;
+    bool reuse = mesh_kind_ == kMeshBlocking && mesh_epoch_ == volume_epoch_;
+    for (int a = 0; a < 3 && reuse; ++a) reuse = mesh_lower_[a] == lower[a] && mesh_upper_[a] == upper[a];
+    if (!reuse) {
+      mesh_kind_ = kMeshNone;
+      start_mesh(lower, upper);
+      mesh_kind_ = kMeshBlocking;
     }
-    const long long nv = 3 * ntri;
-    if ((unsigned long long)nv > (unsigned long long)max_vertices)
-      throw Error("Did not provide enough storage for mesh. (tsdf_volume.cu:796-799)");
-    if (nv > 0) {
-      TDM_CHECK(vert && cols, "null mesh output buffers");
-      TDM_CUDA(cudaMemcpy(vert, d_mesh_vert_, (size_t)nv * 3 * sizeof(float), cudaMemcpyDeviceToHost));
-      TDM_CUDA(cudaMemcpy(cols, d_mesh_cols_, (size_t)nv * 3 * sizeof(float), cudaMemcpyDeviceToHost));
-    }
+    const long long nv = finish_mesh(vert, cols, max_vertices, query_only);
+    if (!query_only) mesh_kind_ = kMeshNone;
     return nv;
   }
   float last_mesh_ms() override { return mesh_ms_; }
@@ -931,7 +872,7 @@ class FusionImpl final : public FusionIface {
     else if (n == "integrate_compact") integrate_compact_ = value != 0;
     else throw Error("unknown fusion option " + n);
   }
-  bool mesh_pending() override { return mesh_pending_; }
+  bool mesh_pending() override { return mesh_kind_ != kMeshNone; }
 
   const float* render_depth_device(int i, void** ready_event, int* device) override {
     TDM_CHECK(i >= 0 && i < n_rendered_, "render_depth_device: no such render");
@@ -1034,6 +975,107 @@ class FusionImpl final : public FusionIface {
     }
   }
   static constexpr int kMeshGrid = 148 * 8;
+  // count + scan + emit + total on stream_ (no host sync)
+  void launch_mesh_all() {
+    TDM_CUDA(cudaEventRecord(ev_mesh0_, stream_));
+    k_mesh<false><<<kMeshGrid, 256, 0, stream_>>>(d_, mesh_axes_, d_mesh_counts_, nullptr, 0, nullptr, nullptr);
+    TDM_CUDA(cudaGetLastError());
+    k_mesh_scan<<<1, 1024, 0, stream_>>>(d_mesh_counts_, d_mesh_offsets_, d_.counters, d_.o.num_blocks, d_mesh_total_);
+    TDM_CUDA(cudaGetLastError());
+    launch_mesh_emit();
+    TDM_CUDA(cudaMemcpyAsync(h_mesh_total_, d_mesh_total_, sizeof(int), cudaMemcpyDeviceToHost, stream_));
+    TDM_CUDA(cudaEventRecord(ev_mesh1_, stream_));
+  }
+  void start_mesh(const float* lower, const float* upper) {
+    TDM_CUDA(cudaSetDevice(device_));
+    const int nblk = d_.o.num_blocks;
+    if (!d_mesh_counts_) {
+      TDM_CUDA(cudaMalloc(&d_mesh_counts_, (size_t)nblk * sizeof(int)));
+      TDM_CUDA(cudaMalloc(&d_mesh_offsets_, (size_t)nblk * sizeof(int)));
+      TDM_CUDA(cudaMalloc(&d_mesh_total_, sizeof(int)));
+      TDM_CUDA(cudaMallocHost(&h_mesh_total_, sizeof(int)));
+      TDM_CUDA(cudaEventCreate(&ev_mesh0_));
+      TDM_CUDA(cudaEventCreate(&ev_mesh1_));
+    }
+    // per-axis tables -> one device buffer: [cells x | cells y | cells z | ranges x | ranges y | ranges z]
+    MeshAxisHost A[3];
+    size_t bytes = 0;
+    bool empty = false;
+    for (int a = 0; a < 3; ++a) {
+      A[a] = build_mesh_axis(lower[a], upper[a], d_.o.voxel_size);
+      empty = empty || A[a].cells.empty();
+      bytes += A[a].cells.size() * sizeof(MeshAxisCell) + A[a].ranges.size() * sizeof(int2) + 64;
+      mesh_lower_[a] = lower[a];
+      mesh_upper_[a] = upper[a];
+    }
+    TDM_CHECK(d_.slab_lo == INT_MIN && d_.slab_hi == INT_MAX,
+              "mesh extraction of a Z-slab-partitioned volume is not supported (cells at slab faces would be emitted by two ranks)");
+    mesh_empty_ = empty;
+    mesh_epoch_ = volume_epoch_;
+    *h_mesh_total_ = 0;
+    if (empty) return;
+    if (bytes > mesh_tables_cap_) {
+      cudaFree(d_mesh_tables_);
+      d_mesh_tables_ = nullptr;
+      TDM_CUDA(cudaMalloc(&d_mesh_tables_, bytes));
+      mesh_tables_cap_ = bytes;
+    }
+    std::vector<char> host(bytes, 0);
+    size_t off = 0;
+    for (int a = 0; a < 3; ++a) {
+      const size_t nb = A[a].cells.size() * sizeof(MeshAxisCell);
+      std::memcpy(host.data() + off, A[a].cells.data(), nb);
+      mesh_axes_.cells[a] = reinterpret_cast<const MeshAxisCell*>(d_mesh_tables_ + off);
+      off += (nb + 15) / 16 * 16;
+    }
+    for (int a = 0; a < 3; ++a) {
+      const size_t nb = A[a].ranges.size() * sizeof(int2);
+      std::memcpy(host.data() + off, A[a].ranges.data(), nb);
+      mesh_axes_.brange[a] = reinterpret_cast<const int2*>(d_mesh_tables_ + off);
+      off += (nb + 15) / 16 * 16;
+      mesh_axes_.bmin[a] = A[a].bmin;
+      mesh_axes_.nb[a] = A[a].nb;
+    }
+    TDM_CUDA(cudaMemcpyAsync(d_mesh_tables_, host.data(), off, cudaMemcpyHostToDevice, stream_));  // pageable: staged before return
+    if (!d_mesh_vert_) {   // first estimate (72 B per triangle, 2 M triangles = 151 MB); finish_mesh grows it when the count says so
+      const char* init = getenv("TDM_MESH_INIT_TRIS");
+      grow_mesh_buffers(init && atoll(init) > 0 ? atoll(init) : (1 << 21));
+    }
+    launch_mesh_all();
+  }
+  // waits for the extraction, grows the output buffers if the count says so, copies out; returns the vertex count
+  long long finish_mesh(float* vert, float* cols, size_t max_vertices, bool query_only) {
+    if (mesh_empty_) { mesh_ms_ = 0.f; return 0; }
+    TDM_CUDA(cudaSetDevice(device_));
+    TDM_CUDA(cudaEventSynchronize(ev_mesh1_));
+    TDM_CUDA(cudaEventElapsedTime(&mesh_ms_, ev_mesh0_, ev_mesh1_));
+    long long ntri = *h_mesh_total_;
+    if (query_only) return 3 * ntri;
+    // First estimate too small: grow and run the extraction again.  The per-block counts / offsets of the first run are
+    // only valid for the volume they were counted on; scans may have been integrated since ExtractMeshAsync (the call-order
+    // state machine allows a whole Integrate -> Render -> GetRenderResult cycle in between), so count + scan + emit are all
+    // redone, and once more should the newer volume need even more room.
+    for (int attempt = 0; ntri > mesh_cap_tris_; ++attempt) {
+      TDM_CHECK(attempt < 4, "mesh output kept outgrowing its buffers");
+      grow_mesh_buffers(ntri + ntri / 4);
+      launch_mesh_all();
+      TDM_CUDA(cudaEventSynchronize(ev_mesh1_));
+      float again = 0.f;
+      TDM_CUDA(cudaEventElapsedTime(&again, ev_mesh0_, ev_mesh1_));
+      mesh_ms_ += again;
+      ntri = *h_mesh_total_;
+      mesh_epoch_ = volume_epoch_;
+    }
+    const long long nv = 3 * ntri;
+    if ((unsigned long long)nv > (unsigned long long)max_vertices)
+      throw Error("Did not provide enough storage for mesh. (tsdf_volume.cu:796-799)");
+    if (nv > 0) {
+      TDM_CHECK(vert && cols, "null mesh output buffers");
+      TDM_CUDA(cudaMemcpy(vert, d_mesh_vert_, (size_t)nv * 3 * sizeof(float), cudaMemcpyDeviceToHost));
+      TDM_CUDA(cudaMemcpy(cols, d_mesh_cols_, (size_t)nv * 3 * sizeof(float), cudaMemcpyDeviceToHost));
+    }
+    return nv;
+  }
   void grow_mesh_buffers(long long tris) {
     cudaFree(d_mesh_vert_); cudaFree(d_mesh_cols_);
     d_mesh_vert_ = d_mesh_cols_ = nullptr;
@@ -1090,7 +1132,11 @@ class FusionImpl final : public FusionIface {
   float *d_mesh_vert_ = nullptr, *d_mesh_cols_ = nullptr;
   int mesh_cap_tris_ = 0;
   cudaEvent_t ev_mesh0_ = nullptr, ev_mesh1_ = nullptr;
-  bool mesh_pending_ = false, mesh_empty_ = false;
+  enum MeshKind { kMeshNone, kMeshAsync, kMeshBlocking };
+  MeshKind mesh_kind_ = kMeshNone;   // who owns the extraction sitting in the device buffers
+  bool mesh_empty_ = false;
+  float mesh_lower_[3] = {0, 0, 0}, mesh_upper_[3] = {0, 0, 0};
+  unsigned long long volume_epoch_ = 0, mesh_epoch_ = 0;   // scans integrated so far / at the time of the extraction
   float mesh_ms_ = 0.f;
 };
 

@@ -22,6 +22,7 @@ class FusionIface {
   // marching cubes (ExtractMeshAsync / GetMeshSync); check_order enforces the reference's call-order state machine
   virtual void extract_mesh_async(const float* lower, const float* upper, bool check_order) = 0;
   virtual long long get_mesh(float* vert, float* cols, size_t max_vertices, bool check_order, bool query_only) = 0;
+  virtual long long extract_mesh_blocking(const float* lower, const float* upper, float* vert, float* cols, size_t max_vertices) = 0;
   virtual bool mesh_pending() = 0;
   virtual long long* render_keys_device(int i) = 0;
   virtual void unpack_keys(const long long* keys_dev, float* depth_out, unsigned char* bgr_out) = 0;

@@ -170,6 +170,13 @@ class MvsnetEngine final : public MvsnetIface {
   }
 
   void set_option(const std::string& key, int value) override {
+    {
+      // the worker may be replaying the captured graph: wait for it before the graph is destroyed / options change
+      std::unique_lock<std::mutex> lk(mu_);
+      cv_done_.wait(lk, [this] { return !busy_; });
+    }
+    TDM_CUDA(cudaSetDevice(device_));
+    TDM_CUDA(cudaStreamSynchronize(stream_));
     drop_graph();
     if (key == "filter_all_stages") filter_all_ = value != 0;
     else if (key == "use_graph") use_graph_ = value != 0;
@@ -181,9 +188,11 @@ class MvsnetEngine final : public MvsnetIface {
       // CostRegNet is fully convolutional in D).  Forces a re-plan.
       TDM_CHECK(value == 4 || (value > 0 && value % 8 == 0 && value <= 64), "depth_num must be 4 or a multiple of 8 up to 64");
       depth_num_[key[15] - '1'] = value;
-      std::unique_lock<std::mutex> lk(mu_);
-      cv_done_.wait(lk, [this] { return !busy_; });
-      V_ = H_ = W_ = 0;   // ensure_plan rebuilds
+      // the old plan's buffers are sized for the old D: drop them together with the resident window, so that neither
+      // run_resident / profile nor a stale logits buffer can be used before the next CallAsync re-plans
+      free_plan();
+      V_ = H_ = W_ = 0;
+      have_inputs_ = false;
     }
     else if (key == "keep_intermediates") keep_ = value != 0;
     else if (key == "use_tc") use_tc_ = value != 0;

@@ -588,6 +588,7 @@ class TrackerImpl final : public TrackerIface {
       TDM_CUDA(cudaMemcpyAsync(d_pc_ + a * nm, h_pc_ + a * nm, 4 * (size_t)n, cudaMemcpyHostToDevice, stream_));
     ref_exposure_ = ref_exposure;
     ref_aff_[0] = ref_aff[0]; ref_aff_[1] = ref_aff[1];
+    have_params_ = false;   // a calcG now needs a calcRes against the new reference first
   }
 
   void set_new(const float* dI) override {
@@ -596,6 +597,7 @@ class TrackerImpl final : public TrackerIface {
     std::memcpy(h_dI_, dI, (size_t)3 * w_ * h_ * 4);
     TDM_CUDA(cudaMemcpyAsync(d_dI_, h_dI_, (size_t)3 * w_ * h_ * 4, cudaMemcpyHostToDevice, stream_));
     have_new_ = true;
+    have_params_ = false;   // calcG is only defined on the buffers of a calcRes against THIS image (cuda_coarse_tracker.cpp:277-281)
   }
 
   void calc_res(const double* refToNew, float new_exposure, const double aff[2], float cutoffTH, double res6[6]) override {
@@ -605,7 +607,7 @@ class TrackerImpl final : public TrackerIface {
     finish_res(res6);
   }
   void calc_g(float new_exposure, const double aff[2], double H[64], double b[8]) override {
-    TDM_CHECK(have_params_, "calcG before calcRes");
+    TDM_CHECK(have_params_, "calcG before calcRes (or the reference / new image changed since the last calcRes)");
     set_aff(new_exposure, aff);
     launch(1);
     TDM_CUDA(cudaStreamSynchronize(stream_));
@@ -709,6 +711,7 @@ class TrackerImpl final : public TrackerIface {
     n_ = a.n_sparse + total;      // the pre-increment quirk: the last appended point is not counted
     ref_exposure_ = a.ref_exposure;
     ref_aff_[0] = a.ref_aff[0]; ref_aff_[1] = a.ref_aff[1];
+    have_params_ = false;
     return n_;
   }
   int width() const override { return w_; }
@@ -729,6 +732,7 @@ class TrackerImpl final : public TrackerIface {
     if (ready_event) TDM_CUDA(cudaStreamWaitEvent(stream_, (cudaEvent_t)ready_event, 0));
     TDM_CUDA(cudaMemcpyAsync(d_dI_, d_dI, (size_t)3 * w_ * h_ * 4, cudaMemcpyDeviceToDevice, stream_));
     have_new_ = true;
+    have_params_ = false;   // calcG is only defined on the buffers of a calcRes against THIS image (cuda_coarse_tracker.cpp:277-281)
   }
   // ---------------------------------------------------------------------------------------------- n3
   void track(const TrackArgs& a, TrackResult* r) override {
@@ -850,6 +854,7 @@ class TrackerImpl final : public TrackerIface {
     have_params_ = true;
   }
   void launch(int mode, bool dev_loop = false) {
+    TDM_CUDA(cudaSetDevice(device_));   // another handle of this thread may have switched the current device
     TrkBufs b;
     const size_t nm = (size_t)n_max_;
     b.lm = dev_loop ? d_lm_ctx_ : nullptr;

@@ -142,6 +142,65 @@ def test_front_oracle_pyramid_and_dense_reference():
     assert n3 == 2 + interior - 2 and arrs3[0][0] == 7 and arrs3[0][1] == 9
 
 
+def _front_ref():
+    from oracle.cpu import FrontRef
+    if not FrontRef.available():
+        pytest.skip("oracle/_ref/libfront_ref.so not built (needs /root/reference: make -C oracle -f ref_build.mk)")
+    return FrontRef()
+
+
+@pytest.mark.parametrize("size,levels", [((480, 640), 4), ((96, 130), 2), ((60, 80), 3)])
+def test_front_oracle_pyramid_pinned_to_reference_makeImages(size, levels):
+    """n2 pin: oracle/front_oracle.c == the reference's own FrameHessian::makeImages body (HessianBlocks.cpp:128-191,
+    compiled unmodified into oracle/_ref/libfront_ref.so), bit for bit, incl. a non-finite input pixel."""
+    from oracle.cpu import FrontOracle
+    ref = _front_ref()
+    h, w = size
+    rng = np.random.default_rng(3)
+    gray = (rng.random((h, w)) * 255).astype(np.float32)
+    gray[5, 7] = np.inf
+    a = FrontOracle().make_images(gray, levels)
+    b = ref.make_images(gray, levels)
+    for lvl in range(levels):
+        assert np.array_equal(a[lvl][0], b[lvl][0], equal_nan=True), f"level {lvl} (I,dx,dy)"
+        assert np.array_equal(a[lvl][1], b[lvl][1], equal_nan=True), f"level {lvl} absSquaredGrad"
+
+
+@pytest.mark.parametrize("step,with_sparse,size", [(1, False, (240, 320)), (2, True, (240, 320)), (1, True, (120, 160)),
+                                                    (3, False, (480, 640))])
+def test_front_oracle_dense_reference_pinned_to_reference_setCoarseTrackingRef(step, with_sparse, size):
+    """n1 pin: forward warp + nearest-depth test + raster-order append (incl. the ++pc_n quirk) of oracle/front_oracle.c ==
+    the reference's own dense block of CoarseTracker::setCoarseTrackingRef (CoarseTracker.cpp:655-725), bit for bit: pc_n,
+    all four point arrays and the stale / uncounted slots."""
+    from oracle.cpu import FrontOracle
+    ref = _front_ref()
+    h, w = size
+    f = 160.0 * w / 320.0
+    K4 = (f, f, (w - 1) / 2.0, (h - 1) / 2.0)
+    scene = RoomScene()
+    pose_d = look_at_pose((0.3, 0.0, -0.2), (2.5, 0.2, 0.5))
+    pose_r = look_at_pose((0.34, 0.02, -0.17), (2.5, 0.25, 0.45))
+    _, depth = scene.render(pose_d, h, w, *K4, dropout=0.02, seed=1)
+    bgr_r, _ = scene.render(pose_r, h, w, *K4)
+    gray_r = bgr_r.astype(np.float32) @ np.array([0.114, 0.587, 0.299], np.float32)
+    rng = np.random.default_rng(5)
+    sparse, idepth0 = None, None
+    if with_sparse:
+        ns = 500
+        sparse = [rng.integers(3, w - 3, ns + 1).astype(np.float32), rng.integers(3, h - 3, ns + 1).astype(np.float32),
+                  rng.uniform(0.2, 2.0, ns + 1).astype(np.float32), rng.uniform(0, 255, ns + 1).astype(np.float32)]
+        idepth0 = np.zeros((h, w), np.float32)
+        idepth0[sparse[1][:ns].astype(int), sparse[0][:ns].astype(int)] = sparse[2][:ns]
+    n_ref, arrs_ref, T = ref.dense_reference(depth, pose_d, pose_r.astype(np.float64), K4, step, not with_sparse, sparse,
+                                             idepth0, gray_r)
+    # the transform the reference derives (SE3 inverse * SE3) is the one the oracle / the device path is handed
+    assert np.allclose(T, np.linalg.inv(pose_r.astype(np.float64)) @ pose_d.astype(np.float64), atol=1e-12)
+    n, arrs, _ = FrontOracle().dense_reference(depth, T, K4, step, not with_sparse, sparse, idepth0, gray_r)
+    assert n == n_ref and n > 1000
+    for a, b, name in zip(arrs, arrs_ref, ("u", "v", "idepth", "color")):
+        assert np.array_equal(a, b), name
+
+
 def test_lm_driver_converges_with_oracle_tracker():
     """The host restatement of trackNewestCoarse's level loop (oracle/lm_driver.py) reduces the pose error and the energy."""
     from oracle.lm_driver import se3_exp, track_level0
