@@ -71,6 +71,13 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def measured_tensor_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p)).get("bf16_tflops_sustained", 1374.6))
+    return 1400.0
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
 
@@ -115,42 +122,91 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def pick_cpu_threads():
-    """The reference arm gets the thread count that is fastest on this host (more threads than ~32 slow torch's
-    CPU convolutions down on many-core boxes): probed on a small convolution, a few hundred ms in total."""
+def pick_cpu_threads(run=None):
+    """Thread count of the reference arm: the fastest of {16, 32, 64, all} on ONE FULL forward of the workload each (after a
+    short warm-up conv so that the thread pool exists).  Round 1 probed a toy convolution and the choice - hence the
+    headline ratio - moved 2x between driver runs; a full forward per candidate costs ~10 s in total and is stable."""
     import torch
-    best, best_t = None, 1e30
-    x = torch.rand(1, 16, 32, 120, 160)
-    w = torch.rand(16, 16, 3, 3, 3)
-    cands = sorted({c for c in (8, 16, 32, 64, os.cpu_count()) if c <= os.cpu_count()})
+    ncpu = os.cpu_count() or 1
+    cands = sorted({c for c in (16, 32, 64, ncpu) if c <= ncpu}) or [ncpu]
+    if run is None or len(cands) == 1:
+        torch.set_num_threads(cands[-1])
+        return cands[-1], {}
+    timings = {}
+    torch.set_num_threads(cands[0])
+    run()                                   # cold start (allocator, oneDNN primitive caches) paid before any candidate is timed
     for c in cands:
         torch.set_num_threads(c)
-        torch.nn.functional.conv3d(x, w, padding=1)
+        x = torch.rand(1, 8, 8, 60, 80)
+        torch.nn.functional.conv3d(x, torch.rand(8, 8, 3, 3, 3), padding=1)
         t0 = time.perf_counter()
-        for _ in range(3):
-            torch.nn.functional.conv3d(x, w, padding=1)
-        dt = time.perf_counter() - t0
-        if dt < best_t:
-            best, best_t = c, dt
+        run()
+        timings[c] = time.perf_counter() - t0
+    best = min(timings, key=timings.get)
     torch.set_num_threads(best)
-    return best
+    return best, {str(k): round(v, 3) for k, v in timings.items()}
 
 
-def oracle_forward_fn(win):
+def oracle_forward_fn(win, device=None):
+    """The reference graph (cva_mvsnet.py:98-184) as restated by oracle/mvsnet_oracle.py (pinned against the reference model
+    and its shipped goldens).  device=None: torch CPU fp32 = the reference's CPU path; device='cuda:0': the same torch ops on
+    cuDNN fp32 (TF32 off) = the compute path of the reference's libdr `module.forward` (dr_mvsnet.cpp:292-294)."""
     import torch
     from oracle import mvsnet_oracle as O
     from tandem_b200 import default_weights
     from tandem_b200.weights_io import load_tdmw
-    win["cpu_threads"] = pick_cpu_threads()
     w, dn, va = load_tdmw(default_weights(WEIGHTS))
     img, order = O.preprocess_bgr(win["bgr_all"], win["ref_index"])
     Ks = [torch.from_numpy(np.asarray(k, np.float32)) for k in win["Ks"]]
     c2w = torch.from_numpy(win["c2w_all"][order])
+    if device is not None:
+        dev = torch.device(device)
+        w = {k: torch.from_numpy(np.asarray(v)).to(dev) for k, v in w.items()}
+        img, c2w, Ks = img.to(dev), c2w.to(dev), [k.to(dev) for k in Ks]
+
+        def run():
+            with torch.no_grad(), torch.device(dev):
+                return O.forward(w, dn, img, Ks, c2w, win["dmin"], win["dmax"], win["discard"], va)
+        return run
 
     def run():
         with torch.no_grad():
             return O.forward(w, dn, img, Ks, c2w, win["dmin"], win["dmax"], win["discard"], va)
+    win["cpu_threads"], win["cpu_thread_probe_s"] = pick_cpu_threads(run)
     return run
+
+
+def time_gpu_reference(win, local, steps=10, warmup=3):
+    """GPU comparator (VERDICT r01 item 3 / SURVEY 8d iii): the reference graph in eager PyTorch on cuDNN on the same B200,
+    timed with CUDA events outside our arm's timed regions: fp32 with TF32 off (bit-comparable arithmetic) and with TF32 on
+    (what torch 1.9, the reference's libtorch, allows cuDNN by default).  Returns a dict for the JSON line."""
+    import torch
+    try:
+        torch.backends.cudnn.benchmark = True
+        run = oracle_forward_fn(win, device=f"cuda:{local}")
+        res = {}
+        for tf32 in (False, True):
+            torch.backends.cuda.matmul.allow_tf32 = tf32
+            torch.backends.cudnn.allow_tf32 = tf32
+            for _ in range(warmup):
+                out = run()
+            torch.cuda.synchronize(local)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                out = run()
+            e1.record()
+            torch.cuda.synchronize(local)
+            res[tf32] = (e0.elapsed_time(e1) / steps, out[2]["depth_dense"].float().cpu().numpy())
+        ms = res[False][0]
+        return {"value": 1e3 / ms, "unit": "keyframes/s", "ms_per_step": ms, "steps": steps, "warmup": warmup,
+                "tf32_value": 1e3 / res[True][0], "tf32_ms_per_step": res[True][0],
+                "depth_dense_gpu": res[False][1],
+                "what": "oracle/mvsnet_oracle.py (the reference graph, pinned) in eager PyTorch on cuda: cuDNN fp32 (value: TF32 off; "
+                        "tf32_value: TF32 allowed), cudnn.benchmark on, inputs resident - the compute path of the reference's libdr "
+                        "module.forward (dr_mvsnet.cpp:292-294)"}
+    except Exception as e:   # the comparator must never take the bench line down
+        return {"unavailable": f"{type(e).__name__}: {e}"[:200]}
 
 
 def time_cpu(win, steps, warmup):
@@ -162,6 +218,48 @@ def time_cpu(win, steps, warmup):
         run()
     dt = time.perf_counter() - t0
     return steps / dt, dt / steps * 1e3
+
+
+def bind_to_gpu_numa(local, n_local):
+    """Pin this rank (and every thread it creates afterwards: engine workers, the copy pool; page-locked allocations are then
+    node-local too) to its GPU's NUMA node, sharing the node's CPUs evenly with the other ranks whose GPUs hang off the same
+    node.  Returns a short description for the JSON line."""
+    try:
+        q = subprocess.run(["nvidia-smi", "--query-gpu=index,pci.bus_id", "--format=csv,noheader"], capture_output=True, text=True,
+                           timeout=20).stdout
+        bus = {}
+        for line in q.strip().splitlines():
+            idx, b = [x.strip() for x in line.split(",")]
+            bus[int(idx)] = b.lower()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        phys = [int(x) for x in vis.split(",")] if vis and all(t.strip().isdigit() for t in vis.split(",")) else sorted(bus)
+
+        def node_of(i):
+            b = bus[phys[i]]
+            b = b[-12:] if len(b) > 12 else b            # nvidia-smi prints an 8-digit domain, sysfs a 4-digit one
+            with open(f"/sys/bus/pci/devices/{b}/numa_node") as f:
+                return int(f.read().strip())
+        nodes = [node_of(i) for i in range(n_local)]
+        node = nodes[local]
+        if node < 0:
+            return "numa node unknown (-1): not bound"
+        cpus = []
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus += list(range(int(a), int(b or a) + 1))
+        cpus = sorted(set(cpus) & os.sched_getaffinity(0))
+        peers = [i for i in range(n_local) if nodes[i] == node]
+        k, m = peers.index(local), len(peers)
+        # physical cores first, hyper-thread siblings second, in Linux's usual numbering: give each rank a slice of both halves
+        half = len(cpus) // 2
+        lo, hi = cpus[:half], cpus[half:]
+        mine = lo[k * len(lo) // m:(k + 1) * len(lo) // m] + hi[k * len(hi) // m:(k + 1) * len(hi) // m]
+        if not mine:
+            return "no cpus left for this rank: not bound"
+        os.sched_setaffinity(0, mine)
+        return f"GPU {local} -> NUMA node {node}, {len(mine)} of its {len(cpus)} cpus ({m} ranks on the node)"
+    except Exception as e:
+        return f"not bound ({type(e).__name__}: {e})"[:160]
 
 
 def dist_setup(n):
@@ -213,6 +311,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default="mixed16", choices=["mixed16", "fp32", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gpu-reference", action="store_true", help="skip the eager-PyTorch/cuDNN comparator record")
+    ap.add_argument("--no-bind", action="store_true", help="do not bind ranks to their GPU's NUMA node (multi-GPU runs)")
     ap.add_argument("--inflight", type=int, default=8, choices=[1, 2, 3, 4, 5, 6, 7, 8],
                     help="independent windows in flight per GPU (n DrMvsnet handles, one stream each, used round-robin) in both legs")
     ap.add_argument("--e2e-inflight", type=int, default=4, choices=[1, 2, 3, 4, 5, 6, 7, 8],
@@ -238,14 +338,16 @@ def main():
             "vs_baseline": None, "dtype": "f32", "data": "golden sample window (tests/golden/sample_640x480.npz)",
             "config": {"workload": WORKLOAD},
             "cpu_baseline": {"value": kfs, "unit": "keyframes/s", "cores": cores, "kind": "port",
-                             "sample": f"{steps} full forwards of the workload window (oracle/mvsnet_oracle.py, torch CPU fp32, {cores} of {os.cpu_count()} host threads: fastest of a probe)"},
+                             "sample": f"{steps} full forwards of the workload window (oracle/mvsnet_oracle.py, torch CPU fp32, {cores} of {os.cpu_count()} host threads: fastest of one full forward per candidate {win.get('cpu_thread_probe_s')})"},
             "e2e": {"value": kfs, "unit": "keyframes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         }))
         return 0
 
     rank, world, local, dist = dist_setup(a.gpus)
+    affinity = bind_to_gpu_numa(local, int(os.environ.get("LOCAL_WORLD_SIZE", world))) if world > 1 and not a.no_bind else "single rank: not bound"
     import torch  # device plumbing + torch.distributed only
-    from tandem_b200 import DrMvsnet, default_weights
+    from tandem_b200 import DrMvsnet, DrMvsnetOutput, default_weights
+    from tandem_b200._lib import pinned_empty
     win = load_window(rank)
     m = DrMvsnet(default_weights(WEIGHTS), precision=a.precision, device=local)
     # second handle for the end-to-end leg: two windows in flight per GPU (window k+1's staging copy + H2D and window
@@ -293,58 +395,115 @@ def main():
     ms_single /= max(a.steps // 2, 1)
     barrier()
     # ---- end to end through the public call with host buffers ----
-    for _ in range(2):
-        call()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(a.steps):
-        call()
-    torch.cuda.synchronize(local)
-    ms_e2e_serial = (time.perf_counter() - t0) * 1e3
-    ms_e2e = ms_e2e_serial
-    hs_e2e = hs[:max(1, min(a.e2e_inflight, len(hs)))]
-    if len(hs_e2e) > 1:
-        hs_dev, hs = hs, hs_e2e
-        n = len(hs)
+    # Headline leg: the caller keeps its images and its (recycled) result maps in PAGE-LOCKED host memory - the library then
+    # DMA's straight from / into them (H2D of the 7 u8 images + D2H of the 4 maps inside the timed region, every step).
+    # Secondary leg ("pageable_*"): ordinary numpy arrays and a freshly allocated DrMvsnetOutput per call, i.e. the
+    # reference's ownership contract verbatim, staged through the library's pinned buffers by its copy pool.
+    pin_bgrs = []
+    for b in win["bgrs"]:
+        pb = pinned_empty(b.shape, np.uint8)
+        pb[...] = b
+        pin_bgrs.append(pb)
+
+    def submit_pinned(h):
+        h.CallAsync(win["H"], win["W"], win["V"], win["ref_index"], pin_bgrs, win["K"], win["c2ws"], win["dmin"],
+                    win["dmax"], win["discard"])
+
+    def e2e_leg(handles, sub, outs):
+        n = len(handles)
         barrier()
         t0 = time.perf_counter()
         for j in range(min(n - 1, a.steps)):
-            submit(hs[j])
+            sub(handles[j])
+        r = None
         for i in range(a.steps):            # EXACTLY K windows submitted and K results fetched
             if i + n - 1 < a.steps:
-                submit(hs[(i + n - 1) % n])
-            r = hs[i % n].GetResult()
+                sub(handles[(i + n - 1) % n])
+            r = handles[i % n].GetResult(out=outs[i % n] if outs else None)
         torch.cuda.synchronize(local)
-        ms_e2e = (time.perf_counter() - t0) * 1e3
+        ms = (time.perf_counter() - t0) * 1e3
         assert np.isfinite(r.depth_dense).all()
+        return ms
+
+    hs_e2e = hs[:max(1, min(a.e2e_inflight, len(hs)))]
+    pin_outs = [DrMvsnetOutput(win["H"], win["W"], pinned=True) for _ in hs_e2e]
+    for _ in range(2):
+        call()
+    ms_pg_serial = e2e_leg(hs_e2e[:1], submit, None)
+    ms_pg = e2e_leg(hs_e2e, submit, None) if len(hs_e2e) > 1 else ms_pg_serial
+    for h in hs_e2e:
+        h.set_option("eager_d2h", 0)        # GetResult DMA's into the caller's page-locked maps itself
+    for h, o in zip(hs_e2e, pin_outs):
+        submit_pinned(h); h.GetResult(out=o)
+    ms_e2e_serial = e2e_leg(hs_e2e[:1], submit_pinned, pin_outs[:1])
+    ms_e2e = e2e_leg(hs_e2e, submit_pinned, pin_outs) if len(hs_e2e) > 1 else ms_e2e_serial
+    for h in hs_e2e:
+        h.set_option("eager_d2h", 1)
+    assert np.array_equal(pin_outs[0].depth_dense, out.depth_dense), "page-locked and pageable paths must return the same map"
     barrier()
     clocks = sampler.stop() if sampler else None
 
     from tandem_b200.parallel import reduce_max
-    ms_dev, ms_e2e, ms_e2e_serial = reduce_max(dist, [ms_dev, ms_e2e, ms_e2e_serial], device=f"cuda:{local}")   # slowest rank
+    ms_dev, ms_e2e, ms_e2e_serial, ms_pg, ms_pg_serial = reduce_max(dist, [ms_dev, ms_e2e, ms_e2e_serial, ms_pg, ms_pg_serial],
+                                                                    device=f"cuda:{local}")   # slowest rank
 
     if rank == 0:
         value = world * a.steps / (ms_dev / 1e3)
         e2e = world * a.steps / (ms_e2e / 1e3)
-        # roofline of the dominant kernel: algorithmic bytes / CUDA-event duration, measured live
+        # roofline, measured live: per-kernel CUDA-event durations of one forward (m.profile()) with each record's
+        # algorithmic bytes / flops.  Reported per FAMILY (tcgen05 convs / cost volume / tail) and for the whole step; the
+        # "dominant kernel" entry the contract asks for is the largest single record.
         rows = m.profile()
         tot = sum(r[1] for r in rows)
         top = max(rows, key=lambda r: r[1])
         peak, how = measured_peaks()
+        tpeak = measured_tensor_peak()
         ach = top[2] / (top[1] * 1e-3) / 1e9
         alg_total = sum(r[2] for r in rows)
         traffic, traffic_src = ncu_traffic(top[0])
+
+        def family(name):
+            if "cost_volume" in name:
+                return "cost_volume"
+            if "[tc" in name or name.startswith("f.") and name != "f.img":
+                return "convs"
+            if "preprocess" in name:
+                return "preprocess"
+            return "tail"
+        fam = {}
+        for name, ms_k, by, fl in rows:
+            f = fam.setdefault(family(name), {"ms": 0.0, "bytes": 0.0, "flops": 0.0, "launches": 0})
+            f["ms"] += ms_k; f["bytes"] += by; f["flops"] += fl; f["launches"] += 1
+        families = {k: {"ms": round(v["ms"], 4), "share_of_kernel_time": round(v["ms"] / tot, 4), "launches": v["launches"],
+                        "algorithmic_GB": round(v["bytes"] / 1e9, 4),
+                        "achieved_GBps": round(v["bytes"] / (v["ms"] * 1e-3) / 1e9, 1),
+                        "frac_of_hbm_peak": round(v["bytes"] / (v["ms"] * 1e-3) / 1e9 / peak, 4),
+                        "achieved_TFLOPs": round(v["flops"] / (v["ms"] * 1e-3) / 1e12, 2),
+                        "frac_of_tensor_peak": round(v["flops"] / (v["ms"] * 1e-3) / 1e12 / tpeak, 4) if k == "convs" else None}
+                    for k, v in fam.items()}
         roof = {"bound": "hbm", "kernel": top[0], "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                 "traffic": traffic, "traffic_source": traffic_src, "algorithmic_bytes": top[2],
-                "note": "the kernel is issue/L1-bound (ncu: DRAM < 5 %, issue 57-73 %, L1/TEX 54-90 %); hbm is the nearest of the two allowed bounds",
+                "note": "largest single kernel record; see `families` for the per-family fractions and step_* for the whole step",
                 "peak_source": how, "kernel_ms": top[1], "kernel_share_of_step": top[1] / tot,
+                "families": families, "tensor_peak_TFLOPs": tpeak,
                 "step_algorithmic_GB": alg_total / 1e9, "step_achieved_GBps": alg_total / (ms_dev / a.steps * 1e-3) / 1e9,
-                "step_frac_of_peak": alg_total / (ms_dev / a.steps * 1e-3) / 1e9 / peak}
+                "step_frac_of_peak": alg_total / (ms_dev / a.steps * 1e-3) / 1e9 / peak,
+                "single_window_frac_of_peak": alg_total / (ms_single * 1e-3) / 1e9 / peak}
         cpu = None
         if world == 1 and not a.no_cpu_baseline:
             kfs, ms = time_cpu(win, 2, 1)
             cpu = {"value": kfs, "unit": "keyframes/s", "cores": win["cpu_threads"], "kind": "port",
-                   "sample": "2 full forwards of the workload window after 1 warm-up (oracle/mvsnet_oracle.py, torch CPU fp32)"}
+                   "sample": f"2 full forwards of the workload window after 1 warm-up (oracle/mvsnet_oracle.py, torch CPU fp32; threads: fastest of one full forward per candidate {win.get('cpu_thread_probe_s')})"}
+        gpu_ref = None
+        if world == 1 and not a.no_gpu_reference:
+            gpu_ref = time_gpu_reference(win, local)
+            dd = gpu_ref.pop("depth_dense_gpu", None)
+            if dd is not None:   # our output vs the comparator's on the same window (sanity of both arms)
+                msk = dd > 0
+                gpu_ref["abs_rel_ours_vs_gpu_reference"] = float(np.mean(np.abs(dd[msk] - out.depth_dense[msk]) / dd[msk]))
+                gpu_ref["speedup_device"] = value / gpu_ref["value"]
+                gpu_ref["speedup_single_window"] = (1e3 / ms_single) / gpu_ref["value"]
+                gpu_ref["speedup_device_vs_tf32"] = value / gpu_ref["tf32_value"]
         h2d = win["V"] * win["H"] * win["W"] * 3
         d2h = 4 * win["H"] * win["W"] * 4
         line = {
@@ -358,10 +517,12 @@ def main():
             "e2e": {"value": e2e, "unit": "keyframes/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e / a.steps, "windows_in_flight_per_gpu": len(hs_e2e),
                     "serial_value": world * a.steps / (ms_e2e_serial / 1e3), "serial_ms_per_step": ms_e2e_serial / a.steps,
-                    "note": "CallAsync -> GetResult with host buffers; serial_* = one window at a time (latency bound)",
-                    "host_malloc": host_malloc},
+                    "note": "CallAsync -> GetResult(out=recycled) with PAGE-LOCKED host buffers (images and result maps): DMA straight from / into caller memory; serial_* = one window at a time (latency bound)",
+                    "pageable_value": world * a.steps / (ms_pg / 1e3), "pageable_serial_value": world * a.steps / (ms_pg_serial / 1e3),
+                    "pageable_note": "ordinary numpy inputs + a freshly allocated DrMvsnetOutput per call (the reference's ownership contract), staged through the library's pinned buffers by the process-wide copy pool",
+                    "host_malloc": host_malloc, "affinity": affinity},
             "gpu_launches": launches * a.steps, "launches_per_step": launches,
-            "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
+            "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "gpu_reference": gpu_ref,
         }
         print(json.dumps(line))
     if dist is not None:

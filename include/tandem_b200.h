@@ -33,6 +33,13 @@ const char* tdm_version(void);
 /* Number of CUDA devices visible (0 on a CPU-only box; never throws). */
 int tdm_device_count(void);
 
+/* Page-locked ("pinned") host memory, portable across devices.  Optional: every entry point accepts ordinary pageable
+ * memory (staged through the library's own pinned buffers by a small copy pool), but image / result buffers that ARE
+ * page-locked - from here, cudaHostAlloc or cudaHostRegister - are detected (cudaPointerGetAttributes) and DMA'd from / into
+ * directly, with no staging copy.  The reference does the same staging by hand (tsdf_volume.cu:542-543, dr_mvsnet.cpp:260). */
+int tdm_host_alloc_pinned(size_t bytes, void** out);
+int tdm_host_free_pinned(void* p);
+
 /* ------------------------------------------------------------------------------------------------
  * CVA-MVSNet (replaces DrMvsnet; dr_mvsnet.h:36-66, implementation dr_mvsnet.cpp:125-331)
  * ---------------------------------------------------------------------------------------------- */

@@ -21,7 +21,10 @@ BN_EPS = 1e-5  # torch.nn.BatchNorm default, used by every BN in module.py
 
 
 def _t(w, name):
-    return torch.from_numpy(np.asarray(w[name]))
+    v = w[name]
+    if isinstance(v, torch.Tensor):      # weights already converted / placed on a device by the caller (bench.py's GPU comparator)
+        return v
+    return torch.from_numpy(np.asarray(v))
 
 
 def _bn(x, w, prefix):

@@ -62,6 +62,8 @@ def _declare(l):
         "tdm_last_error": (cp, []),
         "tdm_version": (cp, []),
         "tdm_device_count": (i, []),
+        "tdm_host_alloc_pinned": (i, [c.c_size_t, P(vp)]),
+        "tdm_host_free_pinned": (i, [vp]),
         "tdm_mvsnet_create": (i, [cp, i, i, P(vp)]),
         "tdm_mvsnet_destroy": (None, [vp]),
         "tdm_mvsnet_call_async": (i, [vp, i, i, i, i, P(vp), fp, P(vp), f, f, f]),
@@ -124,6 +126,21 @@ def _declare(l):
         fn.restype = res
         fn.argtypes = args
     l._tdm_missing = missing
+
+
+def pinned_empty(shape, dtype):
+    """numpy array over page-locked host memory (tdm_host_alloc_pinned); freed when the array is collected.  DrMvsnet DMA's
+    straight from / into such arrays (no staging copy)."""
+    import numpy as np
+    import weakref
+    dt = np.dtype(dtype)
+    n = int(np.prod(shape)) * dt.itemsize
+    p = ctypes.c_void_p()
+    check(lib().tdm_host_alloc_pinned(max(n, 1), ctypes.byref(p)))
+    buf = (ctypes.c_char * max(n, 1)).from_address(p.value)
+    a = np.frombuffer(buf, dtype=dt, count=int(np.prod(shape))).reshape(shape)
+    weakref.finalize(buf, lambda addr=p.value: lib().tdm_host_free_pinned(ctypes.c_void_p(addr)))
+    return a
 
 
 API_SYMBOLS = None

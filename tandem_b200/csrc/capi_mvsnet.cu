@@ -27,6 +27,20 @@ int tdm_device_count(void) {
   return n;
 }
 
+int tdm_host_alloc_pinned(size_t bytes, void** out) {
+  TDM_API_BEGIN
+  TDM_CHECK(out && bytes > 0, "null argument");
+  TDM_CUDA(cudaHostAlloc(out, bytes, cudaHostAllocPortable));
+  return TDM_OK;
+  TDM_API_END
+}
+int tdm_host_free_pinned(void* p) {
+  TDM_API_BEGIN
+  if (p) TDM_CUDA(cudaFreeHost(p));
+  return TDM_OK;
+  TDM_API_END
+}
+
 int tdm_debug_homography(const float* K3x3, const float* c2w_ref, const float* c2w_src, float* rot9, float* trans3) {
   TDM_API_BEGIN
   TDM_CHECK(K3x3 && c2w_ref && c2w_src && rot9 && trans3, "null argument");

@@ -835,9 +835,8 @@ class FusionImpl final : public FusionIface {
     if (check_order && next_ != kIntegrate)
       throw Error("Please call this function after GetRenderResult (tsdf_volume.cu:782-785)");
     if (mesh_kind_ != kMeshAsync) throw Error("GetMeshSync without ExtractMeshAsync (tsdf_volume.cu:787-790)");
-    const long long nv = finish_mesh(vert, cols, max_vertices, query_only);
-    if (!query_only) mesh_kind_ = kMeshNone;
-    return nv;
+    if (!query_only) mesh_kind_ = kMeshNone;   // consumed even if the copy-out below fails (the reference exits there)
+    return finish_mesh(vert, cols, max_vertices, query_only);
   }
 
   // TsdfVolume::ExtractMesh (blocking, tsdf_volume.cu:739-757).  The reference runs it on an extractor of its own, so it
@@ -856,9 +855,8 @@ class FusionImpl final : public FusionIface {
       start_mesh(lower, upper);
       mesh_kind_ = kMeshBlocking;
     }
-    const long long nv = finish_mesh(vert, cols, max_vertices, query_only);
     if (!query_only) mesh_kind_ = kMeshNone;
-    return nv;
+    return finish_mesh(vert, cols, max_vertices, query_only);
   }
   float last_mesh_ms() override { return mesh_ms_; }
   float last_alloc_ms() override { return last_alloc_ms_; }
@@ -1050,7 +1048,7 @@ class FusionImpl final : public FusionIface {
     TDM_CUDA(cudaEventSynchronize(ev_mesh1_));
     TDM_CUDA(cudaEventElapsedTime(&mesh_ms_, ev_mesh0_, ev_mesh1_));
     long long ntri = *h_mesh_total_;
-    if (query_only) return 3 * ntri;
+    // (also for a count-only query: the count handed out must be the count of the mesh the copy call will deliver)
     // First estimate too small: grow and run the extraction again.  The per-block counts / offsets of the first run are
     // only valid for the volume they were counted on; scans may have been integrated since ExtractMeshAsync (the call-order
     // state machine allows a whole Integrate -> Render -> GetRenderResult cycle in between), so count + scan + emit are all
@@ -1066,6 +1064,7 @@ class FusionImpl final : public FusionIface {
       ntri = *h_mesh_total_;
       mesh_epoch_ = volume_epoch_;
     }
+    if (query_only) return 3 * ntri;
     const long long nv = 3 * ntri;
     if ((unsigned long long)nv > (unsigned long long)max_vertices)
       throw Error("Did not provide enough storage for mesh. (tsdf_volume.cu:796-799)");

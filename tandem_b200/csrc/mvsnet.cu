@@ -8,6 +8,7 @@
 // memory (6.45 MB instead of 25.8 MB fp32), everything else stays on the device until the four output maps
 // are copied back in one pinned D2H.
 #include <algorithm>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <atomic>
@@ -142,6 +143,7 @@ class MvsnetEngine final : public MvsnetIface {
     TDM_CUDA(cudaEventCreateWithFlags(&ev_join_, cudaEventDisableTiming));
     slot_ = acquire_slot();
     for (auto& e : ev_out_) TDM_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    TDM_CUDA(cudaEventCreateWithFlags(&ev_in_, cudaEventDisableTiming));
     upload_weights();
     worker_ = std::thread([this] { this->loop(); });
   }
@@ -163,6 +165,7 @@ class MvsnetEngine final : public MvsnetIface {
     if (h_params_) cudaFreeHost(h_params_);
     if (d_params_) cudaFree(d_params_);
     for (auto& e : ev_out_) if (e) cudaEventDestroy(e);
+    if (ev_in_) cudaEventDestroy(ev_in_);
     if (ev_fork_) cudaEventDestroy(ev_fork_);
     if (ev_join_) cudaEventDestroy(ev_join_);
     if (side_stream_) cudaStreamDestroy(side_stream_);
@@ -177,6 +180,7 @@ class MvsnetEngine final : public MvsnetIface {
     }
     TDM_CUDA(cudaSetDevice(device_));
     TDM_CUDA(cudaStreamSynchronize(stream_));
+    if (key == "eager_d2h") { eager_d2h_ = value != 0; return; }   // not part of the captured launch sequence
     drop_graph();
     if (key == "filter_all_stages") filter_all_ = value != 0;
     else if (key == "use_graph") use_graph_ = value != 0;
@@ -220,19 +224,31 @@ class MvsnetEngine final : public MvsnetIface {
     ensure_plan(V, H, W);
     // copy inputs (owned by the caller only during this call); reference view first (dr_mvsnet.cpp:190-197)
     const size_t img = (size_t)H * W * 3;
-    // The staging copy of view v+1 overlaps the DMA of view v (the worker is idle here, so this thread may enqueue on
-    // the engine's stream); the worker then only launches the forward behind these copies.
-    // Each view is split into slices copied by the pool; a slice's H2D is enqueued by whichever thread finished copying it
-    // (CUDA stream calls are thread-safe; the order of the DMAs inside the stream does not matter, the forward is
-    // enqueued behind all of them).
-    {
+    for (int vi = 0; vi < V; ++vi) {
+      const int view = vi == 0 ? ref_index : (vi <= ref_index ? vi - 1 : vi);
+      std::memcpy(c2w_[vi], c2ws[view], 16 * sizeof(float));
+    }
+    if (all_page_locked((const void* const*)bgrs, V)) {
+      // Page-locked caller images (cudaHostAlloc / cudaHostRegister): DMA straight from them - no staging copy, no copy
+      // threads.  The caller owns them only during this call, so the call returns once the seven DMAs have landed
+      // (6.45 MB over PCIe gen5: ~0.13 ms, less than the staging memcpy it replaces).
+      for (int vi = 0; vi < V; ++vi) {
+        const int view = vi == 0 ? ref_index : (vi <= ref_index ? vi - 1 : vi);
+        TDM_CUDA(cudaMemcpyAsync(d_bgr_ + (size_t)vi * img, bgrs[view], img, cudaMemcpyHostToDevice, stream_));
+      }
+      TDM_CUDA(cudaEventRecord(ev_in_, stream_));
+      TDM_CUDA(cudaEventSynchronize(ev_in_));
+    } else {
+      // Pageable caller memory: staged through pinned memory.  The staging copy of view v+1 overlaps the DMA of view v (the
+      // worker is idle here, so this thread may enqueue on the engine's stream); each view is split into slices copied by the
+      // process-wide pool; a slice's H2D is enqueued by whichever thread finished copying it (CUDA stream calls are
+      // thread-safe; the order of the DMAs inside the stream does not matter, the forward is enqueued behind all of them).
       std::vector<CopyPool::Job> jobs;
       constexpr int kSlices = 2;
       std::mutex err_mu;
       cudaError_t first_err = cudaSuccess;
       for (int vi = 0; vi < V; ++vi) {
         const int view = vi == 0 ? ref_index : (vi <= ref_index ? vi - 1 : vi);
-        std::memcpy(c2w_[vi], c2ws[view], 16 * sizeof(float));
         for (int sl = 0; sl < kSlices; ++sl) {
           const size_t b0 = img * sl / kSlices, b1 = img * (sl + 1) / kSlices;
           unsigned char* hp = h_bgr_ + (size_t)vi * img + b0;
@@ -244,7 +260,7 @@ class MvsnetEngine final : public MvsnetIface {
                           }});
         }
       }
-      pool_.run(jobs);
+      CopyPool::shared().run(jobs);
       TDM_CUDA(first_err);
     }
     std::memcpy(K_, K3x3x3, 27 * sizeof(float));
@@ -271,8 +287,23 @@ class MvsnetEngine final : public MvsnetIface {
     if (!has_result_) throw Error("GetResult without a pending result (dr_mvsnet.cpp:100-102)");
     const size_t n = (size_t)H_ * W_;
     float* dst[4] = {depth, conf, depth_dense, conf_dense};
-    {
-      // each map is copied to caller memory by the pool as soon as its D2H has landed (the D2H of map k+1 overlaps)
+    const char* names[4] = {"s3.depth", "s3.confidence", "s3.depth_dense", "s3.confidence_dense"};
+    TDM_CUDA(cudaSetDevice(device_));
+    const void* dstv[4] = {depth, conf, depth_dense, conf_dense};
+    if (all_page_locked(dstv, 4)) {
+      // Page-locked result buffers: the four maps are DMA'd from the device straight into them (they stay on the device
+      // until this handle's next forward, which cannot start before this call returns) - no staging copy.
+      for (int k = 0; k < 4; ++k)
+        TDM_CUDA(cudaMemcpyAsync(dst[k], fbuf(names[k]), n * 4, cudaMemcpyDeviceToHost, stream_));
+      TDM_CUDA(cudaStreamSynchronize(stream_));
+    } else {
+      if (!eager_d2h_) {   // the worker did not copy back: do it now
+        for (int k = 0; k < 4; ++k) {
+          TDM_CUDA(cudaMemcpyAsync(h_out_ + k * n, fbuf(names[k]), n * 4, cudaMemcpyDeviceToHost, stream_));
+          TDM_CUDA(cudaEventRecord(ev_out_[k], stream_));
+        }
+      }
+      // each map is copied to caller memory by the pool as soon as its D2H has landed
       std::vector<CopyPool::Job> jobs;
       TDM_CUDA(cudaEventSynchronize(ev_out_[3]));   // 4.9 MB over PCIe: ~0.1 ms; simpler than per-map hand-off
       constexpr int kSlices = 2;
@@ -282,7 +313,7 @@ class MvsnetEngine final : public MvsnetIface {
             const size_t e0 = n * sl / kSlices, e1 = n * (sl + 1) / kSlices;
             jobs.push_back({dst[k] + e0, h_out_ + k * n + e0, (e1 - e0) * 4, nullptr});
           }
-      pool_.run(jobs);
+      CopyPool::shared().run(jobs);
     }
     has_result_ = false;
   }
@@ -322,6 +353,8 @@ class MvsnetEngine final : public MvsnetIface {
     TDM_CUDA(cudaMemcpyAsync(out, tmp, n * 4, cudaMemcpyDeviceToHost, stream_));
     TDM_CUDA(cudaStreamSynchronize(stream_));
     cudaFree(tmp);
+    if (b.kind == 2 && kVolScale != 1.f)
+      for (long long i = 0; i < n; ++i) out[i] *= 1.f / kVolScale;   // report the volume in its own units
     return n;
   }
 
@@ -373,7 +406,10 @@ class MvsnetEngine final : public MvsnetIface {
 
  private:
   // ---------------------------------------------------------------- weights
-  void add_conv(const std::string& key, const FoldedConv& fc) {
+  void add_conv(const std::string& key, const FoldedConv& fc_in) {
+    FoldedConv fc = fc_in;
+    if (kVolScale != 1.f && key.size() > 6 && key.compare(key.size() - 6, 6, ".conv0") == 0 && key[0] == 's')
+      for (auto& v : fc.w) v *= 1.f / kVolScale;   // the stage's conv0 reads the volume stored as value * kVolScale (exact power of two)
     DevConv dc;
     dc.cin = fc.cin; dc.cout = fc.cout; dc.kd = fc.kd; dc.kh = fc.kh; dc.kw = fc.kw; dc.transposed = fc.transposed;
     TDM_CUDA(cudaMalloc(&dc.w, fc.w.size() * 4));
@@ -505,7 +541,12 @@ class MvsnetEngine final : public MvsnetIface {
 
   void upload_weights() {
     const std::string f = "feature_net.";
-    add_conv("f.conv0.0", fold_conv(wf_, f + "conv0.0.conv.weight", "", f + "conv0.0.bn", false, 8));
+    {
+      FoldedConv c00 = fold_conv(wf_, f + "conv0.0.conv.weight", "", f + "conv0.0.bn", false, 8);
+      if constexpr (kRawInput)   // the image is stored as exact u8/256 (k_preprocess_bgr<RAW255>): 256/255 lives in the weights
+        for (auto& v : c00.w) v = (float)((double)v * (256.0 / 255.0));
+      add_conv("f.conv0.0", c00);
+    }
     add_conv("f.conv0.1", fold_conv(wf_, f + "conv0.1.conv.weight", "", f + "conv0.1.bn", false));
     for (int b = 1; b <= 2; ++b)
       for (int i = 0; i < 3; ++i) {
@@ -1029,6 +1070,7 @@ class MvsnetEngine final : public MvsnetIface {
       }
     }
     p.view_aggregation = va_ ? 1 : 0;
+    p.vol_scale = kVolScale;
     if (va_) {
       const Gate& g = gates_[s - 1];
       for (int c = 0; c < g.C; ++c) p.gw1[c] = g.w1[c];
@@ -1175,7 +1217,7 @@ class MvsnetEngine final : public MvsnetIface {
       for (int v = 0; v < V; ++v) vp.v[v] = d_bgr_ + (size_t)v * H * W * 3;
       const long long n = (long long)V * H * W;
       rec_begin("preprocess", 3.0 * n + 8.0 * n * sizeof(TA), 0);
-      k_preprocess_bgr<TA><<<cdiv(n, 256), 256, 0, stream_>>>(vp, p8<TA>(bufs_.at("f.img")), V, H * W);
+      k_preprocess_bgr<TA, kRawInput><<<cdiv(n, 256), 256, 0, stream_>>>(vp, p8<TA>(bufs_.at("f.img")), V, H * W);
       TDM_CUDA(cudaGetLastError());
       rec_end();
     }
@@ -1280,12 +1322,16 @@ class MvsnetEngine final : public MvsnetIface {
       try {
         const size_t n = (size_t)H_ * W_;
         forward(false);
-        const char* names[4] = {"s3.depth", "s3.confidence", "s3.depth_dense", "s3.confidence_dense"};
-        for (int k = 0; k < 4; ++k) {
-          TDM_CUDA(cudaMemcpyAsync(h_out_ + k * n, fbuf(names[k]), n * 4, cudaMemcpyDeviceToHost, stream_));
-          TDM_CUDA(cudaEventRecord(ev_out_[k], stream_));
+        if (eager_d2h_) {
+          const char* names[4] = {"s3.depth", "s3.confidence", "s3.depth_dense", "s3.confidence_dense"};
+          for (int k = 0; k < 4; ++k) {
+            TDM_CUDA(cudaMemcpyAsync(h_out_ + k * n, fbuf(names[k]), n * 4, cudaMemcpyDeviceToHost, stream_));
+            TDM_CUDA(cudaEventRecord(ev_out_[k], stream_));
+          }
+        } else {
+          TDM_CUDA(cudaEventRecord(ev_out_[0], stream_));   // GetResult copies back itself (page-locked caller buffers)
         }
-        TDM_CUDA(cudaEventSynchronize(ev_out_[0]));   // result "ready" as soon as the first map is home; GetResult waits per map
+        wait_event_politely(ev_out_[0]);   // result "ready" as soon as the first map is home; GetResult waits per map
       } catch (const std::exception& e) {
         err = e.what();
       }
@@ -1300,7 +1346,32 @@ class MvsnetEngine final : public MvsnetIface {
     }
   }
 
+  // true when every non-null pointer is page-locked host memory the device can DMA from / into directly
+  static bool all_page_locked(const void* const* ptrs, int n) {
+    for (int i = 0; i < n; ++i) {
+      if (!ptrs[i]) return false;
+      cudaPointerAttributes at{};
+      if (cudaPointerGetAttributes(&at, ptrs[i]) != cudaSuccess) { cudaGetLastError(); return false; }
+      if (at.type != cudaMemoryTypeHost) return false;
+    }
+    return true;
+  }
+  // cudaEventSynchronize spins a core for the whole forward; with several handles per GPU and several ranks per host those
+  // spinning workers compete with the copy threads and the callers.  Poll with short sleeps instead (<= 20 us late).
+  static void wait_event_politely(cudaEvent_t ev) {
+    for (;;) {
+      const cudaError_t e = cudaEventQuery(ev);
+      if (e == cudaSuccess) return;
+      if (e != cudaErrorNotReady) TDM_CUDA(e);
+      std::this_thread::sleep_for(std::chrono::microseconds(20));
+    }
+  }
+
   struct Gate { int C = 0; float w1[64]; float b1 = 0, w2 = 0, b2 = 0; };
+  // mixed16: the cost volume is fp16 too, stored x 2^-5 (values reach ~1e4 and fp16 ends at 65504; bf16 has the range but only 8
+  // significant bits - the CPU study (profiles/r02_precision_study.md) attributes 1 % of mask IoU to that alone)
+  static constexpr float kVolScale = (std::is_same<TA, __half>::value && std::is_same<TV, __half>::value) ? 0.03125f : 1.f;
+  static constexpr bool kRawInput = sizeof(TA) == 2;   // 16-bit engines: exact u8/256 input, 256/255 folded into f.conv0.0
 
   int device_ = 0;
   cudaStream_t stream_ = nullptr;
@@ -1316,7 +1387,9 @@ class MvsnetEngine final : public MvsnetIface {
   unsigned char* d_bgr_ = nullptr;
   float* h_out_ = nullptr;
   cudaEvent_t ev_out_[4] = {nullptr, nullptr, nullptr, nullptr};
-  CopyPool pool_{3};   // + the calling thread = 4 copy lanes
+  cudaEvent_t ev_in_ = nullptr;
+  bool eager_d2h_ = true;   // worker copies the four maps into pinned staging right behind the forward (pageable callers);
+                            // 0: GetResult copies back itself - for callers that pass page-locked result buffers
   float c2w_[kMaxSrc + 1][16];
   float K_[27];
   float dmin_ = 0, dmax_ = 0, discard_ = 0;
@@ -1349,8 +1422,7 @@ class MvsnetEngine final : public MvsnetIface {
 };
 
 template <> template <> float MvsnetEngine<float, float>::from_host<float>(float v) { return v; }
-template <> template <> __half MvsnetEngine<__half, __nv_bfloat16>::from_host<__half>(float v) { return __float2half_rn(v); }
-template <> template <> __nv_bfloat16 MvsnetEngine<__half, __nv_bfloat16>::from_host<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+template <> template <> __half MvsnetEngine<__half, __half>::from_host<__half>(float v) { return __float2half_rn(v); }
 template <> template <> __nv_bfloat16 MvsnetEngine<__nv_bfloat16, __nv_bfloat16>::from_host<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
 
 MvsnetIface* make_mvsnet(const std::string& path, int precision, int device) {
@@ -1358,7 +1430,7 @@ MvsnetIface* make_mvsnet(const std::string& path, int precision, int device) {
   if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0)
     throw Error("tandem_b200: no CUDA device visible - this library has no CPU fallback");
   if (precision == 0) return new MvsnetEngine<float, float>(path, device);
-  if (precision == 1) return new MvsnetEngine<__half, __nv_bfloat16>(path, device);       // mixed16
+  if (precision == 1) return new MvsnetEngine<__half, __half>(path, device);               // mixed16 (fp16 volume x 2^-5)
   if (precision == 2) return new MvsnetEngine<__nv_bfloat16, __nv_bfloat16>(path, device);  // pure bf16
   throw Error("unknown precision");
 }

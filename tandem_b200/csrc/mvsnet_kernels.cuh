@@ -43,7 +43,12 @@ struct ViewPtrs {
   const unsigned char* v[16];
 };
 
-template <typename T>
+// RAW255: the 16-bit engines store u8/256 - exact in fp16 / bf16 (8 significant bits, power-of-two scale) - and fold the
+// remaining 256/255 of dr_mvsnet.cpp:203-210 into the first convolution's weights (which keeps the weights' magnitude, so
+// their hi/lo halves stay in the normal fp16 range): the network input carries no rounding error at all, where u8/255
+// rounded to 16 bit would inject a relative error of up to 2^-11 into every feature.  The fp32 parity engine divides as the
+// reference does.
+template <typename T, bool RAW255 = false>
 __global__ void k_preprocess_bgr(ViewPtrs src, P8<T> out, int V, int HW) {
   long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (i >= (long long)V * HW) return;
@@ -51,9 +56,13 @@ __global__ void k_preprocess_bgr(ViewPtrs src, P8<T> out, int V, int HW) {
   int p = (int)(i - (long long)v * HW);
   const unsigned char* s = src.v[v] + 3ll * p;
   float o[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  o[0] = __fdiv_rn((float)s[2], 255.0f);
-  o[1] = __fdiv_rn((float)s[1], 255.0f);
-  o[2] = __fdiv_rn((float)s[0], 255.0f);
+  if (RAW255) {
+    o[0] = (float)s[2] * 0.00390625f; o[1] = (float)s[1] * 0.00390625f; o[2] = (float)s[0] * 0.00390625f;
+  } else {
+    o[0] = __fdiv_rn((float)s[2], 255.0f);
+    o[1] = __fdiv_rn((float)s[1], 255.0f);
+    o[2] = __fdiv_rn((float)s[0], 255.0f);
+  }
   store_vec<T, 8>(out.p + out.pos(v, p / out.W, p % out.W), o);
 }
 
@@ -293,6 +302,12 @@ constexpr int kMaxSrc = 15;
 // Per-call parameters (homographies, depth range, filter rank) live in ONE device buffer that is refreshed by a small
 // async copy before every forward, so that the kernel arguments never change and the whole forward replays as a CUDA
 // graph.
+// fp16 volumes saturate instead of overflowing to inf (65504 * 32 = 2.1e6 in volume units; largest value seen: 9.5e3)
+template <typename TV> __device__ __forceinline__ float vol_store(float v) {
+  if constexpr (std::is_same<TV, __half>::value) return fminf(v, 65504.f);
+  else return v;
+}
+
 struct CvParams {
   int nsrc, D, H, W;
   float rot[kMaxSrc][9];
@@ -303,6 +318,8 @@ struct CvParams {
   float dot_unscale;   // 4096 / gw1_scale: undoes the fp16 path's operand scaling of the gate's dot product
   int view_aggregation;
   HypSpec hyp;
+  float vol_scale;     // the volume is STORED as value * vol_scale (1 for fp32 / bf16 volumes; 2^-5 for the fp16 volume of the
+                       // mixed16 engine, whose conv0 weights carry the inverse): a power of two, i.e. exact
 };
 
 // C = channels handled by ONE thread; CSPLIT adjacent lanes share a voxel and split its channels (C*CSPLIT in total):
@@ -489,7 +506,7 @@ k_cost_volume(P8<const T> feats /*views on the D axis, ref first*/, const float*
     for (int c0 = 0; c0 < C; c0 += 8) {
       float o8[8];
 #pragma unroll
-      for (int c = 0; c < 8; ++c) o8[c] = acc[c0 + c];
+      for (int c = 0; c < 8; ++c) o8[c] = vol_store<TV>(acc[c0 + c] * p.vol_scale);
       store_vec<TV, 8>(vol.p + op + (c0 >> 3) * vol.gs, o8);
     }
   }
@@ -633,7 +650,7 @@ k_cost_volume_va16(P8<const __half> feats, const float* __restrict__ dmin_map, P
     }
   }
   if (active) {
-    const float sc = 4096.f / (float)p.nsrc;
+    const float sc = 4096.f / (float)p.nsrc * p.vol_scale;
     TV* vbase_p = vol.p + (size_t)part * (C / 8) * vol.gs;
 #pragma unroll
     for (int k = 0; k < ND; ++k) {
@@ -645,8 +662,8 @@ k_cost_volume_va16(P8<const __half> feats, const float* __restrict__ dmin_map, P
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const float2 v = ACC16 ? __half22float2(acch[k][c0 / 2 + j]) : acc[k][c0 / 2 + j];
-            o8[2 * j] = v.x * sc;
-            o8[2 * j + 1] = v.y * sc;
+            o8[2 * j] = vol_store<TV>(v.x * sc);
+            o8[2 * j + 1] = vol_store<TV>(v.y * sc);
           }
           store_vec<TV, 8>(vbase_p + op + (size_t)(c0 >> 3) * vol.gs, o8);
         }

@@ -10,7 +10,7 @@ import os
 
 import numpy as np
 
-from ._lib import TandemError, check, lib
+from ._lib import TandemError, check, lib, pinned_empty
 
 _WEIGHTS_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "weights")
 PRECISION = {"fp32": 0, "mixed16": 1, "bf16": 2}
@@ -23,12 +23,11 @@ def default_weights(name="abl03_view_aggregation"):
 class DrMvsnetOutput:
     """dr_mvsnet.h:12-34."""
 
-    def __init__(self, height, width):
+    def __init__(self, height, width, pinned=False):
+        """pinned=True: the four maps live in page-locked memory (GetResult(out=...) then DMA's straight into them)."""
         self.height, self.width = height, width
-        self.depth = np.empty((height, width), np.float32)
-        self.confidence = np.empty((height, width), np.float32)
-        self.depth_dense = np.empty((height, width), np.float32)
-        self.confidence_dense = np.empty((height, width), np.float32)
+        mk = (lambda: pinned_empty((height, width), np.float32)) if pinned else (lambda: np.empty((height, width), np.float32))
+        self.depth, self.confidence, self.depth_dense, self.confidence_dense = mk(), mk(), mk(), mk()
 
 
 class DrMvsnet:
@@ -80,10 +79,14 @@ class DrMvsnet:
                    np.asarray(K_stages, np.float32).reshape(27), cam_to_worlds, depth_min, depth_max,
                    discard_percentage)
 
-    def GetResult(self):
+    def GetResult(self, out=None):
+        """Returns a fresh DrMvsnetOutput (the reference's ownership contract, dr_mvsnet.h:12-34), or fills `out` - a
+        DrMvsnetOutput the caller recycles, e.g. DrMvsnetOutput(h, w, pinned=True) for a zero-copy read-back."""
         if self._hw is None:
             raise TandemError("GetResult before CallAsync")
-        o = DrMvsnetOutput(*self._hw)
+        o = out if out is not None else DrMvsnetOutput(*self._hw)
+        if (o.height, o.width) != tuple(self._hw):
+            raise TandemError("GetResult(out=...): output has the wrong size")
         fp = ctypes.POINTER(ctypes.c_float)
         check(lib().tdm_mvsnet_get_result(self._h, o.depth.ctypes.data_as(fp), o.confidence.ctypes.data_as(fp),
                                           o.depth_dense.ctypes.data_as(fp), o.confidence_dense.ctypes.data_as(fp)))

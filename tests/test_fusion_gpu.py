@@ -153,6 +153,41 @@ def test_full_size_properties():
     assert np.median(np.abs(rd[ok] - depth[ok])) < 0.01
 
 
+def test_config3_shape_matches_oracle():
+    """BASELINE.json configs[2] shape: 640x480 depth maps of the config-3 scene (5 m room + 3 spheres, camera
+    circle r = 1 m, 2 mm noise, 2 % drop-outs) into the initDr-sized map (1 M buckets x 10, 1 M blocks, FullSystem.cpp:259-276):
+    block set / count / weights / colours exact, sdf <= 1e-5, render of each integrated view equal to the oracle's."""
+    hh, ww = 480, 640
+    intr = dict(fx=320.0, fy=320.0, cx=319.5, cy=239.5)
+    scene = RoomScene()
+    poses = circle_trajectory(3, radius=1.0)
+    frames = [scene.render(p, hh, ww, **intr, noise_sigma=0.002, dropout=0.02, seed=k) for k, p in enumerate(poses)]
+    for p in poses:
+        p[:3, 3] += np.float32(5.12)     # the 5.12 m cube of config 3; keeps block (0,0,0) out of the map (SURVEY Appendix B.2)
+    f, o = DrFusion(DrFusionOptions(height=hh, width=ww, **intr)), TsdfOracle(DrFusionOptions(height=hh, width=ww, **intr))
+    for k, ((bgr, depth), pose) in enumerate(zip(frames, poses)):
+        f.IntegrateScanAsync(bgr, depth, pose)
+        o.integrate(bgr, depth, pose)
+        f.RenderAsync([pose])
+        (rb,), (rd,) = f.GetRenderResult()
+        sg, so = f.stats(), o.stats()
+        assert sg["allocated_blocks"] == so["allocated_blocks"] and sg["visible_blocks"] == so["visible_blocks"]
+        assert sg["dropped_blocks"] == so["dropped_blocks"] == 0
+        if k == 0:
+            continue                      # the oracle's ray-cast takes ~8 s per 640x480 view: two views are compared
+        ob, od = o.render(pose)
+        hit_g, hit_o = rd > 0, od > 0
+        assert np.mean(hit_g != hit_o) <= 1e-3
+        both = hit_g & hit_o
+        assert both.mean() > 0.9
+        assert np.mean(np.abs(rd[both] - od[both])) <= 1e-3
+        assert np.mean(rd == od) > 0.999, f"rendered depth bit-equality {np.mean(rd == od)}"
+        assert np.mean(rb == ob) > 0.999
+    nblk, exact = _compare_maps(f, o)
+    print(f"config-3 shape: {nblk} blocks after 3 frames, sdf bit-exact fraction {exact:.6f}")
+    assert nblk > 20000 and exact > 0.9999
+
+
 def test_z_slab_partition_matches_single_volume():
     """two Z-slabs (each + 1 halo block) integrated from the same scans reproduce the single-volume map on
     their owned blocks bit-for-bit, and the per-pixel nearest-hit reduction of the two slab renders reproduces the
@@ -265,6 +300,41 @@ def test_mesh_call_order_capacity_and_regrow(monkeypatch):
     # empty boxes
     assert len(f.GetMesh(np.float32([5, 5, 5]), np.float32([5.5, 5.5, 5.5]))[0]) == 0
     assert len(f.GetMesh(lo, np.float32([lo[0], 1, 1]))[0]) == 0
+
+
+def test_mesh_state_machine_stale_and_blocking_paths(monkeypatch):
+    """Advisor r01: (1) scans integrated between ExtractMeshAsync and a GetMeshSync that has to grow its buffers must not be
+    classified against stale per-block offsets - the whole extraction is redone on the current volume; (2) the blocking
+    ExtractMesh path (GetMesh / SaveMeshToFile) never consumes an ExtractMeshAsync result and never re-uses a count-only
+    query for a different box or a changed volume."""
+    monkeypatch.setenv("TDM_MESH_INIT_TRIS", "64")
+    f, o = _mesh_pair(1)
+    lo, up = np.float32([-1.28] * 3), np.float32([1.28] * 3)
+    poses, frames = _scene_frames(3)
+    f.ExtractMeshAsync(lo, up)
+    for k in (1, 2):                                     # a full Integrate -> Render -> GetRenderResult cycle is legal here
+        f.IntegrateScanAsync(frames[k][0], frames[k][1], poses[k]); o.integrate(frames[k][0], frames[k][1], poses[k])
+        f.RenderAsync([poses[k]]); f.GetRenderResult()
+    vg, cg = f.GetMeshSync()                             # count-only query inside, then the grow path: re-extracted
+    vo, co = o.extract_mesh(lo, up)
+    assert len(vg) == len(vo) > 64 * 3
+    assert np.array_equal(_sorted_tris(vg, cg), _sorted_tris(vo, co))
+    # blocking path while an asynchronous result is pending: rejected, and the pending result survives
+    f.ExtractMeshAsync(lo, up)
+    with pytest.raises(Exception):
+        f.GetMesh(lo, up)
+    v2, c2 = f.GetMeshSync()
+    assert np.array_equal(_sorted_tris(v2, c2), _sorted_tris(vo, co))
+    # a count-only query of one box followed by a copy call for another box: the second box is what comes back
+    import ctypes
+    from tandem_b200._lib import lib
+    fp = ctypes.POINTER(ctypes.c_float)
+    n_full = lib().tdm_fusion_extract_mesh(f._h, lo.ctypes.data_as(fp), up.ctypes.data_as(fp), None, None, 0)
+    up2 = np.float32([0.0, 1.28, 1.28])
+    vh, ch = f.GetMesh(lo, up2)
+    voh, coh = o.extract_mesh(lo, up2)
+    assert 0 < len(vh) == len(voh) < n_full
+    assert np.array_equal(_sorted_tris(vh, ch), _sorted_tris(voh, coh))
 
 
 def test_mesh_full_size_properties():

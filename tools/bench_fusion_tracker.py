@@ -113,3 +113,47 @@ wall_two = (time.perf_counter() - t0) / 200 * 1e6
 print(json.dumps({"what": "tracker ours", "n_points": c["n"], "kernel_us(fused, device)": ms / 200 * 1e3,
                   "wall_us(fused call incl sync)": wall_fused, "wall_us(calcRes+calcG calls)": wall_two,
                   "algorithmic_MB": (16 * c["n"] + 12 * c["w"] * c["h"] + 416) / 1e6}))
+
+# ---- comparators the north-star names: the tandem CPU tracker on this box's host cores (single thread, as
+# the reference: CoarseTracker::calcRes + calcGSSSE, restated in oracle/tracker_oracle.c and pinned to the reference kernels) and
+# the reference's own CUDA kernels (calcResKernelNew + calcGKernel<float>, compiled unmodified) on this GPU, same inputs.
+from oracle.cpu import TrackerOracle  # noqa: E402  (comparator only; never on the product path)
+orc = TrackerOracle(c["w"], c["h"])
+orc.setK(c["w"], c["h"], c["fx"], c["fy"], c["cx"], c["cy"])
+orc.setReference(c["n"], c["pc_u"], c["pc_v"], c["pc_idepth"], c["pc_color"], c["ref_exposure"], c["ref_aff"])
+orc.setNew(c["dInew"])
+orc.calcRes(c["refToNew"], c["new_exposure"], c["new_aff"], c["cutoffTH"]); orc.calcG(c["new_exposure"], c["new_aff"])
+reps = 10
+t0 = time.perf_counter()
+for _ in range(reps):
+    orc.calcRes(c["refToNew"], c["new_exposure"], c["new_aff"], c["cutoffTH"])
+t1 = time.perf_counter()
+for _ in range(reps):
+    orc.calcG(c["new_exposure"], c["new_aff"])
+t2 = time.perf_counter()
+cpu_res_us, cpu_g_us = (t1 - t0) / reps * 1e6, (t2 - t1) / reps * 1e6
+print(json.dumps({"what": "tracker CPU baseline (oracle/tracker_oracle.c = CoarseTracker::calcRes + calcGSSSE, gcc -O2, 1 thread)",
+                  "n_points": c["n"], "calcRes_us": cpu_res_us, "calcG_us": cpu_g_us, "pair_us": cpu_res_us + cpu_g_us,
+                  "host_threads_used": 1, "host_threads_available": os.cpu_count(),
+                  "ours_kernel_speedup": (cpu_res_us + cpu_g_us) / (ms / 200 * 1e3)}))
+trk_lib = os.path.join(ROOT, "oracle", "_ref", "libtracker_ref.so")
+if os.path.exists(trk_lib):
+    l = ctypes.CDLL(trk_lib)
+    if hasattr(l, "ref_tracker_eval_timed"):
+        aff = orc._aff(c["new_exposure"], c["new_aff"])
+        T = np.ascontiguousarray(c["refToNew"], np.float32)
+        Ki = np.array([1.0 / c["fx"], 0, -c["cx"] / c["fx"], 0, 1.0 / c["fy"], -c["cy"] / c["fy"], 0, 0, 1], np.float32)
+        o7, o45 = np.zeros(7, np.float32), np.zeros(45, np.float32)
+        mr, mg = ctypes.c_float(0), ctypes.c_float(0)
+        fl = ctypes.c_float
+        rc = l.ref_tracker_eval_timed(c["w"], c["h"], fl(c["fx"]), fl(c["fy"]), fl(c["cx"]), fl(c["cy"]), T.ctypes.data_as(_fp),
+                                      Ki.ctypes.data_as(_fp), fl(aff[0]), fl(aff[1]), fl(c["ref_aff"][1]), fl(9.0), fl(c["cutoffTH"]),
+                                      c["n"], c["pc_u"].ctypes.data_as(_fp), c["pc_v"].ctypes.data_as(_fp),
+                                      c["pc_idepth"].ctypes.data_as(_fp), c["pc_color"].ctypes.data_as(_fp),
+                                      np.ascontiguousarray(c["dInew"]).ctypes.data_as(_fp), o7.ctypes.data_as(_fp),
+                                      o45.ctypes.data_as(_fp), None, 200, ctypes.byref(mr), ctypes.byref(mg))
+        print(json.dumps({"what": "tracker reference kernels (calcResKernelNew + calcGKernel<float>, unmodified, sm_100a) on this GPU",
+                          "rc": rc, "n_points": c["n"], "calcRes_kernel_us(device)": mr.value * 1e3, "calcG_kernel_us(device)": mg.value * 1e3,
+                          "pair_us(device)": (mr.value + mg.value) * 1e3, "ours_fused_kernel_us(device)": ms / 200 * 1e3,
+                          "ours_speedup": (mr.value + mg.value) * 1e3 / (ms / 200 * 1e3),
+                          "note": "device time of the kernels + the per-call output memsets only; the reference's host wrapper adds a blocking sync and D2H per call (cuda_coarse_tracker.cpp:195-356)"}))
