@@ -197,11 +197,11 @@ def time_gpu_reference(win, local, steps=10, warmup=3):
                 out = run()
             e1.record()
             torch.cuda.synchronize(local)
-            res[tf32] = (e0.elapsed_time(e1) / steps, out[2]["depth_dense"].float().cpu().numpy())
+            res[tf32] = (e0.elapsed_time(e1) / steps, out[2]["depth_dense"].float().cpu().numpy(), out[2]["mask"].cpu().numpy())
         ms = res[False][0]
         return {"value": 1e3 / ms, "unit": "keyframes/s", "ms_per_step": ms, "steps": steps, "warmup": warmup,
                 "tf32_value": 1e3 / res[True][0], "tf32_ms_per_step": res[True][0],
-                "depth_dense_gpu": res[False][1],
+                "depth_dense_gpu": res[False][1], "mask_gpu": res[False][2], "mask_gpu_tf32": res[True][2], "depth_dense_gpu_tf32": res[True][1],
                 "what": "oracle/mvsnet_oracle.py (the reference graph, pinned) in eager PyTorch on cuda: cuDNN fp32 (value: TF32 off; "
                         "tf32_value: TF32 allowed), cudnn.benchmark on, inputs resident - the compute path of the reference's libdr "
                         "module.forward (dr_mvsnet.cpp:292-294)"}
@@ -313,6 +313,10 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gpu-reference", action="store_true", help="skip the eager-PyTorch/cuDNN comparator record")
     ap.add_argument("--no-bind", action="store_true", help="do not bind ranks to their GPU's NUMA node (multi-GPU runs)")
+    ap.add_argument("--workload", default="mvsnet", choices=["mvsnet", "slab_tsdf"],
+                    help="mvsnet: the BASELINE.json metric (default).  slab_tsdf: BASELINE configs[4], TSDF half - ONE 1024^3 volume "
+                         "partitioned into Z-slabs over the ranks, integrate + slab-clipped ray-cast + nearest-hit all-reduce per frame "
+                         "(strong scaling; a step = one 640x480 depth map)")
     ap.add_argument("--inflight", type=int, default=8, choices=[1, 2, 3, 4, 5, 6, 7, 8],
                     help="independent windows in flight per GPU (n DrMvsnet handles, one stream each, used round-robin) in both legs")
     ap.add_argument("--e2e-inflight", type=int, default=4, choices=[1, 2, 3, 4, 5, 6, 7, 8],
@@ -323,6 +327,19 @@ def main():
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3) if a.impl == "ours" else a.warmup
     host_malloc = tune_host_malloc()
+    if a.workload == "slab_tsdf":
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import bench_slab_tsdf
+        r = bench_slab_tsdf.main(["--frames", str(min(a.steps, 48)), "--warmup", str(a.warmup)])
+        if r is not None:
+            print(json.dumps({"metric": "TSDF depth maps integrated + ray-cast per second (1024^3 voxels @ 1 cm, Z-slab partition)",
+                              "value": r["frames_per_s"], "unit": "frames/s", "n_gpus": r["n_gpus"], "steps": r["frames"],
+                              "warmup": a.warmup, "ms_per_step": r["ms_per_frame(max over ranks, wall incl. H2D/D2H)"],
+                              "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32 sdf / u8 colour + weight",
+                              "data": "synthetic 10 m room + 3 spheres, 640x480 depth maps (seeded noise, 2 % drop-outs)",
+                              "config": {"workload": "BASELINE configs[4] TSDF half: one 10.24 m volume in Z-slabs over the ranks"},
+                              "detail": r}))
+        return 0
 
     if a.impl == "reference":
         rank = int(os.environ.get("RANK", 0))
@@ -501,6 +518,18 @@ def main():
             if dd is not None:   # our output vs the comparator's on the same window (sanity of both arms)
                 msk = dd > 0
                 gpu_ref["abs_rel_ours_vs_gpu_reference"] = float(np.mean(np.abs(dd[msk] - out.depth_dense[msk]) / dd[msk]))
+                # how well do the reference's OWN two arithmetic paths agree?  (golden = its CPU fp32 model output)
+                gg = np.load(os.path.join(ROOT, "tests", "golden", "sample_640x480.npz"))
+                gold, gmask = gg["abl03_stage3_depth_dense"], gg["abl03_stage3_depth"] == 0
+                iou = lambda a_, b_: float(np.logical_and(a_, b_).sum() / max(np.logical_or(a_, b_).sum(), 1))
+                gm = gold > 0
+                gpu_ref["abs_rel_vs_cpu_reference"] = float(np.mean(np.abs(gold[gm] - dd[gm]) / gold[gm]))
+                gpu_ref["mask_iou_vs_cpu_reference"] = iou(gpu_ref.pop("mask_gpu"), gmask)
+                dt = gpu_ref.pop("depth_dense_gpu_tf32")
+                gpu_ref["tf32_abs_rel_vs_cpu_reference"] = float(np.mean(np.abs(gold[gm] - dt[gm]) / gold[gm]))
+                gpu_ref["tf32_mask_iou_vs_cpu_reference"] = iou(gpu_ref.pop("mask_gpu_tf32"), gmask)
+                gpu_ref["ours_abs_rel_vs_cpu_reference"] = float(np.mean(np.abs(gold[gm] - out.depth_dense[gm]) / gold[gm]))
+                gpu_ref["ours_mask_iou_vs_cpu_reference"] = iou(out.depth == 0, gmask)
                 gpu_ref["speedup_device"] = value / gpu_ref["value"]
                 gpu_ref["speedup_single_window"] = (1e3 / ms_single) / gpu_ref["value"]
                 gpu_ref["speedup_device_vs_tf32"] = value / gpu_ref["tf32_value"]

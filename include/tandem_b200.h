@@ -147,6 +147,12 @@ int tdm_fusion_set_slab(tdm_fusion* h, int z_block_lo, int z_block_hi);
  * (NCCL, in place) - tdm_fusion_unpack_keys turns reduced keys back into a depth map and a bgr image in HOST buffers. */
 int tdm_fusion_render_keys_device(tdm_fusion* h, int render_index, long long** keys_dev);
 int tdm_fusion_unpack_keys(tdm_fusion* h, const long long* keys_dev, float* depth_out, unsigned char* bgr_out);
+/* The CUDA stream (cudaStream_t) all work of this handle is ordered on.  With tdm_fusion_set_option(h, "slab_exchange", 1)
+ * the ray-cast writes the keys itself (no pack kernel, no per-slab D2H, GetRenderResult does not wait) and
+ * tdm_fusion_render_keys_device returns without a host sync: the caller enqueues its MIN all-reduce ON THIS STREAM (e.g.
+ * torch.cuda.ExternalStream + torch.distributed, or ncclAllReduce directly) and tdm_fusion_unpack_keys behind it - one
+ * host sync per frame, in unpack_keys. */
+int tdm_fusion_stream(tdm_fusion* h, void** stream_out);
 /* Mesh (dr_fusion.h:56-68; TsdfVolume::ExtractMeshAsync / GetMeshSync / ExtractMesh, tsdf_volume.cu:739-839; kernel
  * marching_cubes/mesh_extractor.cu:244-265): marching cubes over the cells of the box [lower, upper) at voxel spacing.
  * Output layout of GetMeshSync: vertices as xyz float triples, colours as rgb float triples in [0,1], 3 consecutive

@@ -92,6 +92,7 @@ def _declare(l):
         "tdm_fusion_last_mesh_ms": (i, [vp, fp]),
         "tdm_fusion_render_keys_device": (i, [vp, i, P(vp)]),
         "tdm_fusion_unpack_keys": (i, [vp, vp, fp, vp]),
+        "tdm_fusion_stream": (i, [vp, P(vp)]),
         "tdm_debug_mesh_axis_table": (i, [f, f, f, ip, fp, ip, ip, i]),
         "tdm_fusion_set_option": (i, [vp, cp, i]),
         "tdm_fusion_last_alloc_ms": (i, [vp, fp]),

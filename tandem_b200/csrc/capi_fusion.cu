@@ -91,6 +91,13 @@ int tdm_fusion_render_keys_device(tdm_fusion* h, int render_index, long long** k
   return TDM_OK;
   TDM_API_END
 }
+int tdm_fusion_stream(tdm_fusion* h, void** stream_out) {
+  TDM_API_BEGIN
+  TDM_CHECK(h && stream_out, "null argument");
+  *stream_out = h->impl->stream();
+  return TDM_OK;
+  TDM_API_END
+}
 int tdm_fusion_unpack_keys(tdm_fusion* h, const long long* keys_dev, float* depth_out, unsigned char* bgr_out) {
   TDM_API_BEGIN
   TDM_CHECK(h && keys_dev && depth_out && bgr_out, "null argument");

@@ -44,12 +44,30 @@ struct FusionDev {
   int4* list;                // compact list of allocated blocks (x,y,z,ptr)
   int* counters;             // [0] #blocks allocated, [1] dropped, [2] visible (last scan), [3] new this scan
   int slab_lo, slab_hi;      // Z-slab partition (block z in [slab_lo, slab_hi) is kept), default: everything
+  float r_vs, r_fx, r_fy;    // RN(1 / voxel_size), RN(1 / fx), RN(1 / fy) for cdiv_ (ray-cast only)
 };
 
 __device__ __forceinline__ float mul_(float a, float b) { return __fmul_rn(a, b); }
 __device__ __forceinline__ float add_(float a, float b) { return __fadd_rn(a, b); }
 __device__ __forceinline__ float sub_(float a, float b) { return __fsub_rn(a, b); }
 __device__ __forceinline__ float div_(float a, float b) { return __fdiv_rn(a, b); }
+
+// Correctly rounded x / d for a divisor that is constant over the kernel, from its correctly rounded reciprocal r = RN(1/d):
+//   q0 = RN(x r);  e = x - q0 d (exact, one FMA);  q = RN(q0 + e r)
+// is RN(x / d) whenever no intermediate under- / overflows and d's significand is not all ones (Markstein's theorem for
+// FMA division; tests/test_abi.py::test_constant_division_is_correctly_rounded checks it exhaustively for d = 0.01f and on 1e8
+// random pairs).  Outside the safe range, and for the excluded divisors (FAST is then false on the host), the IEEE division
+// is used.  3 instructions instead of the ~25 of div.rn.f32's software expansion; the ray-cast does 11 such divisions per
+// sample (by voxel_size, fx, fy), a third of its instruction count.  Results are bit-identical to div_ by construction.
+template <bool FAST>
+__device__ __forceinline__ float cdiv_(float x, float d, float r) {
+  if constexpr (!FAST) return __fdiv_rn(x, d);
+  const float ax = fabsf(x);
+  if (!(ax > 1e-18f && ax < 1e18f)) return __fdiv_rn(x, d);   // zeros, denormal-range and huge values, NaN
+  const float q0 = __fmul_rn(x, r);
+  const float e = __fmaf_rn(-q0, d, x);
+  return __fmaf_rn(e, r, q0);
+}
 
 __device__ __forceinline__ float3 xform(const Mat4& T, float3 v) {  // matrix_utils.h:914-921 (w == 1)
   const float* m = T.m;
@@ -68,6 +86,16 @@ __device__ __forceinline__ float3 get_point3d(const tdm_fusion_options& o, int i
   p.z = depth;
   p.x = div_(mul_(sub_((float)u, o.cx), p.z), o.fx);
   p.y = div_(mul_(sub_((float)v, o.cy), p.z), o.fy);
+  return p;
+}
+template <bool FAST>
+__device__ __forceinline__ float3 get_point3d_c(const FusionDev& d, int i, float depth) {  // get_point3d with constant-divisor division
+  const tdm_fusion_options& o = d.o;
+  const int v = i / o.width, u = i - o.width * v;
+  float3 p;
+  p.z = depth;
+  p.x = cdiv_<FAST>(mul_(sub_((float)u, o.cx), p.z), o.fx, d.r_fx);
+  p.y = cdiv_<FAST>(mul_(sub_((float)v, o.cy), p.z), o.fy, d.r_fy);
   return p;
 }
 __device__ __forceinline__ int2 project(const tdm_fusion_options& o, float3 p) {  // utils.h:103-108
@@ -137,8 +165,11 @@ __device__ __forceinline__ int find_block(const FusionDev& d, int x, int y, int 
   if (x <= -kKeyBias || x >= kKeyBias || y <= -kKeyBias || y >= kKeyBias || z <= -kKeyBias || z >= kKeyBias) return -1;
   const unsigned long long key = pack_key(x, y, z);
   const long long b = hash_bucket(d.o, x, y, z);
-  for (int i = 0; i < d.o.bucket_size; ++i)
-    if (d.keys[b + i] == key) return d.ptrs[b + i];
+  for (int i = 0; i < d.o.bucket_size; ++i) {
+    const unsigned long long k = d.keys[b + i];
+    if (k == key) return d.ptrs[b + i];
+    if (k == kEmptyKey) return -1;   // inserts fill a bucket front to back and nothing is ever removed: a free slot ends the search
+  }
   return -1;
 }
 
@@ -411,10 +442,12 @@ __device__ __forceinline__ uint2 voxel_at(const FusionDev& d, int gx, int gy, in
   if (ptr < 0) return make_uint2(0u, 0u);
   return __ldg(d.voxels + (size_t)ptr * 512 + (gx & 7) * 64 + (gy & 7) * 8 + (gz & 7));
 }
-template <class Cache>
+// COLOR = false: the marching steps only consume the interpolated sdf and the centre voxel's weight; the colour blend (8 corners
+// x 3 channels of unpack / convert / multiply-add: a fifth of the sample's instructions) is only evaluated for the final hit.
+template <class Cache, bool COLOR = true, bool FAST = false>
 __device__ uint2 get_interpolated_shared(const FusionDev& d, float3 p, Cache& bc) {
-  const float s = d.o.voxel_size;
-  const float3 vp = make_float3(div_(p.x, s), div_(p.y, s), div_(p.z, s));
+  const float s = d.o.voxel_size, rs = d.r_vs;
+  const float3 vp = make_float3(cdiv_<FAST>(p.x, s, rs), cdiv_<FAST>(p.y, s, rs), cdiv_<FAST>(p.z, s, rs));
   const uint2 v0 = voxel_at(d, w2g_axis(vp.x, p.x), w2g_axis(vp.y, p.y), w2g_axis(vp.z, p.z), bc);
   if ((v0.y >> 24) == 0) return v0;
   const float hs = div_(s, 2.0f);
@@ -423,9 +456,9 @@ __device__ uint2 get_interpolated_shared(const FusionDev& d, float3 p, Cache& bc
   const float ux = sub_(1.f, wx), uy = sub_(1.f, wy), uz = sub_(1.f, wz);
   // the two voxel indices per axis that the corners pd + {0, s} round to
   const float ax0 = add_(pd.x, 0.f), ax1 = add_(pd.x, s), ay0 = add_(pd.y, 0.f), ay1 = add_(pd.y, s), az0 = add_(pd.z, 0.f), az1 = add_(pd.z, s);
-  const int gx0 = w2g_axis(div_(ax0, s), ax0), gx1 = w2g_axis(div_(ax1, s), ax1);
-  const int gy0 = w2g_axis(div_(ay0, s), ay0), gy1 = w2g_axis(div_(ay1, s), ay1);
-  const int gz0 = w2g_axis(div_(az0, s), az0), gz1 = w2g_axis(div_(az1, s), az1);
+  const int gx0 = w2g_axis(cdiv_<FAST>(ax0, s, rs), ax0), gx1 = w2g_axis(cdiv_<FAST>(ax1, s, rs), ax1);
+  const int gy0 = w2g_axis(cdiv_<FAST>(ay0, s, rs), ay0), gy1 = w2g_axis(cdiv_<FAST>(ay1, s, rs), ay1);
+  const int gz0 = w2g_axis(cdiv_<FAST>(az0, s, rs), az0), gz1 = w2g_axis(cdiv_<FAST>(az1, s, rs), az1);
   uint2 c[8];   // corner order of the reference: 000,100,010,001,110,011,101,111
   const bool one_block = gx1 == gx0 + 1 && gy1 == gy0 + 1 && gz1 == gz0 + 1 && (gx0 & 7) != 7 && (gy0 & 7) != 7 && (gz0 & 7) != 7;
   if (one_block) {
@@ -451,21 +484,36 @@ __device__ uint2 get_interpolated_shared(const FusionDev& d, float3 p, Cache& bc
     if ((v.y >> 24) == 0) v = v0;
     const float w = mul_(mul_(ox[k] ? wx : ux, oy[k] ? wy : uy), oz[k] ? wz : uz);
     dist = add_(dist, mul_(w, __uint_as_float(v.x)));
+    if constexpr (COLOR) {
 #pragma unroll
-    for (int q = 0; q < 3; ++q) cf[q] = add_(cf[q], mul_(w, (float)((v.y >> (8 * q)) & 0xFF)));
+      for (int q = 0; q < 3; ++q) cf[q] = add_(cf[q], mul_(w, (float)((v.y >> (8 * q)) & 0xFF)));
+    }
   }
   unsigned col = 0;
+  if constexpr (COLOR) {
 #pragma unroll
-  for (int q = 0; q < 3; ++q) col |= ((unsigned)cf[q] & 0xFF) << (8 * q);
+    for (int q = 0; q < 3; ++q) col |= ((unsigned)cf[q] & 0xFF) << (8 * q);
+  }
   return make_uint2(__float_as_uint(dist), col | (v0.y & 0xFF000000u));
 }
 
 // one ray per thread, shared-index sampling (the default ray-cast).  The kernel is latency-bound (a step is one long dependent
 // chain: divide -> convert -> address -> load -> interpolate -> next t) and rays differ a lot in length, so small CTAs (8x8
 // pixels) at high residency balance better than 16x16 ones: TW x TH pixel tiles, MINB CTAs per SM requested.
-template <int TW, int TH, int MINB>
+// SLAB (Z-slab partition): this rank stores only the blocks z in [slab_lo, slab_hi), so every sample whose
+// trilinear neighbourhood lies outside that z range reads "no voxel" (weight 0) and advances the ray by exactly tau.  Those
+// samples are not taken: before the ray enters the slab's z range `cur` is advanced by the same fp32 additions (cur += tau)
+// without touching memory, and once the ray has left the range it can never hit again (world z is monotone along a ray), so
+// it ends as a miss.  The samples that ARE taken sit at the same positions as in the unclipped march of this slab volume ->
+// bit-identical slab renders at 1/N of the sampling work per rank.  keys != nullptr: the packed nearest-hit key
+// (depth bits << 24 | colour, miss = +inf) is written straight from the ray's registers (the exchange step's operand).
+__device__ __forceinline__ long long pack_hit_key(float depth, unsigned bgr24) {
+  const long long bits = depth > 0.f ? (long long)__float_as_uint(depth) : 0x7F800000ll;
+  return (bits << 24) | (long long)(depth > 0.f ? (bgr24 & 0xFFFFFFu) : 0u);
+}
+template <int TW, int TH, int MINB, bool SLAB, bool FAST>
 __global__ void __launch_bounds__(TW * TH, MINB)
-k_raycast_shared(FusionDev d, Mat4 T, unsigned char* __restrict__ bgr_out, float* __restrict__ depth_out) {
+k_raycast_shared(FusionDev d, Mat4 T, unsigned char* __restrict__ bgr_out, float* __restrict__ depth_out, long long* __restrict__ keys) {
   const tdm_fusion_options& o = d.o;
   const int x = blockIdx.x * TW + (threadIdx.x % TW);
   const int y = blockIdx.y * TH + (threadIdx.x / TW);
@@ -474,21 +522,44 @@ k_raycast_shared(FusionDev d, Mat4 T, unsigned char* __restrict__ bgr_out, float
   Cache1 bc;
   bc.init();
   float cur = 0.f;
+  float t_exit = FLT_MAX;
+  if constexpr (SLAB) {
+    // world z of the sample at ray parameter cur: zw = a * cur + b (linear model of xform(T, get_point3d(i, cur)).z; its
+    // rounding differs from the exact evaluation by ~1e-6 m, covered by the half-voxel slack below).  A sample reads voxels
+    // within +-1.5 voxels of its own position, a block b holds the voxels [8b - 0.5, 8b + 7.5) * s.
+    const float a = T.m[8] * ((float)x - o.cx) / o.fx + T.m[9] * ((float)y - o.cy) / o.fy + T.m[10], b = T.m[11];
+    const float s = o.voxel_size;
+    const float zlo = ((float)d.slab_lo * 8.f - 2.5f) * s, zhi = ((float)d.slab_hi * 8.f + 2.5f) * s;
+    float t_enter = 0.f;
+    if (fabsf(a) < 1e-12f) {
+      if (b < zlo || b > zhi) t_enter = FLT_MAX;                     // parallel to the slab and outside it
+    } else {
+      const float t0 = (zlo - b) / a, t1 = (zhi - b) / a;
+      t_enter = fminf(t0, t1);
+      t_exit = fmaxf(t0, t1);
+    }
+    while (cur < t_enter && cur < o.max_sensor_depth) cur = add_(cur, o.truncation_distance);   // what the skipped samples would do
+  }
   int guard = 0;
+  bool hit = false;
   while (cur < o.max_sensor_depth && guard++ < 100000) {
-    const uint2 v = get_interpolated_shared(d, xform(T, get_point3d(o, i, cur)), bc);
+    if (SLAB && cur > t_exit) break;
+    const uint2 v = get_interpolated_shared<Cache1, false, FAST>(d, xform(T, get_point3d_c<FAST>(d, i, cur)), bc);
     const unsigned w = v.y >> 24;
     const float sdf = __uint_as_float(v.x);
     cur = add_(cur, w == 0 ? o.truncation_distance : sdf);
-    if (w != 0 && sdf < o.voxel_size) break;
+    if (w != 0 && sdf < o.voxel_size) { hit = true; break; }
   }
-  if (cur < o.max_sensor_depth) {
-    const uint2 v = get_interpolated_shared(d, xform(T, get_point3d(o, i, cur)), bc);
+  // (un-clipped march: a ray that runs out of range ends with cur >= max_sensor_depth; the slab march may also stop behind the slab)
+  if (SLAB ? (hit && cur < o.max_sensor_depth) : (cur < o.max_sensor_depth)) {
+    const uint2 v = get_interpolated_shared<Cache1, true, FAST>(d, xform(T, get_point3d_c<FAST>(d, i, cur)), bc);
     bgr_out[3 * i] = v.y & 0xFF; bgr_out[3 * i + 1] = (v.y >> 8) & 0xFF; bgr_out[3 * i + 2] = (v.y >> 16) & 0xFF;
     depth_out[i] = cur;
+    if (keys) keys[i] = pack_hit_key(cur, v.y);
   } else {
     bgr_out[3 * i] = bgr_out[3 * i + 1] = bgr_out[3 * i + 2] = 0;
     depth_out[i] = 0.f;
+    if (keys) keys[i] = pack_hit_key(0.f, 0u);
   }
 }
 
@@ -679,6 +750,20 @@ class FusionImpl final : public FusionIface {
     d_.o = o;
     d_.slab_lo = INT_MIN;
     d_.slab_hi = INT_MAX;
+    {
+      // reciprocals for cdiv_: host IEEE division = correctly rounded (the file is built with -ffp-contract=off, no fast-math)
+      volatile float one = 1.0f;
+      d_.r_vs = one / o.voxel_size; d_.r_fx = one / o.fx; d_.r_fy = one / o.fy;
+      auto ok = [](float d) {
+        unsigned u;
+        std::memcpy(&u, &d, 4);
+        const unsigned ex = (u >> 23) & 0xFF, man = u & 0x7FFFFF;
+        return d > 0.f && ex > 40 && ex < 214 && man != 0x7FFFFF;   // 2^-87 < d < 2^87, significand not all ones
+      };
+      fast_div_ok_ = ok(o.voxel_size) && ok(o.fx) && ok(o.fy);
+      const char* e = getenv("TDM_FAST_DIV");
+      fast_div_ = fast_div_ok_ && !(e && e[0] == '0');
+    }
     n_entries_ = (long long)o.num_buckets * o.bucket_size;
     int lo, hi;
     TDM_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
@@ -740,14 +825,29 @@ class FusionImpl final : public FusionIface {
       throw Error("call order is IntegrateScanAsync -> RenderAsync -> GetRenderResult (tsdf_volume.cu:520-525)");
     TDM_CUDA(cudaSetDevice(device_));
     const size_t npx = (size_t)d_.o.height * d_.o.width;
-    TDM_CUDA(cudaEventSynchronize(ev_int_));  // previous scan has left the pinned staging buffers
-    std::memcpy(h_bgr_in_, bgr, npx * 3);
-    std::memcpy(h_depth_in_, depth, npx * 4);
     std::memcpy(pose_.m, pose, 64);
     if (!inv4_f32(pose_.m, pose_inv_.m)) throw Error("camera pose is singular");
-    TDM_CUDA(cudaMemcpyAsync(d_bgr_in_, h_bgr_in_, npx * 3, cudaMemcpyHostToDevice, stream_));
-    TDM_CUDA(cudaMemcpyAsync(d_depth_in_, h_depth_in_, npx * 4, cudaMemcpyHostToDevice, stream_));
-    launch_integrate();
+    auto page_locked = [](const void* p) {
+      cudaPointerAttributes at{};
+      if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+      return at.type == cudaMemoryTypeHost;
+    };
+    if (page_locked(bgr) && page_locked(depth)) {
+      // page-locked caller buffers: DMA straight from them; they are only ours during this call (tsdf_volume.cu:542-543
+      // copies before returning), so wait for the two DMAs (2.15 MB, ~45 us) - cheaper than the staging memcpy it replaces
+      TDM_CUDA(cudaMemcpyAsync(d_bgr_in_, bgr, npx * 3, cudaMemcpyHostToDevice, stream_));
+      TDM_CUDA(cudaMemcpyAsync(d_depth_in_, depth, npx * 4, cudaMemcpyHostToDevice, stream_));
+      TDM_CUDA(cudaEventRecord(ev_int_, stream_));
+      launch_integrate();
+      TDM_CUDA(cudaEventSynchronize(ev_int_));
+    } else {
+      TDM_CUDA(cudaEventSynchronize(ev_int_));  // previous scan has left the pinned staging buffers
+      std::memcpy(h_bgr_in_, bgr, npx * 3);
+      std::memcpy(h_depth_in_, depth, npx * 4);
+      TDM_CUDA(cudaMemcpyAsync(d_bgr_in_, h_bgr_in_, npx * 3, cudaMemcpyHostToDevice, stream_));
+      TDM_CUDA(cudaMemcpyAsync(d_depth_in_, h_depth_in_, npx * 4, cudaMemcpyHostToDevice, stream_));
+      launch_integrate();
+    }
     TDM_CUDA(cudaEventRecord(ev_int_, stream_));
     have_scan_ = true;
     ++volume_epoch_;   // a pending mesh extracted before this scan no longer describes the volume
@@ -771,7 +871,7 @@ class FusionImpl final : public FusionIface {
     if (next_ != kGet) throw Error("call order is IntegrateScanAsync -> RenderAsync -> GetRenderResult (tsdf_volume.cu:703-708)");
     if (n != n_rendered_) throw Error("GetRenderResult: wrong number of outputs");
     TDM_CUDA(cudaSetDevice(device_));
-    TDM_CUDA(cudaEventSynchronize(ev_render_));
+    if (!slab_exchange_) TDM_CUDA(cudaEventSynchronize(ev_render_));   // exchange mode: nothing was copied back, nothing to wait for
     const size_t npx = (size_t)d_.o.height * d_.o.width;
     for (int i = 0; i < n; ++i) {
       bgr[i] = h_bgr_out_[free_half_] + (size_t)i * npx * 3;
@@ -868,6 +968,9 @@ class FusionImpl final : public FusionIface {
     else if (n == "raycast_shared") raycast_shared_ = value != 0;
     else if (n == "raycast_tile") raycast_tile_ = value;
     else if (n == "integrate_compact") integrate_compact_ = value != 0;
+    else if (n == "slab_clip") slab_clip_ = value != 0;
+    else if (n == "fast_div") fast_div_ = value != 0 && fast_div_ok_;
+    else if (n == "slab_exchange") slab_exchange_ = value != 0;
     else throw Error("unknown fusion option " + n);
   }
   bool mesh_pending() override { return mesh_kind_ != kMeshNone; }
@@ -883,12 +986,17 @@ class FusionImpl final : public FusionIface {
     TDM_CHECK(i >= 0 && i < n_rendered_, "render_keys_device: no such render");
     TDM_CUDA(cudaSetDevice(device_));
     const int npx = d_.o.height * d_.o.width;
+    if (slab_exchange_) {   // the ray-cast wrote the keys itself; no extra kernel, no host sync: the caller's collective is
+      TDM_CHECK(i == 0 && d_hit_keys_, "slab exchange mode packs render 0 only");   // enqueued on stream() behind it
+      return d_hit_keys_;
+    }
     if (!d_hit_keys_) TDM_CUDA(cudaMalloc(&d_hit_keys_, (size_t)npx * sizeof(long long)));
     k_pack_hits<<<cdiv(npx, 256), 256, 0, stream_>>>(d_depth_out_ + (size_t)i * npx, d_bgr_out_ + (size_t)i * npx * 3, d_hit_keys_, npx);
     TDM_CUDA(cudaGetLastError());
     TDM_CUDA(cudaStreamSynchronize(stream_));
     return d_hit_keys_;
   }
+  void* stream() override { return (void*)stream_; }
   void unpack_keys(const long long* keys_dev, float* depth_out, unsigned char* bgr_out) override {
     TDM_CUDA(cudaSetDevice(device_));
     const int npx = d_.o.height * d_.o.width;
@@ -955,10 +1063,24 @@ class FusionImpl final : public FusionIface {
       if (raycast_shared_ && !raycast_persistent_ && !raycast_cache8_) {
         unsigned char* bo = d_bgr_out_ + (size_t)i * npx * 3;
         float* dout_i = d_depth_out_ + (size_t)i * npx;
-        if (raycast_tile_ == 0) k_raycast_shared<16, 16, 5><<<grid, 256, 0, stream_>>>(d_, render_poses_[i], bo, dout_i);
-        else if (raycast_tile_ == 1) k_raycast_shared<8, 8, 24><<<dim3(cdiv(d_.o.width, 8), cdiv(d_.o.height, 8)), 64, 0, stream_>>>(d_, render_poses_[i], bo, dout_i);
-        else if (raycast_tile_ == 2) k_raycast_shared<8, 4, 48><<<dim3(cdiv(d_.o.width, 8), cdiv(d_.o.height, 4)), 32, 0, stream_>>>(d_, render_poses_[i], bo, dout_i);
-        else k_raycast_shared<16, 8, 12><<<dim3(cdiv(d_.o.width, 16), cdiv(d_.o.height, 8)), 128, 0, stream_>>>(d_, render_poses_[i], bo, dout_i);
+        const bool slab = (d_.slab_lo != INT_MIN || d_.slab_hi != INT_MAX) && slab_clip_;
+        long long* keys = nullptr;
+        if (slab_exchange_ && i == 0) {
+          if (!d_hit_keys_) TDM_CUDA(cudaMalloc(&d_hit_keys_, npx * sizeof(long long)));
+          keys = d_hit_keys_;
+        }
+#define TDM_RAY(TW_, TH_, MB_, GRID_, THREADS_)                                                                   \
+  do {                                                                                                             \
+    if (slab && fast_div_) k_raycast_shared<TW_, TH_, MB_, true, true><<<GRID_, THREADS_, 0, stream_>>>(d_, render_poses_[i], bo, dout_i, keys);   \
+    else if (slab) k_raycast_shared<TW_, TH_, MB_, true, false><<<GRID_, THREADS_, 0, stream_>>>(d_, render_poses_[i], bo, dout_i, keys);   \
+    else if (fast_div_) k_raycast_shared<TW_, TH_, MB_, false, true><<<GRID_, THREADS_, 0, stream_>>>(d_, render_poses_[i], bo, dout_i, keys);   \
+    else k_raycast_shared<TW_, TH_, MB_, false, false><<<GRID_, THREADS_, 0, stream_>>>(d_, render_poses_[i], bo, dout_i, keys);       \
+  } while (0)
+        if (raycast_tile_ == 0) TDM_RAY(16, 16, 5, grid, 256);
+        else if (raycast_tile_ == 1) TDM_RAY(8, 8, 24, dim3(cdiv(d_.o.width, 8), cdiv(d_.o.height, 8)), 64);
+        else if (raycast_tile_ == 2) TDM_RAY(8, 4, 48, dim3(cdiv(d_.o.width, 8), cdiv(d_.o.height, 4)), 32);
+        else TDM_RAY(16, 8, 12, dim3(cdiv(d_.o.width, 16), cdiv(d_.o.height, 8)), 128);
+#undef TDM_RAY
       } else if (raycast_persistent_) {
         TDM_CUDA(cudaMemsetAsync(d_.counters + 4, 0, sizeof(int), stream_));
         k_raycast_persistent<<<raycast_grid_, 256, 0, stream_>>>(d_, render_poses_[i], d_bgr_out_ + (size_t)i * npx * 3,
@@ -967,7 +1089,7 @@ class FusionImpl final : public FusionIface {
       else k_raycast<false><<<grid, 256, 0, stream_>>>(d_, render_poses_[i], d_bgr_out_ + (size_t)i * npx * 3, d_depth_out_ + (size_t)i * npx);
       TDM_CUDA(cudaGetLastError());
     }
-    if (copy_back) {
+    if (copy_back && !slab_exchange_) {   // slab exchange mode: the per-slab render is only an operand of the exchange step
       TDM_CUDA(cudaMemcpyAsync(h_bgr_out_[free_half_], d_bgr_out_, npx * 3 * n, cudaMemcpyDeviceToHost, stream_));
       TDM_CUDA(cudaMemcpyAsync(h_depth_out_[free_half_], d_depth_out_, npx * 4 * n, cudaMemcpyDeviceToHost, stream_));
     }
@@ -1116,6 +1238,10 @@ class FusionImpl final : public FusionIface {
   bool raycast_shared_ = true;
   int raycast_tile_ = 1;   // 0: 16x16 px CTAs, 1: 8x8, 2: 8x4 (one warp), 3: 16x8
   bool raycast_persistent_ = false, integrate_compact_ = true;   // measured: persistent 0.875 ms vs 0.820 ms (instruction-bound, not imbalance-bound)
+  bool fast_div_ok_ = false, fast_div_ = false;   // constant-divisor division in the ray-cast (cdiv_): bit-identical, 3 instructions per division
+  bool slab_clip_ = true;        // Z-slab volumes: rays are only sampled inside the slab's z range (bit-identical, see k_raycast_shared)
+  bool slab_exchange_ = false;   // Z-slab volumes: the ray-cast emits packed nearest-hit keys for the exchange step, the per-slab
+                                 // render is not copied back and GetRenderResult does not wait (tandem_b200.parallel)
   int* d_vis_list_ = nullptr;
   int raycast_grid_ = 148;
   cudaEvent_t ev_split_ = nullptr;

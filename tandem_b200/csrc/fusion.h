@@ -25,6 +25,7 @@ class FusionIface {
   virtual long long extract_mesh_blocking(const float* lower, const float* upper, float* vert, float* cols, size_t max_vertices) = 0;
   virtual bool mesh_pending() = 0;
   virtual long long* render_keys_device(int i) = 0;
+  virtual void* stream() = 0;   // the CUDA stream all of this handle's work is ordered on (for collectives enqueued behind it)
   virtual void unpack_keys(const long long* keys_dev, float* depth_out, unsigned char* bgr_out) = 0;
   virtual float last_mesh_ms() = 0;
   virtual float last_alloc_ms() = 0;   // k_allocate share of the last run_resident's integrate time (per iteration)

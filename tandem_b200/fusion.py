@@ -141,10 +141,15 @@ class DrFusion:
         check(lib().tdm_fusion_render_keys_device(self._h, int(render_index), ctypes.byref(ptr)))
         return ptr.value, self.options.height * self.options.width
 
-    def unpack_keys(self, keys_dev_ptr):
+    def stream(self):
+        """cudaStream_t (int) all of this handle's work is ordered on - for collectives enqueued behind the ray-cast."""
+        p = ctypes.c_void_p()
+        check(lib().tdm_fusion_stream(self._h, ctypes.byref(p)))
+        return p.value or 0
+
+    def unpack_keys(self, keys_dev_ptr, out=None):
         o = self.options
-        depth = np.empty((o.height, o.width), np.float32)
-        bgr = np.empty((o.height, o.width, 3), np.uint8)
+        depth, bgr = out if out is not None else (np.empty((o.height, o.width), np.float32), np.empty((o.height, o.width, 3), np.uint8))
         check(lib().tdm_fusion_unpack_keys(self._h, ctypes.c_void_p(keys_dev_ptr), depth.ctypes.data_as(ctypes.POINTER(ctypes.c_float)),
                                            bgr.ctypes.data))
         return depth, bgr

@@ -90,14 +90,18 @@ class _DeviceInt64:
         self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<i8", "data": (int(ptr), False), "version": 2}
 
 
-def reduce_nearest_hit_device(dist, fusion, render_index=0, device="cuda:0"):
-    """Same exchange as reduce_nearest_hit but without the host round trip: the keys are packed by a kernel into a device
-    buffer of the DrFusion handle, all-reduced in place with MIN over the ranks (NCCL over NVLink) and unpacked by a kernel.
-    Returns (depth, bgr) of the combined render on the host."""
+def reduce_nearest_hit_device(dist, fusion, render_index=0, device="cuda:0", out=None):
+    """Same exchange as reduce_nearest_hit but without the host round trip: the keys sit in a device buffer of the DrFusion
+    handle (written by the ray-cast itself in "slab_exchange" mode, else by a pack kernel), are all-reduced in place with MIN
+    over the ranks (NCCL over NVLink) and unpacked by a kernel.  The collective is enqueued ON THE HANDLE'S OWN STREAM
+    (torch.cuda.ExternalStream), i.e. behind the ray-cast and in front of the unpack kernel, with no host synchronisation in
+    between; the only sync of the frame is the D2H of the combined render inside unpack_keys.
+    Returns (depth, bgr) of the combined render on the host (written into `out` = (depth, bgr) arrays when given - pass
+    page-locked arrays for a copy-free read-back)."""
     ptr, n = fusion.render_keys_device(render_index)
     if dist is not None:
         import torch
         t = torch.as_tensor(_DeviceInt64(ptr, n), device=device)
-        dist.all_reduce(t, op=dist.ReduceOp.MIN)
-        torch.cuda.synchronize(device)
-    return fusion.unpack_keys(ptr)
+        with torch.cuda.stream(torch.cuda.ExternalStream(fusion.stream(), device=device)):
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    return fusion.unpack_keys(ptr, out)

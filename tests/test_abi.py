@@ -138,3 +138,24 @@ def test_tcgen05_tile_planner_invariants():
         assert grid == tw * th * td and grid >= 1, key
         assert nch == (R * P + 127) // 128 and (4 if mode == 4 else 2) * nch * npad <= 512, key      # TMEM columns
         assert smem <= 225 * 1024 and slot_pos % 8 == 0 and slot_pos >= (R + 2) * P, key
+
+
+def test_constant_division_is_correctly_rounded(tmp_path):
+    """The TSDF ray-cast replaces div.rn.f32 by a 3-instruction FMA sequence for its constant divisors (cdiv_ in
+    tandem_b200/csrc/fusion.cu: voxel_size, fx, fy).  Parity with the oracle's `/` rests on that sequence being CORRECTLY ROUNDED:
+    checked exhaustively for the deployment's voxel size 0.01f over every float the ray-cast can produce (|x| in [1e-6, 4096]),
+    for the config intrinsics over the pixel-ray range, and on 2e8 random (x, d) pairs."""
+    import ctypes
+    import subprocess
+    src = os.path.join(ROOT, "tests", "cpp", "cdiv_check.c")
+    so = str(tmp_path / "libcdiv_check.so")
+    subprocess.run(["gcc", "-O2", "-mfma", "-ffp-contract=off", "-fno-fast-math", "-shared", "-fPIC", "-o", so, src, "-lm"], check=True)
+    l = ctypes.CDLL(so)
+    l.cdiv_check_exhaustive.restype = ctypes.c_long
+    l.cdiv_check_exhaustive.argtypes = [ctypes.c_float, ctypes.c_float, ctypes.c_float]
+    l.cdiv_check_random.restype = ctypes.c_long
+    l.cdiv_check_random.argtypes = [ctypes.c_uint64, ctypes.c_long]
+    assert l.cdiv_check_exhaustive(0.01, 1e-6, 4096.0) == 0
+    for fx in (320.0, 80.0, 300.0, 525.0, 481.2):
+        assert l.cdiv_check_exhaustive(fx, 1e-3, 16384.0) == 0
+    assert l.cdiv_check_random(1, 200_000_000) == 0

@@ -106,9 +106,17 @@ def test_benchmark_config_abs_rel(golden_full, precision):
     mours = out.depth == 0
     iou = np.logical_and(mref, mours).sum() / max(np.logical_or(mref, mours).sum(), 1)
     print(f"C2 {precision}: Abs Rel {ar:.3e}, conf mean-abs {ec:.3e}, filter IoU {iou:.4f}")
-    assert ar < (1e-4 if precision == "fp32" else 5e-4)   # budget 1e-3 (BASELINE.json); mixed16 keeps 2x margin
+    # Abs Rel budget 1e-3 (BASELINE.json).  Filter-mask bar (SURVEY 8d config 2 asks IoU >= 0.99):
+    #  * fp32 parity engine: IoU >= 0.999 (measured 0.9997).
+    #  * mixed16: IoU >= 0.98 (measured 0.9853), a DEFENDED bar (profiles/r02_precision_study.md): the
+    #    mask keeps the 2.5 % largest values of an order statistic of depth differences, i.e. it is decided at depth edges where
+    #    soft-argmin is bimodal; the oracle itself, with nothing changed but its tensors rounded to this engine's 16-bit
+    #    storage types, reaches Abs Rel 1.12e-4 / IoU 0.9868 - the engine sits on that floor (1.09e-4 / 0.9853) - and the
+    #    reference's own two arithmetic paths (CPU fp32 vs cuDNN fp32 on the B200) agree with each other no better (bench
+    #    line, gpu_reference.mask_iou_vs_cpu_reference).  IoU >= 0.99 needs > 16-bit feature maps (the fp32 engine).
+    assert ar < (2e-5 if precision == "fp32" else 2.5e-4)
     assert ec < 2e-2
-    assert iou > (0.98 if precision == "fp32" else 0.95)
+    assert iou > (0.999 if precision == "fp32" else 0.98)
 
 
 def test_cpp_wrapper_intrinsics_path(golden_small):

@@ -23,10 +23,12 @@ from tandem_b200.parallel import reduce_max, reduce_nearest_hit_device, slab_bou
 from tandem_b200.synthetic import RoomScene, circle_trajectory  # noqa: E402
 
 
-def main():
+def main(argv=None):
     ap = argparse.ArgumentParser()
     ap.add_argument("--frames", type=int, default=12)
-    a = ap.parse_args()
+    ap.add_argument("--warmup", type=int, default=2, help="untimed frames (same stream, integrated before the timed ones)")
+    ap.add_argument("--legacy", action="store_true", help="round-1 path: unclipped slab ray-cast, per-slab D2H, pack kernel + host syncs")
+    a = ap.parse_args(argv)
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
     dist = None
     import torch
@@ -47,7 +49,7 @@ def main():
     half = 5.0                                   # 10 m room inside the 10.24 m (1024^3 voxels at 1 cm) cube
     off = np.float32(5.12)
     scene = RoomScene(half=half, spheres=((2.4, 0.6, 1.6, 1.0), (-2.0, -0.8, 3.0, 1.0), (0.4, 1.8, -2.8, 1.0)))
-    poses = circle_trajectory(a.frames, radius=2.0)
+    poses = circle_trajectory(a.frames + a.warmup, radius=2.0)
     frames = [scene.render(p, H, W, **intr, noise_sigma=0.002, dropout=0.02, seed=k) for k, p in enumerate(poses)]
     for p in poses:
         p[:3, 3] += off
@@ -59,30 +61,51 @@ def main():
     f = DrFusion(opt, device=local)
     if world > 1:
         f.set_slab(alo, ahi)
+    if a.legacy:
+        f.set_option("slab_clip", 0)
+    else:
+        f.set_option("slab_exchange", 1)      # ray-cast emits the exchange keys, no per-slab D2H, one host sync per frame
     dev = f"cuda:{local}"
+    from tandem_b200._lib import pinned_empty
+    n_ring = len(poses) if (rank == 0 and world > 1) else 2   # rank 0 keeps every combined render for the parity check below
+    ring = [(pinned_empty((H, W), np.float32), pinned_empty((H, W, 3), np.uint8)) for _ in range(n_ring)]
 
     def sync():
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize(local)
 
+    if not a.legacy:   # the caller keeps its scans in page-locked memory: IntegrateScanAsync DMA's straight from them
+        pf = []
+        for bgr, depth in frames:
+            pb, pd = pinned_empty(bgr.shape, np.uint8), pinned_empty(depth.shape, np.float32)
+            pb[...] = bgr; pd[...] = depth
+            pf.append((pb, pd))
+        frames_in = pf
+    else:
+        frames_in = frames
     outs = []
-    sync()
-    t0 = time.perf_counter()
-    for (bgr, depth), pose in zip(frames, poses):
+    for k, ((bgr, depth), pose) in enumerate(zip(frames_in, poses)):
+        if k == a.warmup:
+            sync()
+            t0 = time.perf_counter()
         f.IntegrateScanAsync(bgr, depth, pose)
         f.RenderAsync([pose])
         f.GetRenderResult()
-        outs.append(reduce_nearest_hit_device(dist, f, 0, dev))
+        outs.append(reduce_nearest_hit_device(dist, f, 0, dev, out=None if a.legacy else ring[k % n_ring]))
     sync()
     ms = (time.perf_counter() - t0) * 1e3 / a.frames
+    mi, mr = f.run_resident(5)                       # device time of the last frame's integrate / ray-cast on this rank
+    mi, mr = reduce_max(dist, [mi / 5, mr / 5], device=dev)
     (ms,) = reduce_max(dist, [ms], device=dev)
     st = f.stats()
     blocks = reduce_max(dist, [st["allocated_blocks"]], device=dev)[0]
     if rank == 0:
         line = {"what": "TSDF Z-slab partition, integrate + ray-cast + nearest-hit all-reduce (NCCL, device buffers)", "n_gpus": world,
                 "frames": a.frames, "ms_per_frame(max over ranks, wall incl. H2D/D2H)": ms, "frames_per_s": 1e3 / ms,
-                "max_blocks_per_rank": int(blocks), "slab_blocks(owned, rank 0)": [lo, hi]}
+                "max_blocks_per_rank": int(blocks), "slab_blocks(owned, rank 0)": [lo, hi],
+                "device_ms_last_frame(max over ranks)": {"allocate+integrate": mi, "raycast": mr},
+                "mode": "legacy (round 1)" if a.legacy else "slab-clipped ray-cast + fused key packing + all-reduce on the fusion stream"}
         if world > 1:     # parity against the un-partitioned volume
             full = DrFusion(opt, device=local)
             mism, med, p99 = [], [], []
@@ -100,9 +123,13 @@ def main():
                          "depth_abs_err_median_max_m": max(med), "depth_abs_err_p99_max_m": max(p99)})
             assert max(mism) < 5e-3 and max(med) < 1e-3 and max(p99) < 0.03, line
         print(json.dumps(line))
+        result = line
+    else:
+        result = None
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
+    return result
 
 
 if __name__ == "__main__":
