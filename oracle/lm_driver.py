@@ -3,8 +3,14 @@
 numpy restatement of the level-0 part of the Levenberg-Marquardt driver CoarseTracker::trackNewestCoarse
 (tandem/src/FullSystem/CoarseTracker.cpp:761-916) on top of a tracker object with the CudaCoarseTracker call surface
 (calcRes / calcG).  SURVEY.md section 8(f) row n3 moves this loop onto the device (tdm_tracker_track); this file is what
-the device loop is checked against.  PARITY UNPINNED: the reference driver needs Eigen + Sophus (absent here); the
-restatement follows the listed lines statement by statement: cutoff doubling while the saturated ratio exceeds 0.6
+the device loop is checked against.  PINNED (round 2): the reference driver as a whole needs Eigen + Sophus (absent here),
+but its level loop (CoarseTracker.cpp:750-916) is cut out of the file where it lies by oracle/ref_build.mk and compiled,
+unmodified, against a stand-in Eigen / SE3 (tests/cpp/eigen_stub, oracle/ref_wrap_lm.cpp) into oracle/_ref/liblm_ref.so;
+tests/test_oracle_cpu.py::test_lm_driver_pinned_to_reference_trackNewestCoarse drives that loop and this restatement with the
+SAME tracker object and requires the same number of evaluations (= the same accept / reject sequence, cutoff doublings, stop
+iteration and level repeat) and the same pose / affine parameters, for free, fixed-a, fixed-b and fixed-a-b optimisation and
+a saturating start.  Without /root/reference the test skips and this file is "parity unpinned".  The restatement follows
+the listed lines statement by statement: cutoff doubling while the saturated ratio exceeds 0.6
 (:779-790), lambda = 0.01 (:798), H diagonal *(1+lambda) and LDLT solve on the free parameters (:814-840), the
 extrapolation factor (:843-845), SCALE_* (:847-851, cuda_coarse_tracker.cpp:12-19), left-multiplicative SE3 update
 (:855), accept iff the mean energy drops (:868), lambda *0.5 / *4 with the extrapolation limit as floor (:887-900), stop

@@ -37,3 +37,11 @@ $(OUT)/gen/dense_ref.inc: $(FS)/CoarseTracker.cpp
 	sed -n '655,725p' $< > $@
 $(OUT)/libfront_ref.so: ref_wrap_front.cpp $(OUT)/gen/make_images.inc $(OUT)/gen/dense_ref.inc ../tests/cpp/eigen_stub/Eigen/Dense
 	$(CXX) -O2 -std=c++14 -fPIC -shared -ffp-contract=off -fno-fast-math -w -I. -I../tests/cpp/eigen_stub -o $@ ref_wrap_front.cpp
+
+# n3 pin: the LM level loop of CoarseTracker::trackNewestCoarse (CoarseTracker.cpp:750-916), same recipe style.
+all: $(OUT)/liblm_ref.so
+$(OUT)/gen/lm_loop.inc: $(FS)/CoarseTracker.cpp
+	@mkdir -p $(OUT)/gen
+	sed -n '750,916p' $< > $@
+$(OUT)/liblm_ref.so: ref_wrap_lm.cpp $(OUT)/gen/lm_loop.inc ../tests/cpp/eigen_stub/Eigen/Dense
+	$(CXX) -O2 -std=c++14 -fPIC -shared -ffp-contract=off -fno-fast-math -w -I. -I../tests/cpp/eigen_stub -o $@ ref_wrap_lm.cpp

@@ -220,6 +220,76 @@ def test_lm_driver_converges_with_oracle_tracker():
     assert np.allclose(se3_exp(np.zeros(6)), np.eye(4))
 
 
+@pytest.mark.parametrize("start,fix_a,fix_b,cutoff", [("identity", False, False, 20.0), ("near", False, False, 20.0),
+                                                       ("identity", True, True, 20.0), ("identity", False, True, 20.0),
+                                                       ("identity", True, False, 20.0), ("identity", False, False, 0.8)])
+def test_lm_driver_pinned_to_reference_trackNewestCoarse(start, fix_a, fix_b, cutoff):
+    """n3 pin: oracle/lm_driver.py == the reference's own level loop (CoarseTracker.cpp:750-916 compiled unmodified into
+    oracle/_ref/liblm_ref.so) when both drive the SAME tracker object: same number of residual / normal-equation evaluations
+    (i.e. same accept / reject sequence, cutoff doublings and stop iteration), same pose and affine parameters.  The last case
+    starts with a cutoff so small that > 60 % of the points saturate: the cutoff-doubling and REPEAT-LEVEL rules run."""
+    import ctypes
+    from oracle.lm_driver import track_level0
+    lib_path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "liblm_ref.so")
+    if not os.path.exists(lib_path):
+        pytest.skip("oracle/_ref/liblm_ref.so not built (needs /root/reference: make -C oracle -f ref_build.mk)")
+    l = ctypes.CDLL(lib_path)
+    c = tracker_case(H=120, W=160, fx=80.0, fy=80.0, cx=79.5, cy=59.5)
+    t = TrackerOracle(c["w"], c["h"])
+    t.setK(c["w"], c["h"], c["fx"], c["fy"], c["cx"], c["cy"])
+    t.setReference(c["n"], c["pc_u"], c["pc_v"], c["pc_idepth"], c["pc_color"], c["ref_exposure"], c["ref_aff"])
+    t.setNew(c["dInew"])
+    dp = ctypes.POINTER(ctypes.c_double)
+    RES = ctypes.CFUNCTYPE(None, ctypes.c_void_p, dp, ctypes.c_float, dp, ctypes.c_float, dp)
+    G = ctypes.CFUNCTYPE(None, ctypes.c_void_p, ctypes.c_float, dp, dp, dp)
+    log = []
+
+    def res_cb(_, T16, expo, aff2, cut, out6):
+        T = np.array([T16[i] for i in range(16)]).reshape(4, 4)
+        r = t.calcRes(T, expo, np.array([aff2[0], aff2[1]]), cut)
+        log.append(("res", cut))
+        for i in range(6):
+            out6[i] = r[i]
+
+    def g_cb(_, expo, aff2, H64, b8):
+        H, b = t.calcG(expo, np.array([aff2[0], aff2[1]]))
+        for i in range(8):
+            b8[i] = b[i]
+            for j in range(8):
+                H64[8 * i + j] = H[i, j]
+    T0 = np.eye(4) if start == "identity" else np.array(c["refToNew"], np.float64) @ np.linalg.inv(
+        np.array([[1, 0, 0, 0.004], [0, 1, 0, -0.003], [0, 0, 1, 0.002], [0, 0, 0, 1.0]]))
+    T = np.ascontiguousarray(T0, np.float64).copy()
+    aff = np.array(c["ref_aff"], np.float64).copy()
+    out5 = np.zeros(5)
+    counts = (ctypes.c_int * 2)()
+    l.ref_lm_track_level0.restype = ctypes.c_int
+    ok = l.ref_lm_track_level0(None, RES(res_cb), G(g_cb), T.ctypes.data_as(dp), aff.ctypes.data_as(dp), ctypes.c_float(c["new_exposure"]),
+                               ctypes.c_float(c["ref_exposure"]), np.array(c["ref_aff"], np.float64).ctypes.data_as(dp),
+                               ctypes.c_float(cutoff), int(fix_a), int(fix_b), out5.ctypes.data_as(dp), counts)
+    assert ok == 1
+    # the restatement: one pass, plus the reference's single REPEAT of the level when the cutoff had to be raised (:911-915)
+    r = track_level0(t, T0, c["ref_aff"], c["new_exposure"], coarse_cutoff=cutoff, max_iterations=10, fix_a=fix_a, fix_b=fix_b)
+    evals, passes = r["evaluations"], 1
+    if r["cutoff_repeat"] > 1:
+        r2 = track_level0(t, r["refToNew"], r["aff"], c["new_exposure"], coarse_cutoff=cutoff, max_iterations=10, fix_a=fix_a, fix_b=fix_b)
+        evals += r2["evaluations"]
+        passes, r = 2, r2
+    print(f"{start} fix_a={fix_a} fix_b={fix_b} cutoff={cutoff}: reference loop {counts[0]} calcRes / {counts[1]} calcG, restatement {evals} "
+          f"evaluations in {passes} pass(es); |dT| {np.abs(T - r['refToNew']).max():.2e}, |daff| {np.abs(aff - r['aff']).max():.2e}")
+    assert counts[0] == evals
+    assert np.abs(T - r["refToNew"]).max() < 1e-6 and np.abs(aff - r["aff"]).max() < 1e-4   # fp32 evaluations amplify the 1e-16 difference of the two linear solvers
+    with np.errstate(invalid="ignore"):   # cutoff 0.8 < huber / 2 makes maxEnergy negative: sqrtf(E / n) is NaN in the reference too
+        rms = np.sqrt(np.float32(r["res"][0] / r["res"][1]))
+    assert (np.isnan(out5[0]) and np.isnan(rms)) or abs(out5[0] - rms) < 1e-5
+    if cutoff < 1.0:
+        assert passes == 2, "the small-cutoff case must exercise cutoff doubling + REPEAT LEVEL"
+    if fix_a:
+        assert aff[0] == c["ref_aff"][0]
+    if fix_b:
+        assert aff[1] == c["ref_aff"][1]
+
+
 # ---------------------------------------------------------------------------------------------------------------------
 # marching cubes oracle (SURVEY.md 8f n4): properties on the CPU (the reference has no mesh test or golden)
 def _mesh_scene():
