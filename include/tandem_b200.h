@@ -141,6 +141,28 @@ int tdm_fusion_synchronize(tdm_fusion* h);
  * reads never cross ranks). Every rank integrates the same (broadcast) scans; renders are combined by a per-pixel
  * nearest-hit reduction (tandem_b200/parallel.py: reduce_nearest_hit). Call before the first scan. */
 int tdm_fusion_set_slab(tdm_fusion* h, int z_block_lo, int z_block_hi);
+/* Interleaved variant of the Z-slab partition: block row z is owned by rank ((z - z0_block) div k_blocks) mod world; every rank
+ * additionally stores one halo block row on either side of each of its slabs.  Thin interleaved slabs balance the PER-FRAME work
+ * (allocation, integration, ray-cast samples) over the ranks for any view direction - contiguous slabs only balance memory - at
+ * the price of (k_blocks + 2) / k_blocks redundant integration.  Same exchange step as set_slab.  Call before the first scan. */
+int tdm_fusion_set_interleave(tdm_fusion* h, int rank, int world, int k_blocks, int z0_block);
+/* Pixel-partitioned ray-cast over the Z-slab-partitioned volume (the fused compute + transfer form of the exchange): every rank
+ * exports its hash table and voxel pool (tdm_fusion_peer_export: raw pointers for instances of one process, CUDA IPC handles for
+ * other processes), the handles of all ranks are gathered by the caller (e.g. torch.distributed.all_gather_object) and attached
+ * (tdm_fusion_peer_attach: cudaIpcOpenMemHandle -> NVLink P2P mapping).  From then on RenderAsync renders only the 8x8 pixel
+ * tiles t with t mod world == rank, but marches them through the WHOLE volume, reading each voxel from the rank that owns its
+ * block row (local HBM or P2P loads inside the ray-cast kernel) - bit-identical to the single-volume render, occluders in other
+ * slabs included; foreign tiles carry the "miss" key, so the same MIN all-reduce (slab_exchange mode) assembles the image.
+ * Needs contiguous slabs in rank order WITHOUT halo rows (set_slab(owned_lo, owned_hi)), and the caller must order every rank's
+ * ray-cast behind every rank's integration of the same scan (a stream-ordered barrier, tandem_b200.parallel.stream_barrier). */
+typedef struct tdm_fusion_peer_handle {
+  unsigned long long keys_ptr, ptrs_ptr, voxels_ptr;   /* device pointers (meaningful inside the exporting process) */
+  long long pid;
+  int device, num_buckets, bucket_size, slab_lo, slab_hi, reserved;
+  unsigned char ipc_keys[64], ipc_ptrs[64], ipc_voxels[64];   /* cudaIpcMemHandle_t */
+} tdm_fusion_peer_handle;
+int tdm_fusion_peer_export(tdm_fusion* h, tdm_fusion_peer_handle* out);
+int tdm_fusion_peer_attach(tdm_fusion* h, const tdm_fusion_peer_handle* all_ranks, int world, int rank);
 /* The one exchange step of the slab-partitioned ray-cast, on the device: tdm_fusion_render_keys_device packs render
  * `render_index` of the last RenderAsync into height*width int64 keys (depth bits << 24 | b | g<<8 | r<<16; miss = +inf) in a
  * DEVICE buffer owned by the handle (stream synchronised on return) - the caller all-reduces it with MIN over the ranks

@@ -48,6 +48,14 @@ class FusionStats(ctypes.Structure):
                 ("dropped_blocks", ctypes.c_longlong), ("candidate_blocks", ctypes.c_longlong)]
 
 
+class FusionPeerHandle(ctypes.Structure):
+    """tdm_fusion_peer_handle (include/tandem_b200.h): one rank's exported hash table + voxel pool."""
+    _fields_ = [("keys_ptr", ctypes.c_ulonglong), ("ptrs_ptr", ctypes.c_ulonglong), ("voxels_ptr", ctypes.c_ulonglong),
+                ("pid", ctypes.c_longlong), ("device", ctypes.c_int), ("num_buckets", ctypes.c_int), ("bucket_size", ctypes.c_int),
+                ("slab_lo", ctypes.c_int), ("slab_hi", ctypes.c_int), ("reserved", ctypes.c_int),
+                ("ipc_keys", ctypes.c_ubyte * 64), ("ipc_ptrs", ctypes.c_ubyte * 64), ("ipc_voxels", ctypes.c_ubyte * 64)]
+
+
 class TrackResult(ctypes.Structure):
     _fields_ = [("ref_to_new", ctypes.c_double * 16), ("aff_g2l", ctypes.c_double * 2), ("res", ctypes.c_double * 6),
                 ("iterations", ctypes.c_int), ("evaluations", ctypes.c_int), ("cutoff_repeat", ctypes.c_float), ("device_ms", ctypes.c_float)]
@@ -86,6 +94,9 @@ def _declare(l):
         "tdm_fusion_get_render_result": (i, [vp, P(vp), P(fp), i]),
         "tdm_fusion_synchronize": (i, [vp]),
         "tdm_fusion_set_slab": (i, [vp, i, i]),
+        "tdm_fusion_set_interleave": (i, [vp, i, i, i, i]),
+        "tdm_fusion_peer_export": (i, [vp, P(FusionPeerHandle)]),
+        "tdm_fusion_peer_attach": (i, [vp, P(FusionPeerHandle), i, i]),
         "tdm_fusion_extract_mesh": (c.c_longlong, [vp, fp, fp, fp, fp, c.c_size_t]),
         "tdm_fusion_extract_mesh_async": (i, [vp, fp, fp]),
         "tdm_fusion_get_mesh": (c.c_longlong, [vp, fp, fp, c.c_size_t]),

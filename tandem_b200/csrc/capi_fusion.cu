@@ -50,6 +50,27 @@ int tdm_fusion_set_slab(tdm_fusion* h, int z_block_lo, int z_block_hi) {
   return TDM_OK;
   TDM_API_END
 }
+int tdm_fusion_set_interleave(tdm_fusion* h, int rank, int world, int k_blocks, int z0_block) {
+  TDM_API_BEGIN
+  TDM_CHECK(h, "null handle");
+  h->impl->set_interleave(rank, world, k_blocks, z0_block);
+  return TDM_OK;
+  TDM_API_END
+}
+int tdm_fusion_peer_export(tdm_fusion* h, tdm_fusion_peer_handle* out) {
+  TDM_API_BEGIN
+  TDM_CHECK(h && out, "null argument");
+  h->impl->peer_export(out);
+  return TDM_OK;
+  TDM_API_END
+}
+int tdm_fusion_peer_attach(tdm_fusion* h, const tdm_fusion_peer_handle* all, int world, int rank) {
+  TDM_API_BEGIN
+  TDM_CHECK(h && all, "null argument");
+  h->impl->peer_attach(all, world, rank);
+  return TDM_OK;
+  TDM_API_END
+}
 int tdm_fusion_synchronize(tdm_fusion* h) {
   TDM_API_BEGIN
   TDM_CHECK(h, "null handle");

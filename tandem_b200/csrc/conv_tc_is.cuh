@@ -184,15 +184,23 @@ k_conv_tc_is(const __grid_constant__ CUtensorMap tmap, const TIn* __restrict__ b
         }
         uint32_t v[16];
         float acc[NPAD];
+        if constexpr (NPAD == 8) {
+          // tight packing for the 8- (and 1-) channel outputs: [hi 0..7 | lo 0..7] are the 16 columns of ONE tcgen05.ld
+          static_assert(HILO, "NPAD == 8 is only instantiated with hi/lo weights (N must be a multiple of 16)");
+          tmem_ld16(t_row, v);
 #pragma unroll
-        for (int n0 = 0; n0 < NPAD; n0 += 16) {
-          tmem_ld16(t_row + (uint32_t)n0, v);
+          for (int i = 0; i < 8; ++i) acc[i] = __uint_as_float(v[i]) + __uint_as_float(v[8 + i]);
+        } else {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) acc[n0 + i] = __uint_as_float(v[i]);
-          if constexpr (HILO) {
-            tmem_ld16(t_row + (uint32_t)(NPAD + n0), v);
+          for (int n0 = 0; n0 < NPAD; n0 += 16) {
+            tmem_ld16(t_row + (uint32_t)n0, v);
 #pragma unroll
-            for (int i = 0; i < 16; ++i) acc[n0 + i] += __uint_as_float(v[i]);
+            for (int i = 0; i < 16; ++i) acc[n0 + i] = __uint_as_float(v[i]);
+            if constexpr (HILO) {
+              tmem_ld16(t_row + (uint32_t)(NPAD + n0), v);
+#pragma unroll
+              for (int i = 0; i < 16; ++i) acc[n0 + i] += __uint_as_float(v[i]);
+            }
           }
         }
 #pragma unroll

@@ -16,6 +16,8 @@
 // The hash function, bucket structure (full bucket -> block dropped), voxel record (8 B) and all geometry are
 // the reference's; geometry that decides integers uses __f*_rn intrinsics so it is bit-identical to the CPU
 // oracle (oracle/tsdf_oracle.c) which evaluates the same expressions without FMA contraction.
+#include <unistd.h>
+
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
@@ -42,10 +44,36 @@ struct FusionDev {
   int* ptrs;                 // block index per entry
   uint2* voxels;             // [num_blocks*512] {sdf bits, c0|c1<<8|c2<<16|w<<24}
   int4* list;                // compact list of allocated blocks (x,y,z,ptr)
+  int* bbox;                 // [6] block-coordinate bounding box (min xyz, max xyz) of EVERY block any scan's rays walked through -
+                             // also other ranks' blocks: each rank walks all rays, so the box is replicated knowledge
   int* counters;             // [0] #blocks allocated, [1] dropped, [2] visible (last scan), [3] new this scan
   int slab_lo, slab_hi;      // Z-slab partition (block z in [slab_lo, slab_hi) is kept), default: everything
   float r_vs, r_fx, r_fy;    // RN(1 / voxel_size), RN(1 / fx), RN(1 / fy) for cdiv_ (ray-cast only)
+  // Interleaved Z-slab partition (il_k > 0): block z belongs to rank ((z - il_z0) div il_k) mod il_world; a rank STORES its own
+  // blocks plus one halo block on either side of each of its slabs.  Thin interleaved slabs keep the per-frame work of every
+  // rank proportional to 1 / world for ANY view direction (contiguous slabs only balance memory: a camera looking along a slab
+  // leaves the other ranks idle), at the price of (il_k + 2) / il_k redundant integration.
+  int il_k, il_world, il_rank, il_z0;
+  // Peer view of a Z-slab-partitioned volume (pixel-partitioned ray-cast): the hash tables and voxel pools of ALL
+  // ranks, mapped into this device's address space (CUDA IPC over NVLink P2P, or plain pointers for instances of one process).
+  // Block row z is read from the rank that OWNS it: pr_lo[r] <= z < pr_hi[r].  pr_world == 0: not attached.
+  const unsigned long long* pr_keys[8];
+  const int* pr_ptrs[8];
+  const uint2* pr_voxels[8];
+  int pr_lo[8], pr_hi[8];
+  int pr_world, pr_rank;
 };
+
+__device__ __forceinline__ int il_owner(const FusionDev& d, int bz) {
+  int g = bz - d.il_z0;
+  g = g >= 0 ? g / d.il_k : -((-g + d.il_k - 1) / d.il_k);   // floor division
+  int o = g % d.il_world;
+  return o < 0 ? o + d.il_world : o;
+}
+__device__ __forceinline__ bool slab_stores(const FusionDev& d, int bz) {   // does this rank keep block row bz (own or halo)?
+  if (d.il_k > 0) return il_owner(d, bz) == d.il_rank || il_owner(d, bz - 1) == d.il_rank || il_owner(d, bz + 1) == d.il_rank;
+  return bz >= d.slab_lo && bz < d.slab_hi;
+}
 
 __device__ __forceinline__ float mul_(float a, float b) { return __fmul_rn(a, b); }
 __device__ __forceinline__ float add_(float a, float b) { return __fadd_rn(a, b); }
@@ -119,7 +147,7 @@ __device__ __forceinline__ long long hash_bucket(const tdm_fusion_options& o, in
 // returns true when the block is in the table after the call (found or inserted), false when it was rejected / dropped
 __device__ bool insert_block(const FusionDev& d, int x, int y, int z) {
   if (x <= -kKeyBias || x >= kKeyBias || y <= -kKeyBias || y >= kKeyBias || z <= -kKeyBias || z >= kKeyBias) return false;
-  if (z < d.slab_lo || z >= d.slab_hi) return false;   // another rank's Z-slab
+  if (!slab_stores(d, z)) return false;   // another rank's Z-slab
   const unsigned long long key = pack_key(x, y, z);
   const long long b = hash_bucket(d.o, x, y, z);
   for (int i = 0; i < d.o.bucket_size; ++i) {
@@ -161,17 +189,19 @@ __device__ __forceinline__ void insert_filtered(const FusionDev& d, unsigned lon
   if (insert_block(d, x, y, z)) sfilter[slot] = key;
 }
 
-__device__ __forceinline__ int find_block(const FusionDev& d, int x, int y, int z) {  // hash_table.cu:141-155
+__device__ __forceinline__ int find_in(const unsigned long long* __restrict__ keys, const int* __restrict__ ptrs, const tdm_fusion_options& o,
+                                       int x, int y, int z) {  // hash_table.cu:141-155
   if (x <= -kKeyBias || x >= kKeyBias || y <= -kKeyBias || y >= kKeyBias || z <= -kKeyBias || z >= kKeyBias) return -1;
   const unsigned long long key = pack_key(x, y, z);
-  const long long b = hash_bucket(d.o, x, y, z);
-  for (int i = 0; i < d.o.bucket_size; ++i) {
-    const unsigned long long k = d.keys[b + i];
-    if (k == key) return d.ptrs[b + i];
+  const long long b = hash_bucket(o, x, y, z);
+  for (int i = 0; i < o.bucket_size; ++i) {
+    const unsigned long long k = keys[b + i];
+    if (k == key) return ptrs[b + i];
     if (k == kEmptyKey) return -1;   // inserts fill a bucket front to back and nothing is ever removed: a free slot ends the search
   }
   return -1;
 }
+__device__ __forceinline__ int find_block(const FusionDev& d, int x, int y, int z) { return find_in(d.keys, d.ptrs, d.o, x, y, z); }
 
 // ---------------------------------------------------------------------------------------------- K5
 template <bool FILTER>
@@ -211,6 +241,18 @@ __global__ void __launch_bounds__(128) k_allocate(FusionDev d, const float* __re
   if (bp.x != be.x && dir.x < 0) { diff.x--; neg = true; }
   if (bp.y != be.y && dir.y < 0) { diff.y--; neg = true; }
   if (bp.z != be.z && dir.z < 0) { diff.z--; neg = true; }
+  {
+    // Replicated bounding box of everything the scans' rays touch (own and foreign blocks alike): the DDA is monotone per axis,
+    // so the ray's blocks lie in the box spanned by its first and last block (+-1 for the `neg` pre-step).  Plain read first:
+    // after the first few rays of a scan almost no atomic is issued.
+    const int lo[3] = {min(bp.x, be.x) - 1, min(bp.y, be.y) - 1, min(bp.z, be.z) - 1};
+    const int hi[3] = {max(bp.x, be.x) + 1, max(bp.y, be.y) + 1, max(bp.z, be.z) + 1};
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      if (lo[a] < d.bbox[a]) atomicMin(&d.bbox[a], lo[a]);
+      if (hi[a] > d.bbox[3 + a]) atomicMax(&d.bbox[3 + a], hi[a]);
+    }
+  }
   insert_filtered<FILTER>(d, sfilter, bp.x, bp.y, bp.z);
   if (neg) { bp.x += diff.x; bp.y += diff.y; bp.z += diff.z; insert_filtered<FILTER>(d, sfilter, bp.x, bp.y, bp.z); }
   int guard = 0;
@@ -369,6 +411,30 @@ struct Cache1 {
     if (bx != x || by != y || bz != z) { x = bx; y = by; z = bz; ptr = find_block(d, bx, by, bz); }
     return ptr;
   }
+  __device__ __forceinline__ const uint2* block(const FusionDev& d, int bx, int by, int bz) {   // base of the 512-voxel block or null
+    const int p = find(d, bx, by, bz);
+    return p < 0 ? nullptr : d.voxels + (size_t)p * 512;
+  }
+};
+// Last-block cache over the PEER view: the block is looked up in the table of the rank that owns its z row and its voxels are
+// read from that rank's pool - local HBM for this rank's own rows, NVLink P2P loads for the others.
+struct CachePeer {
+  int x, y, z;
+  const uint2* base;
+  __device__ __forceinline__ void init() { x = y = z = INT_MIN; base = nullptr; }
+  __device__ __forceinline__ const uint2* block(const FusionDev& d, int bx, int by, int bz) {
+    if (bx != x || by != y || bz != z) {
+      x = bx; y = by; z = bz;
+      base = nullptr;
+      int r = 0;
+      while (r < d.pr_world - 1 && bz >= d.pr_hi[r]) ++r;     // contiguous slabs in rank order
+      if (bz >= d.pr_lo[r] && bz < d.pr_hi[r]) {
+        const int p = find_in(d.pr_keys[r], d.pr_ptrs[r], d.o, bx, by, bz);
+        if (p >= 0) base = d.pr_voxels[r] + (size_t)p * 512;
+      }
+    }
+    return base;
+  }
 };
 struct Cache8 {
   unsigned long long* keys;   // [8][256] in shared memory, this thread's column
@@ -438,9 +504,9 @@ __device__ __forceinline__ int w2g_axis(float q /* = x / s */, float x) {   // t
 }
 template <class Cache>
 __device__ __forceinline__ uint2 voxel_at(const FusionDev& d, int gx, int gy, int gz, Cache& bc) {
-  const int ptr = bc.find(d, gx >> 3, gy >> 3, gz >> 3);
-  if (ptr < 0) return make_uint2(0u, 0u);
-  return __ldg(d.voxels + (size_t)ptr * 512 + (gx & 7) * 64 + (gy & 7) * 8 + (gz & 7));
+  const uint2* blk = bc.block(d, gx >> 3, gy >> 3, gz >> 3);
+  if (!blk) return make_uint2(0u, 0u);
+  return __ldg(blk + (gx & 7) * 64 + (gy & 7) * 8 + (gz & 7));
 }
 // COLOR = false: the marching steps only consume the interpolated sdf and the centre voxel's weight; the colour blend (8 corners
 // x 3 channels of unpack / convert / multiply-add: a fifth of the sample's instructions) is only evaluated for the final hit.
@@ -462,12 +528,12 @@ __device__ uint2 get_interpolated_shared(const FusionDev& d, float3 p, Cache& bc
   uint2 c[8];   // corner order of the reference: 000,100,010,001,110,011,101,111
   const bool one_block = gx1 == gx0 + 1 && gy1 == gy0 + 1 && gz1 == gz0 + 1 && (gx0 & 7) != 7 && (gy0 & 7) != 7 && (gz0 & 7) != 7;
   if (one_block) {
-    const int ptr = bc.find(d, gx0 >> 3, gy0 >> 3, gz0 >> 3);
-    if (ptr < 0) {
+    const uint2* blk = bc.block(d, gx0 >> 3, gy0 >> 3, gz0 >> 3);
+    if (!blk) {
 #pragma unroll
       for (int k = 0; k < 8; ++k) c[k] = make_uint2(0u, 0u);
     } else {
-      const uint2* b = d.voxels + (size_t)ptr * 512 + (gx0 & 7) * 64 + (gy0 & 7) * 8 + (gz0 & 7);
+      const uint2* b = blk + (gx0 & 7) * 64 + (gy0 & 7) * 8 + (gz0 & 7);
       c[0] = __ldg(b); c[1] = __ldg(b + 64); c[2] = __ldg(b + 8); c[3] = __ldg(b + 1);
       c[4] = __ldg(b + 72); c[5] = __ldg(b + 9); c[6] = __ldg(b + 65); c[7] = __ldg(b + 73);
     }
@@ -511,7 +577,12 @@ __device__ __forceinline__ long long pack_hit_key(float depth, unsigned bgr24) {
   const long long bits = depth > 0.f ? (long long)__float_as_uint(depth) : 0x7F800000ll;
   return (bits << 24) | (long long)(depth > 0.f ? (bgr24 & 0xFFFFFFu) : 0u);
 }
-template <int TW, int TH, int MINB, bool SLAB, bool FAST>
+// PEER (pixel-partitioned ray-cast over a Z-slab-partitioned volume): this rank renders the pixel tiles t with t mod world ==
+// rank, marching through the WHOLE volume; every voxel is read from the rank that owns its block row (CachePeer: local HBM or
+// NVLink P2P).  Each sample therefore sees exactly the voxels of the un-partitioned volume at exactly the same positions: the
+// union of the ranks' tiles is bit-identical to the single-volume render, occluders in other slabs included.  Foreign tiles
+// get the "miss" key, so the same MIN all-reduce assembles the image.
+template <int TW, int TH, int MINB, bool SLAB, bool FAST, bool PEER = false>
 __global__ void __launch_bounds__(TW * TH, MINB)
 k_raycast_shared(FusionDev d, Mat4 T, unsigned char* __restrict__ bgr_out, float* __restrict__ depth_out, long long* __restrict__ keys) {
   const tdm_fusion_options& o = d.o;
@@ -519,11 +590,43 @@ k_raycast_shared(FusionDev d, Mat4 T, unsigned char* __restrict__ bgr_out, float
   const int y = blockIdx.y * TH + (threadIdx.x / TW);
   if (x >= o.width || y >= o.height) return;
   const int i = y * o.width + x;
-  Cache1 bc;
+  if constexpr (PEER) {
+    if ((int)((blockIdx.y * gridDim.x + blockIdx.x) % (unsigned)d.pr_world) != d.pr_rank) {   // another rank's tile
+      bgr_out[3 * i] = bgr_out[3 * i + 1] = bgr_out[3 * i + 2] = 0;
+      depth_out[i] = 0.f;
+      if (keys) keys[i] = pack_hit_key(0.f, 0u);
+      return;
+    }
+  }
+  typename std::conditional<PEER, CachePeer, Cache1>::type bc;
   bc.init();
   float cur = 0.f;
   float t_exit = FLT_MAX;
-  if constexpr (SLAB) {
+  {
+    // Clip the march to the bounding box of everything any scan ever allocated (d.bbox, replicated on every rank): outside it
+    // every sample reads "no voxel" and advances by tau, so the leading ones are replaced by the same fp32 additions without
+    // memory accesses and the trailing ones by an immediate miss - bit-identical, and it stops (a) rays that look out of the
+    // mapped region and (b), in a Z-slab rank, rays that have passed an occluder stored on ANOTHER rank and would otherwise
+    // march on to max_sensor_depth through this rank's empty space.
+    // ray in world space: P(cur) = O + cur * D (linear model of xform(T, get_point3d(i, cur)); slack: 1 block + 2.5 voxels)
+    const float ux = ((float)x - o.cx) / o.fx, uy = ((float)y - o.cy) / o.fy;
+    const float s8 = 8.f * o.voxel_size, slack = 10.5f * o.voxel_size;
+    float t_in = 0.f;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      const float D = T.m[4 * a] * ux + T.m[4 * a + 1] * uy + T.m[4 * a + 2], O = T.m[4 * a + 3];
+      const float lo = (float)d.bbox[a] * s8 - slack, hi = (float)(d.bbox[3 + a] + 1) * s8 + slack;
+      if (fabsf(D) < 1e-12f) {
+        if (O < lo || O > hi) t_in = FLT_MAX;
+      } else {
+        const float t0 = (lo - O) / D, t1 = (hi - O) / D;
+        t_in = fmaxf(t_in, fminf(t0, t1));
+        t_exit = fminf(t_exit, fmaxf(t0, t1));
+      }
+    }
+    while (cur < t_in && cur < o.max_sensor_depth) cur = add_(cur, o.truncation_distance);
+  }
+  if (SLAB && d.il_k == 0) {
     // world z of the sample at ray parameter cur: zw = a * cur + b (linear model of xform(T, get_point3d(i, cur)).z; its
     // rounding differs from the exact evaluation by ~1e-6 m, covered by the half-voxel slack below).  A sample reads voxels
     // within +-1.5 voxels of its own position, a block b holds the voxels [8b - 0.5, 8b + 7.5) * s.
@@ -536,23 +639,39 @@ k_raycast_shared(FusionDev d, Mat4 T, unsigned char* __restrict__ bgr_out, float
     } else {
       const float t0 = (zlo - b) / a, t1 = (zhi - b) / a;
       t_enter = fminf(t0, t1);
-      t_exit = fmaxf(t0, t1);
+      t_exit = fminf(t_exit, fmaxf(t0, t1));
     }
     while (cur < t_enter && cur < o.max_sensor_depth) cur = add_(cur, o.truncation_distance);   // what the skipped samples would do
   }
   int guard = 0;
   bool hit = false;
+  float il_a = 0.f, il_b = 0.f;
+  if constexpr (SLAB) {
+    if (d.il_k > 0) {   // interleaved slabs: sample world z / voxel_size = il_a * cur + il_b (linear model, 2.5-voxel slack below)
+      il_a = (T.m[8] * ((float)x - o.cx) / o.fx + T.m[9] * ((float)y - o.cy) / o.fy + T.m[10]) / o.voxel_size;
+      il_b = T.m[11] / o.voxel_size;
+    }
+  }
   while (cur < o.max_sensor_depth && guard++ < 100000) {
-    if (SLAB && cur > t_exit) break;
-    const uint2 v = get_interpolated_shared<Cache1, false, FAST>(d, xform(T, get_point3d_c<FAST>(d, i, cur)), bc);
+    if constexpr (SLAB) {
+      if (d.il_k > 0) {
+        // a sample reads voxels within +-1.5 voxels of its position; skip it (advance by tau, exactly what a sample that finds
+        // no voxel does) unless one of the block rows it can touch is stored on this rank
+        const float zv = fmaf(il_a, cur, il_b);
+        const int b0 = (int)floorf(zv - 2.5f) >> 3, b1 = (int)floorf(zv + 2.5f) >> 3;
+        if (!slab_stores(d, b0) && !slab_stores(d, b1)) { cur = add_(cur, o.truncation_distance); continue; }
+      }
+    }
+    if (cur > t_exit) break;
+    const uint2 v = get_interpolated_shared<decltype(bc), false, FAST>(d, xform(T, get_point3d_c<FAST>(d, i, cur)), bc);
     const unsigned w = v.y >> 24;
     const float sdf = __uint_as_float(v.x);
     cur = add_(cur, w == 0 ? o.truncation_distance : sdf);
     if (w != 0 && sdf < o.voxel_size) { hit = true; break; }
   }
   // (un-clipped march: a ray that runs out of range ends with cur >= max_sensor_depth; the slab march may also stop behind the slab)
-  if (SLAB ? (hit && cur < o.max_sensor_depth) : (cur < o.max_sensor_depth)) {
-    const uint2 v = get_interpolated_shared<Cache1, true, FAST>(d, xform(T, get_point3d_c<FAST>(d, i, cur)), bc);
+  if (hit && cur < o.max_sensor_depth) {
+    const uint2 v = get_interpolated_shared<decltype(bc), true, FAST>(d, xform(T, get_point3d_c<FAST>(d, i, cur)), bc);
     bgr_out[3 * i] = v.y & 0xFF; bgr_out[3 * i + 1] = (v.y >> 8) & 0xFF; bgr_out[3 * i + 2] = (v.y >> 16) & 0xFF;
     depth_out[i] = cur;
     if (keys) keys[i] = pack_hit_key(cur, v.y);
@@ -750,6 +869,8 @@ class FusionImpl final : public FusionIface {
     d_.o = o;
     d_.slab_lo = INT_MIN;
     d_.slab_hi = INT_MAX;
+    d_.il_k = 0; d_.il_world = 1; d_.il_rank = 0; d_.il_z0 = 0;
+    d_.pr_world = 0; d_.pr_rank = 0;
     {
       // reciprocals for cdiv_: host IEEE division = correctly rounded (the file is built with -ffp-contract=off, no fast-math)
       volatile float one = 1.0f;
@@ -761,8 +882,10 @@ class FusionImpl final : public FusionIface {
         return d > 0.f && ex > 40 && ex < 214 && man != 0x7FFFFF;   // 2^-87 < d < 2^87, significand not all ones
       };
       fast_div_ok_ = ok(o.voxel_size) && ok(o.fx) && ok(o.fy);
+      // Measured on the B200 (profiles/r02_fusion_tracker.txt): 0.539 ms with, 0.534 ms without - div.rn.f32's fast path is
+      // already ~8 instructions and the ray-cast is latency-, not issue-bound.  Kept as an A/B option (bit-identical), off by default.
       const char* e = getenv("TDM_FAST_DIV");
-      fast_div_ = fast_div_ok_ && !(e && e[0] == '0');
+      fast_div_ = fast_div_ok_ && e && e[0] == '1';
     }
     n_entries_ = (long long)o.num_buckets * o.bucket_size;
     int lo, hi;
@@ -773,6 +896,11 @@ class FusionImpl final : public FusionIface {
     TDM_CUDA(cudaMalloc(&d_.voxels, (size_t)o.num_blocks * 512 * 8));
     TDM_CUDA(cudaMalloc(&d_.list, (size_t)o.num_blocks * sizeof(int4)));
     TDM_CUDA(cudaMalloc(&d_.counters, 8 * sizeof(int)));
+    TDM_CUDA(cudaMalloc(&d_.bbox, 6 * sizeof(int)));
+    {
+      const int init[6] = {INT_MAX, INT_MAX, INT_MAX, INT_MIN, INT_MIN, INT_MIN};
+      TDM_CUDA(cudaMemcpy(d_.bbox, init, sizeof(init), cudaMemcpyHostToDevice));
+    }
     TDM_CUDA(cudaMalloc(&d_vis_list_, (size_t)o.num_blocks * sizeof(int)));
     {
       int per_sm = 0, sms = 0;
@@ -806,7 +934,8 @@ class FusionImpl final : public FusionIface {
   ~FusionImpl() override {
     cudaSetDevice(device_);
     cudaStreamSynchronize(stream_);
-    cudaFree(d_.keys); cudaFree(d_.ptrs); cudaFree(d_.voxels); cudaFree(d_.list); cudaFree(d_.counters); cudaFree(d_vis_list_);
+    for (void* q : ipc_opened_) cudaIpcCloseMemHandle(q);
+    cudaFree(d_.keys); cudaFree(d_.ptrs); cudaFree(d_.voxels); cudaFree(d_.list); cudaFree(d_.counters); cudaFree(d_.bbox); cudaFree(d_vis_list_);
     cudaFreeHost(h_bgr_in_); cudaFreeHost(h_depth_in_); cudaFree(d_bgr_in_); cudaFree(d_depth_in_);
     for (int half = 0; half < 2; ++half) { cudaFreeHost(h_bgr_out_[half]); cudaFreeHost(h_depth_out_[half]); }
     cudaFree(d_bgr_out_); cudaFree(d_depth_out_); cudaFreeHost(h_counters_);
@@ -886,6 +1015,63 @@ class FusionImpl final : public FusionIface {
     TDM_CHECK(!have_scan_, "set_slab must be called before the first scan");
     d_.slab_lo = z_lo;
     d_.slab_hi = z_hi;
+  }
+
+  // Peer view (pixel-partitioned ray-cast): export this instance's tables, attach everybody's.
+  void peer_export(tdm_fusion_peer_handle* out) override {
+    TDM_CUDA(cudaSetDevice(device_));
+    std::memset(out, 0, sizeof(*out));
+    out->keys_ptr = (unsigned long long)(uintptr_t)d_.keys;
+    out->ptrs_ptr = (unsigned long long)(uintptr_t)d_.ptrs;
+    out->voxels_ptr = (unsigned long long)(uintptr_t)d_.voxels;
+    out->device = device_;
+    out->pid = (long long)getpid();
+    out->num_buckets = d_.o.num_buckets; out->bucket_size = d_.o.bucket_size;
+    out->slab_lo = d_.slab_lo; out->slab_hi = d_.slab_hi;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    TDM_CUDA(cudaIpcGetMemHandle((cudaIpcMemHandle_t*)out->ipc_keys, d_.keys));
+    TDM_CUDA(cudaIpcGetMemHandle((cudaIpcMemHandle_t*)out->ipc_ptrs, d_.ptrs));
+    TDM_CUDA(cudaIpcGetMemHandle((cudaIpcMemHandle_t*)out->ipc_voxels, d_.voxels));
+  }
+  void peer_attach(const tdm_fusion_peer_handle* all, int world, int rank) override {
+    TDM_CHECK(world >= 1 && world <= 8 && rank >= 0 && rank < world, "peer_attach: world must be 1..8");
+    TDM_CHECK(d_.il_k == 0, "the peer view needs contiguous Z-slabs (set_slab), not the interleaved partition");
+    TDM_CUDA(cudaSetDevice(device_));
+    for (int r = 0; r < world; ++r) {
+      const tdm_fusion_peer_handle& h = all[r];
+      TDM_CHECK(h.num_buckets == d_.o.num_buckets && h.bucket_size == d_.o.bucket_size, "peer_attach: hash table geometry differs between ranks");
+      TDM_CHECK(r == 0 || h.slab_lo == all[r - 1].slab_hi, "peer_attach: slabs must be contiguous in rank order and WITHOUT halo rows");
+      void *k = nullptr, *p = nullptr, *v = nullptr;
+      if (r == rank) {
+        k = d_.keys; p = d_.ptrs; v = d_.voxels;
+      } else if (h.pid == (long long)getpid()) {      // another instance of this process (tests; single-process multi-GPU)
+        k = (void*)(uintptr_t)h.keys_ptr; p = (void*)(uintptr_t)h.ptrs_ptr; v = (void*)(uintptr_t)h.voxels_ptr;
+        if (h.device != device_) {
+          int can = 0;
+          TDM_CUDA(cudaDeviceCanAccessPeer(&can, device_, h.device));
+          TDM_CHECK(can, "peer_attach: no peer access between the two devices");
+          const cudaError_t e = cudaDeviceEnablePeerAccess(h.device, 0);
+          if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) TDM_CUDA(e);
+          cudaGetLastError();
+        }
+      } else {                                         // another process: CUDA IPC (maps the peer's allocation over NVLink / PCIe P2P)
+        TDM_CUDA(cudaIpcOpenMemHandle(&k, *(const cudaIpcMemHandle_t*)h.ipc_keys, cudaIpcMemLazyEnablePeerAccess));
+        TDM_CUDA(cudaIpcOpenMemHandle(&p, *(const cudaIpcMemHandle_t*)h.ipc_ptrs, cudaIpcMemLazyEnablePeerAccess));
+        TDM_CUDA(cudaIpcOpenMemHandle(&v, *(const cudaIpcMemHandle_t*)h.ipc_voxels, cudaIpcMemLazyEnablePeerAccess));
+        ipc_opened_.push_back(k); ipc_opened_.push_back(p); ipc_opened_.push_back(v);
+      }
+      d_.pr_keys[r] = (const unsigned long long*)k; d_.pr_ptrs[r] = (const int*)p; d_.pr_voxels[r] = (const uint2*)v;
+      d_.pr_lo[r] = h.slab_lo; d_.pr_hi[r] = h.slab_hi;
+    }
+    d_.pr_world = world; d_.pr_rank = rank;
+  }
+
+  void set_interleave(int rank, int world, int k_blocks, int z0_block) override {
+    TDM_CHECK(world >= 1 && rank >= 0 && rank < world && k_blocks >= 1, "bad interleave parameters");
+    TDM_CHECK(!have_scan_, "set_interleave must be called before the first scan");
+    if (world == 1) return;   // one rank stores everything
+    d_.il_k = k_blocks; d_.il_world = world; d_.il_rank = rank; d_.il_z0 = z0_block;
+    d_.slab_lo = INT_MIN + 1;   // marks the volume as partitioned (mesh extraction refuses, ray-cast takes the SLAB path)
   }
 
   void synchronize() override {
@@ -1063,7 +1249,8 @@ class FusionImpl final : public FusionIface {
       if (raycast_shared_ && !raycast_persistent_ && !raycast_cache8_) {
         unsigned char* bo = d_bgr_out_ + (size_t)i * npx * 3;
         float* dout_i = d_depth_out_ + (size_t)i * npx;
-        const bool slab = (d_.slab_lo != INT_MIN || d_.slab_hi != INT_MAX) && slab_clip_;
+        const bool peer = d_.pr_world > 1;
+        const bool slab = !peer && (d_.slab_lo != INT_MIN || d_.slab_hi != INT_MAX) && slab_clip_;
         long long* keys = nullptr;
         if (slab_exchange_ && i == 0) {
           if (!d_hit_keys_) TDM_CUDA(cudaMalloc(&d_hit_keys_, npx * sizeof(long long)));
@@ -1076,7 +1263,8 @@ class FusionImpl final : public FusionIface {
     else if (fast_div_) k_raycast_shared<TW_, TH_, MB_, false, true><<<GRID_, THREADS_, 0, stream_>>>(d_, render_poses_[i], bo, dout_i, keys);   \
     else k_raycast_shared<TW_, TH_, MB_, false, false><<<GRID_, THREADS_, 0, stream_>>>(d_, render_poses_[i], bo, dout_i, keys);       \
   } while (0)
-        if (raycast_tile_ == 0) TDM_RAY(16, 16, 5, grid, 256);
+        if (peer) k_raycast_shared<8, 8, 24, false, false, true><<<dim3(cdiv(d_.o.width, 8), cdiv(d_.o.height, 8)), 64, 0, stream_>>>(d_, render_poses_[i], bo, dout_i, keys);
+        else if (raycast_tile_ == 0) TDM_RAY(16, 16, 5, grid, 256);
         else if (raycast_tile_ == 1) TDM_RAY(8, 8, 24, dim3(cdiv(d_.o.width, 8), cdiv(d_.o.height, 8)), 64);
         else if (raycast_tile_ == 2) TDM_RAY(8, 4, 48, dim3(cdiv(d_.o.width, 8), cdiv(d_.o.height, 4)), 32);
         else TDM_RAY(16, 8, 12, dim3(cdiv(d_.o.width, 16), cdiv(d_.o.height, 8)), 128);
@@ -1239,6 +1427,7 @@ class FusionImpl final : public FusionIface {
   int raycast_tile_ = 1;   // 0: 16x16 px CTAs, 1: 8x8, 2: 8x4 (one warp), 3: 16x8
   bool raycast_persistent_ = false, integrate_compact_ = true;   // measured: persistent 0.875 ms vs 0.820 ms (instruction-bound, not imbalance-bound)
   bool fast_div_ok_ = false, fast_div_ = false;   // constant-divisor division in the ray-cast (cdiv_): bit-identical, 3 instructions per division
+  std::vector<void*> ipc_opened_;   // peers' allocations mapped with cudaIpcOpenMemHandle (closed in the destructor)
   bool slab_clip_ = true;        // Z-slab volumes: rays are only sampled inside the slab's z range (bit-identical, see k_raycast_shared)
   bool slab_exchange_ = false;   // Z-slab volumes: the ray-cast emits packed nearest-hit keys for the exchange step, the per-slab
                                  // render is not copied back and GetRenderResult does not wait (tandem_b200.parallel)

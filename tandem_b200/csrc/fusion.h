@@ -15,6 +15,9 @@ class FusionIface {
   virtual void render_async(const float* const* poses, int n) = 0;
   virtual void get_render_result(unsigned char** bgr, float** depth, int n) = 0;
   virtual void set_slab(int z_block_lo, int z_block_hi) = 0;
+  virtual void set_interleave(int rank, int world, int k_blocks, int z0_block) = 0;
+  virtual void peer_export(tdm_fusion_peer_handle* out) = 0;
+  virtual void peer_attach(const tdm_fusion_peer_handle* all, int world, int rank) = 0;
   virtual void synchronize() = 0;
   virtual void get_stats(tdm_fusion_stats* s) = 0;
   virtual long long dump_blocks(int* coords, void* voxels, size_t cap) = 0;

@@ -111,6 +111,7 @@ struct DevConv {
   int nsplit = 1;          // N slices (blockIdx.y) for the 64-channel layers
   bool hilo = false;       // weights carried as hi + lo 16-bit halves (N doubled), see conv_tc.cuh
   void* bimg_is = nullptr; // input-stationary B image (3-D stride-1 convs), conv_tc_is.cuh
+  int npad_is = 0;         // its column padding: 8 for the <= 8-channel outputs with hi/lo weights (tight [hi|lo] packing), else npad
   bool tc_up2 = false;     // MODE 3: conv3x3 of a nearest-x2 up-sampled map on the coarse grid (fused FPN tail)
   bool tc_s2 = false;      // stride-2 conv on the tensor-map (strided TMA) kernel, conv_tc_s2.cuh
   void* bimg_s2 = nullptr;
@@ -203,6 +204,7 @@ class MvsnetEngine final : public MvsnetIface {
     else if (key == "use_is") use_is_ = value != 0;
     else if (key == "fork_fpn") fork_fpn_ = value != 0;
     else if (key == "prob_direct") prob_direct_ = value != 0;
+    else if (key == "direct_conv00") direct_conv00_ = value != 0;
     else throw Error("unknown option " + key);
   }
 
@@ -529,9 +531,10 @@ class MvsnetEngine final : public MvsnetIface {
     TDM_CUDA(cudaMemcpy(dc.bimg, img.data(), img.size() * sizeof(TB), cudaMemcpyHostToDevice));
     if (fc.kd == 3 && fc.cin <= 32 && dc.nsplit == 1) {
       std::vector<TB> im2;
-      if (fc.cin == 8) tc::build_b_image_is<TB, 8>(fc.w.data(), fc.cin, fc.cout, dc.npad, im2, +cvt, dc.hilo, +back);
-      else if (fc.cin == 16) tc::build_b_image_is<TB, 16>(fc.w.data(), fc.cin, fc.cout, dc.npad, im2, +cvt, dc.hilo, +back);
-      else tc::build_b_image_is<TB, 32>(fc.w.data(), fc.cin, fc.cout, dc.npad, im2, +cvt, dc.hilo, +back);
+      dc.npad_is = (dc.hilo && fc.cout <= 8 && is_npad8_) ? 8 : dc.npad;
+      if (fc.cin == 8) tc::build_b_image_is<TB, 8>(fc.w.data(), fc.cin, fc.cout, dc.npad_is, im2, +cvt, dc.hilo, +back);
+      else if (fc.cin == 16) tc::build_b_image_is<TB, 16>(fc.w.data(), fc.cin, fc.cout, dc.npad_is, im2, +cvt, dc.hilo, +back);
+      else tc::build_b_image_is<TB, 32>(fc.w.data(), fc.cin, fc.cout, dc.npad_is, im2, +cvt, dc.hilo, +back);
       TDM_CUDA(cudaMalloc(&dc.bimg_is, im2.size() * sizeof(TB)));
       TDM_CUDA(cudaMemcpy(dc.bimg_is, im2.data(), im2.size() * sizeof(TB), cudaMemcpyHostToDevice));
     }
@@ -541,6 +544,17 @@ class MvsnetEngine final : public MvsnetIface {
 
   void upload_weights() {
     const std::string f = "feature_net.";
+    if constexpr (kRawInput) {
+      // fused pre-processing + conv0.0 (k_conv00_u8): BN-folded fp32 weights of the 3 real input channels -> constant bank
+      const FoldedConv c3 = fold_conv(wf_, f + "conv0.0.conv.weight", "", f + "conv0.0.bn", false);   // [9][3][8]
+      TDM_CHECK(c3.cin == 3 && c3.cout == 8 && c3.kh == 3 && c3.kw == 3 && c3.kd == 1 && c3.bias.size() == 8, "unexpected conv0.0 shape");
+      Conv00Weights cw;
+      for (int t = 0; t < 9; ++t)
+        for (int ci = 0; ci < 3; ++ci)
+          for (int co = 0; co < 8; ++co) cw.w[t * 3 + ci][co] = c3.w[((size_t)t * 3 + ci) * 8 + co];
+      for (int co = 0; co < 8; ++co) cw.bias[co] = c3.bias[co];
+      TDM_CUDA(cudaMemcpyToSymbol(c_conv00, &cw, sizeof(cw), (size_t)slot_ * sizeof(Conv00Weights)));
+    }
     {
       FoldedConv c00 = fold_conv(wf_, f + "conv0.0.conv.weight", "", f + "conv0.0.bn", false, 8);
       if constexpr (kRawInput)   // the image is stored as exact u8/256 (k_preprocess_bgr<RAW255>): 256/255 lives in the weights
@@ -924,15 +938,20 @@ class MvsnetEngine final : public MvsnetIface {
       }
       if (use_is_ && c.bimg_is && c.kd == 3) {
         if (bo.f32) {
-          if (c.cin == 8 && c.cout == 1 && bi.kind == 1 && c.hilo) { tc_is_inst<TA, TA, 8, 16, true, true>(wkey, bi, c, nullptr, bo, false); return true; }
+          if (c.cin == 8 && c.cout == 1 && bi.kind == 1 && c.hilo) {
+            if (c.npad_is == 8) tc_is_inst<TA, TA, 8, 8, true, true>(wkey, bi, c, nullptr, bo, false);
+            else tc_is_inst<TA, TA, 8, 16, true, true>(wkey, bi, c, nullptr, bo, false);
+            return true;
+          }
           return false;
         }
 #define TDM_IS(TI, CI, NP, HL)                                                             \
-  if (c.cin == CI && c.npad == NP && c.hilo == HL) {                                       \
+  if (c.cin == CI && c.npad_is == NP && c.hilo == HL) {                                    \
     tc_is_inst<TI, TA, CI, NP, false, HL>(wkey, bi, c, rp, bo, relu);                      \
     return true;                                                                           \
   }
         if (bi.kind == 2) {
+          TDM_IS(TV, 32, 8, true) TDM_IS(TV, 16, 8, true) TDM_IS(TV, 8, 8, true)
           TDM_IS(TV, 32, 16, true) TDM_IS(TV, 16, 16, true) TDM_IS(TV, 8, 16, true)
         } else {
           TDM_IS(TA, 16, 16, true) TDM_IS(TA, 32, 32, false)
@@ -1216,12 +1235,24 @@ class MvsnetEngine final : public MvsnetIface {
       ViewPtrs vp;
       for (int v = 0; v < V; ++v) vp.v[v] = d_bgr_ + (size_t)v * H * W * 3;
       const long long n = (long long)V * H * W;
-      rec_begin("preprocess", 3.0 * n + 8.0 * n * sizeof(TA), 0);
-      k_preprocess_bgr<TA, kRawInput><<<cdiv(n, 256), 256, 0, stream_>>>(vp, p8<TA>(bufs_.at("f.img")), V, H * W);
-      TDM_CUDA(cudaGetLastError());
-      rec_end();
+      bool fused = false;
+      if constexpr (kRawInput) {
+        if (direct_conv00_) {
+          fused = true;
+          rec_begin("f.conv0.0[u8-direct]", 3.0 * n + 8.0 * n * sizeof(TA), 2.0 * 27 * 8 * (double)n);
+          k_conv00_u8<TA><<<dim3(cdiv(W, 32), cdiv(H, 8), V), 256, 0, stream_>>>(d_bgr_, p8<TA>(bufs_.at("f.c0_0")), H, W, slot_);
+          TDM_CUDA(cudaGetLastError());
+          rec_end();
+        }
+      }
+      if (!fused) {
+        rec_begin("preprocess", 3.0 * n + 8.0 * n * sizeof(TA), 0);
+        k_preprocess_bgr<TA, kRawInput><<<cdiv(n, 256), 256, 0, stream_>>>(vp, p8<TA>(bufs_.at("f.img")), V, H * W);
+        TDM_CUDA(cudaGetLastError());
+        rec_end();
+        conv("f.conv0.0", "f.img", "f.c0_0", 1, 1, 1, true);
+      }
     }
-    conv("f.conv0.0", "f.img", "f.c0_0", 1, 1, 1, true);
     conv("f.conv0.1", "f.c0_0", "f.c3", 1, 1, 1, true);
     conv("f.conv1.0", "f.c3", "f.c1_0", 1, 2, 2, true);
     conv("f.conv1.1", "f.c1_0", "f.c1_1", 1, 1, 1, true);
@@ -1402,10 +1433,12 @@ class MvsnetEngine final : public MvsnetIface {
   int slot_ = 0;           // index into c_call_params
   int tc_smem_kb_ = 225;   // shared-memory budget of the tile planner (<= 113 lets two CTAs share an SM)
   bool use_is_ = true;   // input-stationary kernel for the 3-D stride-1 convs
+  bool is_npad8_ = std::getenv("TDM_IS_NPAD8") ? std::getenv("TDM_IS_NPAD8")[0] != '0' : true;   // tight [hi|lo] packing of <= 8 output channels (A/B: TDM_IS_NPAD8=0)
   bool fused_fpn_ = false;
   bool prob_direct_ = false;  // `prob` (8 -> 1 channels) on the FMA pipes (k_prob_direct): measured SLOWER than the 1/16-utilised tensor-core tile (0.181 vs 0.143 ms over the three stages, 812 vs 850 keyframes/s); kept as an A/B option
   bool have_prob_w_ = false;
   ProbWeights prob_w_[3] = {};
+  bool direct_conv00_ = true; // 16-bit engines: pre-processing + conv0.0 fused on the FMA pipes (k_conv00_u8); 0 = preprocess + tensor-core conv
   bool fork_fpn_ = true;      // FPN tail on a second stream / graph branch (A/B: set_option("fork_fpn", 0))
   cudaStream_t side_stream_ = nullptr;
   cudaEvent_t ev_fork_ = nullptr, ev_join_ = nullptr;

@@ -67,6 +67,61 @@ __global__ void k_preprocess_bgr(ViewPtrs src, P8<T> out, int V, int HW) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// a1 + the first FeatureNet layer in one kernel (16-bit engines): conv0.0 is 3 -> 8 channels, 3x3 (module.py:500) - 216 MACs per
+// pixel, nothing for the FMA pipes - while the generic route costs two full-resolution round trips: k_preprocess_bgr writes a
+// zero-padded 8-channel 16-bit image (5 of 8 channels are padding: 34 MB for 6.45 MB of pixels) that the tensor-core conv reads
+// back.  Here every thread owns one pixel: the u8 BGR tile (+1 halo, zero outside the image = the conv's zero padding) is
+// staged in shared memory, x = u8 / 255 is formed in fp32 exactly as dr_mvsnet.cpp:203-210 does, the 27 x 8 products run as
+// FFMA against BN-folded fp32 weights held in the constant bank (uniform operands, no load instructions), bias + ReLU, one
+// 16-byte store.  (Dividing inside the 27-tap loop instead of at staging time cost 65 us instead of the ~20 us of the FMAs.)  No 16-bit rounding of the input or of the weights at all.
+// ------------------------------------------------------------------------------------------------
+struct Conv00Weights {
+  float w[27][8];   // [tap = kh*3+kw][cin = R,G,B][cout] flattened as [(tap*3 + cin)][cout]
+  float bias[8];
+};
+__constant__ Conv00Weights c_conv00[8 /* kMaxEngines */];
+
+template <typename T>
+__global__ void __launch_bounds__(256) k_conv00_u8(const unsigned char* __restrict__ bgr /*[V][H][W][3], reference view first*/, P8<T> out, int H, int W, int slot) {
+  constexpr int TX = 32, TY = 8;
+  __shared__ float tile[TY + 2][(TX + 2) * 3];   // x = u8 / 255 formed ONCE per input value (IEEE division, dr_mvsnet.cpp:203-210)
+  const Conv00Weights& cw = c_conv00[slot];
+  const int v = blockIdx.z;
+  const int x0 = blockIdx.x * TX, y0 = blockIdx.y * TY;
+  const unsigned char* img = bgr + (size_t)v * H * W * 3;
+  for (int i = threadIdx.x; i < (TY + 2) * (TX + 2); i += 256) {
+    const int ty = i / (TX + 2), tx = i - ty * (TX + 2);
+    const int yy = y0 + ty - 1, xx = x0 + tx - 1;
+    float b = 0.f, g = 0.f, r = 0.f;
+    if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
+      const unsigned char* s = img + 3ll * ((long long)yy * W + xx);
+      b = __fdiv_rn((float)s[0], 255.0f); g = __fdiv_rn((float)s[1], 255.0f); r = __fdiv_rn((float)s[2], 255.0f);
+    }
+    tile[ty][3 * tx] = r; tile[ty][3 * tx + 1] = g; tile[ty][3 * tx + 2] = b;   // network channel order is RGB
+  }
+  __syncthreads();
+  const int lx = threadIdx.x % TX, ly = threadIdx.x / TX;
+  const int x = x0 + lx, y = y0 + ly;
+  if (x >= W || y >= H) return;
+  float acc[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) acc[c] = cw.bias[c];
+#pragma unroll
+  for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+    for (int kw = 0; kw < 3; ++kw)
+#pragma unroll
+      for (int ci = 0; ci < 3; ++ci) {
+        const float xin = tile[ly + kh][3 * (lx + kw) + ci];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) acc[c] = fmaf(xin, cw.w[(kh * 3 + kw) * 3 + ci][c], acc[c]);
+      }
+#pragma unroll
+  for (int c = 0; c < 8; ++c) acc[c] = fmaxf(acc[c], 0.f);
+  store_vec<T, 8>(out.p + out.pos(v, y, x), acc);
+}
+
+// ------------------------------------------------------------------------------------------------
 // Generic direct convolution / transposed convolution, channels-last.
 // ------------------------------------------------------------------------------------------------
 struct ConvGeom {

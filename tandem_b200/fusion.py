@@ -135,6 +135,23 @@ class DrFusion:
         """Multi-GPU extension: keep only voxel blocks with z_block_lo <= z < z_block_hi (see include/tandem_b200.h)."""
         check(lib().tdm_fusion_set_slab(self._h, int(z_block_lo), int(z_block_hi)))
 
+    def set_interleave(self, rank, world, k_blocks=4, z0_block=0):
+        """Interleaved Z-slab partition (include/tandem_b200.h): block row z -> rank ((z - z0) div k) mod world, + halo rows."""
+        check(lib().tdm_fusion_set_interleave(self._h, int(rank), int(world), int(k_blocks), int(z0_block)))
+
+    def peer_export(self):
+        """bytes of this instance's tdm_fusion_peer_handle (picklable: gather it over the ranks, then peer_attach)."""
+        from ._lib import FusionPeerHandle
+        h = FusionPeerHandle()
+        check(lib().tdm_fusion_peer_export(self._h, ctypes.byref(h)))
+        return bytes(h)
+
+    def peer_attach(self, handles, rank):
+        """handles: list of world peer_export() blobs in rank order.  Enables the pixel-partitioned ray-cast (tandem_b200.h)."""
+        from ._lib import FusionPeerHandle
+        arr = (FusionPeerHandle * len(handles))(*[FusionPeerHandle.from_buffer_copy(b) for b in handles])
+        check(lib().tdm_fusion_peer_attach(self._h, arr, len(handles), int(rank)))
+
     def render_keys_device(self, render_index=0):
         """Device pointer (int) of the packed nearest-hit keys of a render + element count (see include/tandem_b200.h)."""
         ptr = ctypes.c_void_p()

@@ -105,3 +105,32 @@ def reduce_nearest_hit_device(dist, fusion, render_index=0, device="cuda:0", out
         with torch.cuda.stream(torch.cuda.ExternalStream(fusion.stream(), device=device)):
             dist.all_reduce(t, op=dist.ReduceOp.MIN)
     return fusion.unpack_keys(ptr, out)
+
+
+def attach_peers(dist, fusion, rank, world):
+    """Pixel-partitioned ray-cast over the Z-slab-partitioned volume: gather every rank's exported tables (CUDA IPC handles) and
+    map them into this rank (NVLink P2P).  Call once, after set_slab(owned_lo, owned_hi) and before the first scan."""
+    mine = fusion.peer_export()
+    if dist is None or world == 1:
+        fusion.peer_attach([mine], 0)
+        return
+    blobs = [None] * world
+    dist.all_gather_object(blobs, mine)
+    fusion.peer_attach(blobs, rank)
+
+
+_barrier_token = {}
+
+
+def stream_barrier(dist, fusion, device="cuda:0"):
+    """Stream-ordered barrier over the ranks, enqueued on the DrFusion handle's own stream (a 1-element NCCL all-reduce): work
+    enqueued on that stream afterwards - the ray-cast that reads the peers' voxels - runs only after every rank's earlier work
+    on ITS stream - the integration of the same scan - has finished.  No host synchronisation."""
+    if dist is None:
+        return
+    import torch
+    t = _barrier_token.get(device)
+    if t is None:
+        t = _barrier_token[device] = torch.zeros(1, dtype=torch.int32, device=device)
+    with torch.cuda.stream(torch.cuda.ExternalStream(fusion.stream(), device=device)):
+        dist.all_reduce(t)

@@ -231,6 +231,104 @@ def test_z_slab_partition_matches_single_volume():
     assert np.median(np.abs(dm[both] - fd[both])) < 1e-3 and np.quantile(np.abs(dm[both] - fd[both]), 0.99) < 0.02
 
 
+@pytest.mark.parametrize("world", [2, 3])
+def test_pixel_partitioned_raycast_over_peer_slabs_is_bit_identical(world):
+    """The fused form of the slab exchange (tdm_fusion_peer_export / peer_attach): each rank integrates only its OWN Z-slab (no
+    halo rows), renders only its pixel tiles, but marches them through the whole volume reading every voxel from the owning
+    rank's tables.  The MIN-combined render must equal the single-volume render BIT FOR BIT (depth and colour) - occluders in
+    other slabs included - which the slab-local ray-cast cannot deliver.  Here the ranks are instances of one process."""
+    from tandem_b200.parallel import pack_hits, unpack_hits
+    poses, frames = _scene_frames(3)
+    full = DrFusion(_opts())
+    for (bgr, depth), pose in zip(frames, poses):
+        full.IntegrateScanAsync(bgr, depth, pose)
+        full.RenderAsync([poses[1]])
+        (fb,), (fd,) = full.GetRenderResult()
+    cf, _ = full.dump_blocks()
+    zmin, zmax = int(cf[:, 2].min()), int(cf[:, 2].max()) + 1
+    n = zmax - zmin
+    bounds = [zmin + (n * r) // world for r in range(world)] + [zmax]
+    bounds[0], bounds[-1] = -(1 << 19), 1 << 19                      # the outer slabs own everything beyond the map
+    ranks = []
+    for r in range(world):
+        f = DrFusion(_opts())
+        f.set_slab(bounds[r], bounds[r + 1])
+        ranks.append(f)
+    blobs = [f.peer_export() for f in ranks]
+    for r, f in enumerate(ranks):
+        f.peer_attach(blobs, r)
+    keys = None
+    for k, ((bgr, depth), pose) in enumerate(zip(frames, poses)):
+        for f in ranks:
+            f.IntegrateScanAsync(bgr, depth, pose)
+        for f in ranks:
+            f.Synchronize()                                           # the barrier between integration and the peer reads
+        rend = []
+        for f in ranks:
+            f.RenderAsync([poses[1]])
+            (rb,), (rd,) = f.GetRenderResult()
+            rend.append((rd.copy(), rb.copy()))
+    assert sum(f.stats()["allocated_blocks"] for f in ranks) == cf.shape[0], "slabs without halo partition the block set"
+    tiles = [(rd > 0).sum() for rd, _ in rend]
+    assert all(t > 0 for t in tiles), "every rank must have rendered some of the pixels"
+    for rd, rb in rend:
+        kk = pack_hits(rd, rb)
+        keys = kk if keys is None else np.minimum(keys, kk)
+    dm, bm = unpack_hits(keys)
+    assert np.array_equal(dm, fd), f"depth differs on {np.mean(dm != fd):.5f} of the pixels"
+    assert np.array_equal(bm, fb)
+
+
+@pytest.mark.parametrize("world,k", [(2, 1), (3, 2), (4, 1)])
+def test_interleaved_slab_partition_matches_single_volume(world, k):
+    """Interleaved Z-slabs (tdm_fusion_set_interleave: block row z -> rank ((z - z0) div k) mod world, + halo rows): the union of
+    the OWNED blocks of all ranks is the single-volume map bit for bit, the slab-clipped ray-cast of each rank equals its own
+    unclipped march bit for bit (skipped samples only ever read 'no voxel'), and the nearest-hit MIN over the ranks' renders
+    reproduces the single-volume render (same surface; sample positions differ where a ray crosses a foreign slab)."""
+    from tandem_b200.parallel import pack_hits, unpack_hits
+    poses, frames = _scene_frames(3)
+    full = DrFusion(_opts())
+    for (bgr, depth), pose in zip(frames, poses):
+        full.IntegrateScanAsync(bgr, depth, pose)
+        full.RenderAsync([poses[0]])
+        (fb,), (fd,) = full.GetRenderResult()
+    cf, vf = full.dump_blocks()
+    z0 = -3
+    owner = lambda z: (np.floor_divide(z - z0, k)) % world
+    owned_c, owned_v, keys = [], [], None
+    for r in range(world):
+        rend = {}
+        for clip in (1, 0):
+            f = DrFusion(_opts())
+            f.set_interleave(r, world, k, z0)
+            f.set_option("slab_clip", clip)
+            for (bgr, depth), pose in zip(frames, poses):
+                f.IntegrateScanAsync(bgr, depth, pose)
+                f.RenderAsync([poses[0]])
+                (rb,), (rd,) = f.GetRenderResult()
+            rend[clip] = (rd.copy(), rb.copy())
+        assert np.array_equal(rend[1][0], rend[0][0]) and np.array_equal(rend[1][1], rend[0][1]), "clipped march differs from the unclipped one"
+        c, v = f.dump_blocks()
+        stored = (owner(c[:, 2]) == r) | (owner(c[:, 2] - 1) == r) | (owner(c[:, 2] + 1) == r)
+        assert stored.all(), "a rank stores a block row that is neither its own nor a halo"
+        own = owner(c[:, 2]) == r
+        owned_c.append(c[own]); owned_v.append(v[own])
+        kk = pack_hits(*rend[1])
+        keys = kk if keys is None else np.minimum(keys, kk)
+    cu, vu = np.concatenate(owned_c), np.concatenate(owned_v)
+    order = np.lexsort((cu[:, 2], cu[:, 1], cu[:, 0]))
+    assert np.array_equal(cu[order], cf), "union of owned blocks != single volume block set"
+    assert np.array_equal(vu[order]["weight"], vf["weight"]) and np.array_equal(vu[order]["sdf"], vf["sdf"])
+    assert np.array_equal(vu[order]["color"], vf["color"])
+    dm, bm = unpack_hits(keys)
+    hit_m, hit_f = dm > 0, fd > 0
+    assert np.mean(hit_m != hit_f) < 5e-3
+    both = hit_m & hit_f
+    err = np.abs(dm[both] - fd[both])
+    print(f"interleave world={world} k={k}: hit mismatch {np.mean(hit_m != hit_f):.5f}, depth err median {np.median(err):.2e} p99 {np.quantile(err, 0.99):.2e}, bit-equal {np.mean(dm == fd):.4f}")
+    assert np.median(err) < 1e-3 and np.quantile(err, 0.99) < 0.02
+
+
 # ---------------------------------------------------------------------------------------------------------------------
 # marching cubes (SURVEY.md 8f n4): DrFusion::ExtractMeshAsync / GetMeshSync / GetMesh vs the brute-force oracle
 def _sorted_tris(vert, cols):

@@ -19,7 +19,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from tandem_b200 import DrFusion, DrFusionOptions  # noqa: E402
-from tandem_b200.parallel import reduce_max, reduce_nearest_hit_device, slab_bounds  # noqa: E402
+from tandem_b200.parallel import attach_peers, reduce_max, reduce_nearest_hit_device, slab_bounds, stream_barrier  # noqa: E402
 from tandem_b200.synthetic import RoomScene, circle_trajectory  # noqa: E402
 
 
@@ -27,6 +27,8 @@ def main(argv=None):
     ap = argparse.ArgumentParser()
     ap.add_argument("--frames", type=int, default=12)
     ap.add_argument("--warmup", type=int, default=2, help="untimed frames (same stream, integrated before the timed ones)")
+    ap.add_argument("--interleave", type=int, default=0, help="interleaved slabs of this many block rows (0: contiguous slabs)")
+    ap.add_argument("--peer", action="store_true", help="pixel-partitioned ray-cast over the slabs: P2P voxel reads inside the ray-cast kernel (bit-identical to one volume)")
     ap.add_argument("--legacy", action="store_true", help="round-1 path: unclipped slab ray-cast, per-slab D2H, pack kernel + host syncs")
     a = ap.parse_args(argv)
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
@@ -59,8 +61,14 @@ def main(argv=None):
     # 1000 m^3 / (8 cm)^3 = 1.95 M blocks -> 2.5 M blocks (10 GB of voxels) instead of initDr's 1 M
     opt = DrFusionOptions(height=H, width=W, num_blocks=2500000, num_buckets=2500000, **intr)
     f = DrFusion(opt, device=local)
-    if world > 1:
-        f.set_slab(alo, ahi)
+    if world > 1 and a.peer:
+        f.set_slab(-(1 << 19) if rank == 0 else lo, (1 << 19) if rank == world - 1 else hi)   # owned rows only, no halo
+        attach_peers(dist, f, rank, world)
+    elif world > 1:
+        if a.interleave > 0 and not a.legacy:
+            f.set_interleave(rank, world, a.interleave, zmin)
+        else:
+            f.set_slab(alo, ahi)
     if a.legacy:
         f.set_option("slab_clip", 0)
     else:
@@ -90,6 +98,8 @@ def main(argv=None):
             sync()
             t0 = time.perf_counter()
         f.IntegrateScanAsync(bgr, depth, pose)
+        if a.peer:
+            stream_barrier(dist, f, dev)        # every rank's integration of this scan precedes every rank's peer reads
         f.RenderAsync([pose])
         f.GetRenderResult()
         outs.append(reduce_nearest_hit_device(dist, f, 0, dev, out=None if a.legacy else ring[k % n_ring]))
@@ -105,7 +115,8 @@ def main(argv=None):
                 "frames": a.frames, "ms_per_frame(max over ranks, wall incl. H2D/D2H)": ms, "frames_per_s": 1e3 / ms,
                 "max_blocks_per_rank": int(blocks), "slab_blocks(owned, rank 0)": [lo, hi],
                 "device_ms_last_frame(max over ranks)": {"allocate+integrate": mi, "raycast": mr},
-                "mode": "legacy (round 1)" if a.legacy else "slab-clipped ray-cast + fused key packing + all-reduce on the fusion stream"}
+                "mode": "legacy (round 1)" if a.legacy else "slab-clipped ray-cast + fused key packing + all-reduce on the fusion stream",
+                "partition": "contiguous Z-slabs, pixel-partitioned ray-cast with P2P voxel reads" if a.peer else "contiguous Z-slabs" if (a.legacy or a.interleave <= 0) else f"interleaved Z-slabs of {a.interleave} block rows (+1 halo row each side)"}
         if world > 1:     # parity against the un-partitioned volume
             full = DrFusion(opt, device=local)
             mism, med, p99 = [], [], []
@@ -122,6 +133,8 @@ def main(argv=None):
             line.update({"single_volume_blocks": full.stats()["allocated_blocks"], "hit_mismatch_max": max(mism),
                          "depth_abs_err_median_max_m": max(med), "depth_abs_err_p99_max_m": max(p99)})
             assert max(mism) < 5e-3 and max(med) < 1e-3 and max(p99) < 0.03, line
+            if a.peer:
+                assert max(mism) == 0 and max(p99) == 0, ("the peer ray-cast must reproduce the single volume exactly", line)
         print(json.dumps(line))
         result = line
     else:
