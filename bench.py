@@ -295,11 +295,10 @@ def ncu_traffic(record_name):
     files = sorted(glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r*_ncu_traffic.json")))
     if not files or not record_name.endswith("cost_volume"):
         return None, None
-    pat = {"s1": "k_cost_volume_va16<__nv_bfloat16, 16, 2,", "s2": "k_cost_volume_va16<__nv_bfloat16, 16, 1,",
-           "s3": "k_cost_volume_va16<__nv_bfloat16, 8, 1,"}.get(record_name[:2])
+    pat = {"s1": ", 16, 2, ", "s2": ", 16, 1, ", "s3": ", 8, 1, "}.get(record_name[:2])   # <TV, C, CSPLIT, ND, ACC16> of the stage's kernel
     try:
         for k, v in json.load(open(files[-1])).items():
-            if pat and pat in k:
+            if pat and "k_cost_volume_va16<" in k and pat in k:
                 return float(v), os.path.basename(files[-1])
     except (OSError, ValueError):
         pass

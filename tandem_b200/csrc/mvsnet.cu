@@ -27,6 +27,7 @@
 #include "conv_tc.cuh"
 #include "conv_tc_s2.cuh"
 #include "conv_tc_is.cuh"
+#include "cost_volume_tma.cuh"
 #include "weights.h"
 
 namespace tdm {
@@ -160,6 +161,12 @@ class MvsnetEngine final : public MvsnetIface {
     cudaSetDevice(device_);
     free_plan();
     for (auto& kv : convs_) { cudaFree(kv.second.w); cudaFree(kv.second.bias); cudaFree(kv.second.bimg); cudaFree(kv.second.bimg_s2); cudaFree(kv.second.bimg_is); }
+    if (d_cv_stats_) {
+      unsigned st[2] = {0, 0};
+      if (std::getenv("TDM_DEBUG_PLAN") && cudaMemcpy(st, d_cv_stats_, sizeof(st), cudaMemcpyDeviceToHost) == cudaSuccess)
+        fprintf(stderr, "[cv_tma] (CTA, view) pairs staged by TMA: %u, fallen back to global gathers: %u\n", st[0], st[1]);
+      cudaFree(d_cv_stats_);
+    }
     if (select_state_) cudaFree(select_state_);
     release_slot(slot_);
     if (d_bs3_) cudaFree(d_bs3_);
@@ -186,7 +193,7 @@ class MvsnetEngine final : public MvsnetIface {
     if (key == "filter_all_stages") filter_all_ = value != 0;
     else if (key == "use_graph") use_graph_ = value != 0;
     else if (key == "use_pdl") use_pdl_ = value != 0;
-    else if (key == "cv_variant") { TDM_CHECK(value >= 0 && value <= 4, "cv_variant out of range"); cv_variant_ = value; }
+    else if (key == "cv_variant") { TDM_CHECK(value >= 0 && value <= 5, "cv_variant out of range"); cv_variant_ = value; }
     else if (key == "tc_smem_kb") { TDM_CHECK(value >= 48 && value <= 225, "tc_smem_kb out of range"); tc_smem_kb_ = value; tc_cache_.clear(); s2_cache_.clear(); }
     else if (key.rfind("depth_num_stage", 0) == 0 && key.size() == 16 && key[15] >= '1' && key[15] <= '3') {
       // override the checkpoint's MODEL.DEPTH_NUM for one stage (BASELINE.json configs[0] uses 32 stage-1 hypotheses;
@@ -643,6 +650,7 @@ class MvsnetEngine final : public MvsnetIface {
   }
   void free_plan() {
     drop_graph();
+    cv_tmap_ok_ = false;
     s2_cache_.clear();
     tc_cache_.clear();
     for (auto& kv : bufs_) cudaFree(kv.second.p);
@@ -1135,10 +1143,29 @@ class MvsnetEngine final : public MvsnetIface {
     const float* dm = s > 1 ? fbuf(k + "dmin") : nullptr;
     bool done = false;
     if constexpr (std::is_same<TA, __half>::value) {
+      if (va_ && cv_variant_ == 5 && fb.C == 8 && vb.D == 8) {
+        // A/B: source-view tiles staged in shared memory by TMA (cost_volume_tma.cuh); other stages run variant 3
+        if (!cv_tmap_ok_) {
+          const cuuint64_t dims[4] = {8, (cuuint64_t)(fb.W + 2), (cuuint64_t)(fb.H + 2), (cuuint64_t)(fb.D + 2 * fb.pd)};
+          const cuuint64_t strides[3] = {16, (cuuint64_t)(fb.W + 2) * 16, (cuuint64_t)(fb.W + 2) * (fb.H + 2) * 16};
+          const cuuint32_t box[4] = {8, (cuuint32_t)kCvBW, (cuuint32_t)kCvBH, 1};
+          const cuuint32_t estr[4] = {1, 1, 1, 1};
+          const CUresult r = tc::encode_tiled_fn()(&cv_tmap_, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, fb.p, dims, strides, box, estr,
+                                                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+          TDM_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed for the cost-volume source tile");
+          if (!d_cv_stats_) { TDM_CUDA(cudaMalloc(&d_cv_stats_, 2 * sizeof(unsigned))); TDM_CUDA(cudaMemset(d_cv_stats_, 0, 2 * sizeof(unsigned))); }
+          cv_tmap_ok_ = true;
+        }
+        k_cost_volume_va16_tma<TV, true><<<dim3(cdiv(vb.W, 16), cdiv(vb.H, 8)), 256, 0, stream_>>>(cv_tmap_, p8<const __half>(fb), dm, p8<TV>(vb), slot_, s - 1, d_cv_stats_);
+        TDM_CUDA(cudaGetLastError());
+        rec_end();
+        return;
+      }
       if (va_ && cv_variant_ > 0) {
         done = true;
         const int nd = (cv_variant_ == 2 || cv_variant_ == 4) ? 4 : (fb.C == 8 ? 4 : 2);
-        const bool h16 = cv_variant_ >= 3;
+        const bool h16 = cv_variant_ >= 3;   // (variant 5 = variant 3 outside stage 3)
         const long long thr = (long long)cdiv(vb.D, nd) * vb.H * vb.W * (fb.C == 32 ? 2 : 1);
         const unsigned grid = (unsigned)cdiv(thr, 128);
         auto go = [&](auto kern) { kern<<<grid, 128, 0, stream_>>>(p8<const __half>(fb), dm, p8<TV>(vb), slot_, s - 1); };
@@ -1428,6 +1455,9 @@ class MvsnetEngine final : public MvsnetIface {
   CallParams* h_params_ = nullptr;   // pinned
   CallParams* d_params_ = nullptr;
   cudaGraphExec_t graph_exec_ = nullptr;
+  CUtensorMap cv_tmap_{};      // cv_variant 5 (A/B): tiled view of feat3 for the TMA-staged cost volume
+  bool cv_tmap_ok_ = false;
+  unsigned* d_cv_stats_ = nullptr;
   int cv_variant_ = 3;   // 0: generic cost-volume kernel; 1-4: k_cost_volume_va16 (ND 2/2/4 | 4/4/4, fp32 | fp16 accumulate)
   bool warmed_ = false, use_graph_ = true, use_pdl_ = false;   // PDL measured slower (1.86 vs 1.73 ms): dependents squat on SM resources while they wait
   int slot_ = 0;           // index into c_call_params

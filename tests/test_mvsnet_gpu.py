@@ -279,3 +279,20 @@ def test_argument_errors_and_two_handles():
         a.CallAsync(96, 128, 3, 1, win["bgrs"], win["K"], win["c2ws"], 0.5, 5.0, 10.0)
     ra, rb = a.GetResult(), b.GetResult()
     assert np.array_equal(ra.depth_dense, rb.depth_dense) and np.array_equal(ra.confidence, rb.confidence)
+
+
+def test_tma_staged_cost_volume_is_bit_identical(golden_full):
+    """cv_variant 5 (A/B for north_star's "TMA staging of feature tiles"): the stage-3 cost volume with the
+    source-view tile staged in shared memory by one tiled cp.async.bulk.tensor per (CTA, view) - zero-filled outside the map,
+    global-gather fallback when the bounding box exceeds the staged box - must equal the L1-gather kernel bit for bit."""
+    g = golden_full
+    V, H, W, bgrs, c2ws, Ks = _inputs(g)
+    outs, vols = [], []
+    for variant in (3, 5):
+        m = DrMvsnet(default_weights("abl03_view_aggregation"), precision="mixed16")
+        m.set_option("cv_variant", variant)
+        m.CallAsyncStageK(H, W, V, int(g["ref_index"]), bgrs, Ks, c2ws, float(g["depth_min"]), float(g["depth_max"]), float(g["discard"]))
+        outs.append(m.GetResult())
+        vols.append(m.debug_tensor("s3.volume"))
+    assert np.array_equal(vols[0], vols[1]), f"stage-3 volume differs on {np.mean(vols[0] != vols[1]):.6f} of the entries"
+    assert np.array_equal(outs[0].depth_dense, outs[1].depth_dense) and np.array_equal(outs[0].depth, outs[1].depth)

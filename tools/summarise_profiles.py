@@ -136,7 +136,7 @@ def main():
         traffic = old
     json.dump(traffic, open(tj, "w"), indent=1)
     summarise_launches()
-    for f in ("bench.json", "bench_reference.json", "kernels.txt", "fusion_tracker.txt", "loop.txt", "pytest_gpu.log"):
+    for f in ("bench.json", "bench_reference.json", "kernels.txt", "fusion_tracker.txt", "loop.txt", "pytest_gpu.log", "config3.txt", "smoke.log"):
         s = os.path.join(G, f"{R}_{f}")
         if os.path.exists(s):
             shutil.copy(s, os.path.join(P, f"{R}_{f}"))
