@@ -6,6 +6,8 @@
 
 #include <Eigen/Dense>
 
+#include <vector>
+
 struct tdm_tracker;   // include/tandem_b200.h
 struct tdm_pyramid;
 struct tdm_fusion;
@@ -37,6 +39,11 @@ public:
   Eigen::Matrix<double, 6, 1> calcResAndG(Eigen::Matrix<double, 4, 4> const &refToNew, float new_exposure,
                                           Eigen::Vector2d const &aff_g2l, float cutoffTH,
                                           Eigen::Matrix<double, 8, 8> &H_out, Eigen::Matrix<double, 8, 1> &b_out);
+
+  // Extension: calcRes of several motion hypotheses (FullSystem::trackNewCoarse tries up to 31, FullSystem.cpp:437-530) in ONE
+  // launch and one synchronisation; element k equals calcRes(refToNew[k], new_exposure, aff_g2l[k], cutoffTH) bit for bit.
+  std::vector<Eigen::Matrix<double, 6, 1>> calcResBatch(std::vector<Eigen::Matrix<double, 4, 4>> const &refToNew, float new_exposure,
+                                                        std::vector<Eigen::Vector2d> const &aff_g2l, float cutoffTH);
 
   // Extensions for the stages either side of the evaluation:
   //  * setNewFromPyramid: setNew from a device-resident FrameHessian::makeImages replacement (tdm_pyramid);

@@ -239,6 +239,12 @@ int tdm_tracker_calc_g(tdm_tracker* t, float new_exposure, const double aff_g2l[
 /* Fused single-launch calcRes+calcG (no warped buffers), same outputs. */
 int tdm_tracker_calc_res_g(tdm_tracker* t, const double* refToNew, float new_exposure,
                            const double aff_g2l[2], float cutoffTH, double res6[6], double H[64], double b[8]);
+/* Extension (the tracker's only parallel axis): calcRes of n_hyp (<= 64) independent motion hypotheses - the poses
+ * FullSystem::trackNewCoarse tries one after the other (FullSystem.cpp:437-530) - in ONE launch and one synchronisation.
+ * refToNew: n_hyp x 16, aff_g2l: n_hyp x 2, res6: n_hyp x 6; hypothesis k's result equals tdm_tracker_calc_res on that pose bit
+ * for bit.  Does not disturb the buffers of the last calc_res (calc_g still refers to them). */
+int tdm_tracker_calc_res_batch(tdm_tracker* t, int n_hyp, const double* refToNew, float new_exposure, const double* aff_g2l,
+                               float cutoffTH, double* res6);
 int tdm_tracker_synchronize(tdm_tracker* t);
 int tdm_tracker_run_resident(tdm_tracker* t, int iters, float* ms_total);
 

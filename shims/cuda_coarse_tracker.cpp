@@ -5,6 +5,7 @@
 #include <chrono>
 #include <stdexcept>
 #include <string>
+#include <vector>
 
 #include "tandem_b200.h"
 
@@ -82,6 +83,23 @@ Eigen::Matrix<double, 6, 1> CudaCoarseTracker::calcResAndG(Eigen::Matrix<double,
     b_out(rr) = b[rr];
   }
   return r;
+}
+
+std::vector<Eigen::Matrix<double, 6, 1>> CudaCoarseTracker::calcResBatch(std::vector<Eigen::Matrix<double, 4, 4>> const& refToNew,
+                                                                         float new_exposure, std::vector<Eigen::Vector2d> const& aff,
+                                                                         float cutoffTH) {
+  if (refToNew.size() != aff.size() || refToNew.empty()) throw std::runtime_error("CudaCoarseTracker::calcResBatch: size mismatch");
+  const int n = (int)refToNew.size();
+  std::vector<double> T(16 * (size_t)n), a(2 * (size_t)n), res(6 * (size_t)n);
+  for (int k = 0; k < n; ++k) {
+    to_row_major(refToNew[k], &T[16 * (size_t)k]);
+    a[2 * (size_t)k] = aff[k](0); a[2 * (size_t)k + 1] = aff[k](1);
+  }
+  chk(tdm_tracker_calc_res_batch(handle_, n, T.data(), new_exposure, a.data(), cutoffTH, res.data()), "CudaCoarseTracker::calcResBatch");
+  std::vector<Eigen::Matrix<double, 6, 1>> out((size_t)n);
+  for (int k = 0; k < n; ++k)
+    for (int i = 0; i < 6; ++i) out[(size_t)k](i) = res[6 * (size_t)k + i];
+  return out;
 }
 
 void CudaCoarseTracker::setNewFromPyramid(tdm_pyramid* pyramid, int level) {

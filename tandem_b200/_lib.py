@@ -118,6 +118,7 @@ def _declare(l):
         "tdm_tracker_calc_res": (i, [vp, dp, f, dp, f, dp]),
         "tdm_tracker_calc_g": (i, [vp, f, dp, dp, dp]),
         "tdm_tracker_calc_res_g": (i, [vp, dp, f, dp, f, dp, dp, dp]),
+        "tdm_tracker_calc_res_batch": (i, [vp, i, dp, f, dp, f, dp]),
         "tdm_tracker_synchronize": (i, [vp]),
         "tdm_tracker_run_resident": (i, [vp, i, fp]),
         "tdm_pyramid_create": (i, [i, i, i, i, P(vp)]),

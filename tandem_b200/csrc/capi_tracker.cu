@@ -66,6 +66,14 @@ int tdm_tracker_calc_g(tdm_tracker* t, float new_exposure, const double aff_g2l[
   return TDM_OK;
   TDM_API_END
 }
+int tdm_tracker_calc_res_batch(tdm_tracker* t, int n_hyp, const double* refToNew, float new_exposure, const double* aff_g2l,
+                               float cutoffTH, double* res6) {
+  TDM_API_BEGIN
+  TDM_CHECK(t && refToNew && aff_g2l && res6, "null argument");
+  t->impl->calc_res_batch(n_hyp, refToNew, new_exposure, aff_g2l, cutoffTH, res6);
+  return TDM_OK;
+  TDM_API_END
+}
 int tdm_tracker_calc_res_g(tdm_tracker* t, const double* refToNew, float new_exposure, const double aff_g2l[2],
                            float cutoffTH, double res6[6], double H[64], double b[8]) {
   TDM_API_BEGIN

@@ -51,6 +51,8 @@ struct TrkBufs {
   double* partials;     // [kBlocks][kOut]
   unsigned* ticket;
   double* out;          // mapped pinned host memory, kOut doubles
+  const TrkPose* batch; // MODE 3: one pose per blockIdx.y (motion hypotheses evaluated in ONE launch); partials / ticket / out are
+                        // then arrays indexed by blockIdx.y
 };
 
 __device__ bool lm_done(const LmCtx* c);
@@ -90,6 +92,9 @@ __device__ __forceinline__ void accumulate_g(float* g, float dxI, float dyI, flo
 }
 
 // MODE 0: calcRes (stats + warped buffers)   1: calcG from warped buffers   2: fused (stats + G, no buffers)
+// MODE 3: calcRes statistics of blockIdx.y = 0..n_hyp-1 independent poses in one launch (no buffers): the motion hypotheses
+//         DSO tries one after the other (FullSystem.cpp:437-530) evaluated as a batch - SURVEY 8(e)'s only parallel axis of the
+//         tracker.  Same per-thread point striding and the same fixed-order reduction as MODE 0 -> identical numbers.
 template <int MODE>
 __global__ void __launch_bounds__(kThreads)
 k_tracker(const __grid_constant__ TrkParams p_in, TrkBufs b) {
@@ -103,7 +108,18 @@ k_tracker(const __grid_constant__ TrkParams p_in, TrkBufs b) {
     for (int i = 0; i < 3; ++i) p.t[i] = q->t[i];
     p.affa = q->affa; p.affb = q->affb; p.cutoff = q->cutoff; p.maxEnergy = q->maxEnergy;
   }
-  constexpr int NV = MODE == 0 ? kRes : (MODE == 1 ? kG : kOut);
+  if (MODE == 3) {
+    const TrkPose* q = b.batch + blockIdx.y;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) p.RKi[i] = q->RKi[i];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) p.t[i] = q->t[i];
+    p.affa = q->affa; p.affb = q->affb; p.cutoff = q->cutoff; p.maxEnergy = q->maxEnergy;
+    b.partials += (size_t)blockIdx.y * kBlocks * kOut;
+    b.ticket += blockIdx.y;
+    b.out += (size_t)blockIdx.y * kOut;
+  }
+  constexpr int NV = (MODE == 0 || MODE == 3) ? kRes : (MODE == 1 ? kG : kOut);
   constexpr int OFF = MODE == 1 ? kRes : 0;
   float acc[NV];
 #pragma unroll
@@ -555,6 +571,7 @@ class TrackerImpl final : public TrackerIface {
     cudaStreamSynchronize(stream_);
     cudaFree(d_pc_); cudaFree(d_warped_); cudaFree(d_dI_); cudaFree(d_partials_); cudaFree(d_ticket_);
     cudaFreeHost(h_pc_); cudaFreeHost(h_dI_); cudaFreeHost(h_out_);
+    if (d_batch_) { cudaFree(d_batch_); cudaFreeHost(h_batch_); cudaFree(d_batch_partials_); cudaFree(d_batch_ticket_); cudaFreeHost(h_batch_out_); }
     cudaFree(d_proj_); cudaFree(d_depth_); cudaFree(d_idepth0_); cudaFree(d_gray_); cudaFree(d_rowcnt_); cudaFree(d_rowoff_);
     cudaFree(d_total_); cudaFree(d_lm_ctx_); cudaFree(d_lm_out_); cudaFree(d_lm_in_);
     if (h_front_) cudaFreeHost(h_front_);
@@ -860,11 +877,56 @@ class TrackerImpl final : public TrackerIface {
     b.lm = dev_loop ? d_lm_ctx_ : nullptr;
     b.pc_u = d_pc_; b.pc_v = d_pc_ + nm; b.pc_idepth = d_pc_ + 2 * nm; b.pc_color = d_pc_ + 3 * nm;
     b.dInew = d_dI_; b.warped = d_warped_; b.n_max = n_max_;
-    b.partials = d_partials_; b.ticket = d_ticket_; b.out = dev_loop ? d_lm_out_ : d_out_;
+    b.partials = d_partials_; b.ticket = d_ticket_; b.out = dev_loop ? d_lm_out_ : d_out_; b.batch = nullptr;
     if (mode == 0) k_tracker<0><<<kBlocks, kThreads, 0, stream_>>>(p_, b);
     else if (mode == 1) k_tracker<1><<<kBlocks, kThreads, 0, stream_>>>(p_, b);
     else k_tracker<2><<<kBlocks, kThreads, 0, stream_>>>(p_, b);
     TDM_CUDA(cudaGetLastError());
+  }
+  // Batched calcRes over n_hyp poses (motion hypotheses of FullSystem::trackNewCoarse, FullSystem.cpp:437-530) in ONE launch and
+  // one synchronisation: res6 of hypothesis k equals calc_res(refToNew + 16 k, ..., aff + 2 k, ...) bit for bit.  Leaves the
+  // buffers of the last calcRes untouched (calcG still refers to them).
+  void calc_res_batch(int n_hyp, const double* refToNew, float new_exposure, const double* aff, float cutoffTH, double* res6) override {
+    TDM_CHECK(n_hyp >= 1 && n_hyp <= kMaxHyp, "calcResBatch: 1..64 hypotheses");
+    TDM_CHECK(have_k_ && have_new_, "calcResBatch before setK / setNew");
+    TDM_CUDA(cudaSetDevice(device_));
+    if (!d_batch_) {
+      TDM_CUDA(cudaMalloc(&d_batch_, kMaxHyp * sizeof(TrkPose)));
+      TDM_CUDA(cudaMallocHost(&h_batch_, kMaxHyp * sizeof(TrkPose)));
+      TDM_CUDA(cudaMalloc(&d_batch_partials_, (size_t)kMaxHyp * kBlocks * kOut * 8));
+      TDM_CUDA(cudaMalloc(&d_batch_ticket_, kMaxHyp * 4));
+      TDM_CUDA(cudaMemset(d_batch_ticket_, 0, kMaxHyp * 4));
+      TDM_CUDA(cudaHostAlloc(&h_batch_out_, (size_t)kMaxHyp * kOut * 8, cudaHostAllocMapped));
+      TDM_CUDA(cudaHostGetDevicePointer(&d_batch_out_, h_batch_out_, 0));
+    }
+    TDM_CUDA(cudaStreamSynchronize(stream_));   // the pinned pose staging may still be in flight from the previous batch
+    const TrkParams saved = p_;
+    const bool saved_have = have_params_;
+    for (int k = 0; k < n_hyp; ++k) {
+      prepare(refToNew + 16 * k, new_exposure, aff + 2 * k, cutoffTH);   // the exact host arithmetic of calcRes, per pose
+      TrkPose& q = h_batch_[k];
+      for (int i = 0; i < 9; ++i) q.RKi[i] = p_.RKi[i];
+      for (int i = 0; i < 3; ++i) q.t[i] = p_.t[i];
+      q.affa = p_.affa; q.affb = p_.affb; q.cutoff = p_.cutoff; q.maxEnergy = p_.maxEnergy;
+    }
+    TrkParams pb = p_;
+    p_ = saved;                                   // calcG keeps referring to the last plain calcRes
+    have_params_ = saved_have;
+    TDM_CUDA(cudaMemcpyAsync(d_batch_, h_batch_, n_hyp * sizeof(TrkPose), cudaMemcpyHostToDevice, stream_));
+    TrkBufs b;
+    const size_t nm = (size_t)n_max_;
+    b.lm = nullptr;
+    b.pc_u = d_pc_; b.pc_v = d_pc_ + nm; b.pc_idepth = d_pc_ + 2 * nm; b.pc_color = d_pc_ + 3 * nm;
+    b.dInew = d_dI_; b.warped = nullptr; b.n_max = n_max_;
+    b.partials = d_batch_partials_; b.ticket = d_batch_ticket_; b.out = d_batch_out_; b.batch = d_batch_;
+    k_tracker<3><<<dim3(kBlocks, n_hyp), kThreads, 0, stream_>>>(pb, b);
+    TDM_CUDA(cudaGetLastError());
+    TDM_CUDA(cudaStreamSynchronize(stream_));
+    for (int k = 0; k < n_hyp; ++k) {
+      const volatile double* o = h_batch_out_ + (size_t)k * kOut;
+      double* r = res6 + 6 * k;
+      r[0] = o[0]; r[1] = o[1]; r[2] = o[4] / o[6]; r[3] = 0; r[4] = o[5] / o[6]; r[5] = o[3] / o[1];
+    }
   }
   void finish_res(double res6[6]) {  // cpp:264-272
     const volatile double* o = h_out_;
@@ -896,6 +958,10 @@ class TrackerImpl final : public TrackerIface {
   double ref_aff_[2] = {0, 0};
   cudaStream_t stream_ = nullptr;
   float *d_pc_ = nullptr, *d_warped_ = nullptr, *d_dI_ = nullptr, *h_pc_ = nullptr, *h_dI_ = nullptr;
+  static constexpr int kMaxHyp = 64;
+  TrkPose *d_batch_ = nullptr, *h_batch_ = nullptr;
+  double *d_batch_partials_ = nullptr, *h_batch_out_ = nullptr, *d_batch_out_ = nullptr;
+  unsigned* d_batch_ticket_ = nullptr;
   double *d_partials_ = nullptr, *h_out_ = nullptr, *d_out_ = nullptr;
   unsigned* d_ticket_ = nullptr;
   TrkParams p_{};

@@ -12,6 +12,7 @@ class TrackerIface {
                              float ref_exposure, const double ref_aff[2]) = 0;
   virtual void set_new(const float* dI) = 0;
   virtual void calc_res(const double* refToNew, float new_exposure, const double aff[2], float cutoffTH, double res6[6]) = 0;
+  virtual void calc_res_batch(int n_hyp, const double* refToNew, float new_exposure, const double* aff, float cutoffTH, double* res6) = 0;
   virtual void calc_g(float new_exposure, const double aff[2], double H[64], double b[8]) = 0;
   virtual void calc_res_g(const double* refToNew, float new_exposure, const double aff[2], float cutoffTH, double res6[6],
                           double H[64], double b[8]) = 0;

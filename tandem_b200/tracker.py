@@ -103,6 +103,16 @@ class CudaCoarseTracker:
                                        b.ctypes.data_as(_dp)))
         return H, b
 
+    def calcResBatch(self, refToNews, new_exposure, aff_g2ls, cutoffTH):
+        """calcRes of several motion hypotheses in one launch (extension): refToNews (n,4,4), aff_g2ls (n,2) -> res (n,6)."""
+        T = np.ascontiguousarray(refToNews, np.float64).reshape(-1, 16)
+        n = T.shape[0]
+        aff = np.ascontiguousarray(aff_g2ls, np.float64).reshape(n, 2)
+        res = np.zeros((n, 6), np.float64)
+        check(lib().tdm_tracker_calc_res_batch(self._h, n, T.ctypes.data_as(_dp), float(new_exposure), aff.ctypes.data_as(_dp),
+                                               float(cutoffTH), res.ctypes.data_as(_dp)))
+        return res
+
     def calcResAndG(self, refToNew, new_exposure, aff_g2l, cutoffTH):
         T = np.ascontiguousarray(refToNew, np.float64)
         aff = np.ascontiguousarray(aff_g2l, np.float64)

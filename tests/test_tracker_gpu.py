@@ -70,3 +70,34 @@ def test_errors():
         t.setReference(2000, z, z, z, z, 1.0, np.zeros(2))  # n > n_max throws (cpp:82)
     with pytest.raises(Exception):
         t.init()
+
+
+def test_batched_hypotheses_equal_sequential_calc_res():
+    """calcResBatch (extension; the motion hypotheses of FullSystem::trackNewCoarse evaluated in one launch) returns, per
+    hypothesis, exactly what calcRes returns for that pose - and leaves the buffers calcG refers to untouched."""
+    c = tracker_case(H=240, W=320, fx=160.0, fy=160.0, cx=159.5, cy=119.5)
+    t = CudaCoarseTracker(c["w"], c["h"])
+    t.init()
+    t.setK(c["w"], c["h"], c["fx"], c["fy"], c["cx"], c["cy"])
+    t.setReference(c["n"], c["pc_u"], c["pc_v"], c["pc_idepth"], c["pc_color"], c["ref_exposure"], c["ref_aff"])
+    t.setNew(c["dInew"])
+    rng = np.random.default_rng(0)
+    poses, affs = [], []
+    for k in range(9):
+        T = np.array(c["refToNew"], np.float64).copy()
+        T[:3, 3] += rng.normal(0, 0.01, 3) * (k > 0)
+        w = rng.normal(0, 0.005, 3) * (k > 0)
+        R = np.array([[1, -w[2], w[1]], [w[2], 1, -w[0]], [-w[1], w[0], 1]])
+        T[:3, :3] = R @ T[:3, :3]
+        poses.append(T)
+        affs.append(np.array(c["new_aff"], np.float64) + (k % 3) * np.array([0.01, 0.5]))
+    r_keep = t.calcRes(poses[0], c["new_exposure"], affs[0], c["cutoffTH"])
+    H0, b0 = t.calcG(c["new_exposure"], affs[0])
+    batch = t.calcResBatch(np.stack(poses), c["new_exposure"], np.stack(affs), c["cutoffTH"])
+    H1, b1 = t.calcG(c["new_exposure"], affs[0])
+    assert np.array_equal(H0, H1) and np.array_equal(b0, b1), "the batch must not disturb the last calcRes' buffers"
+    assert np.array_equal(batch[0], r_keep)
+    for k in range(9):
+        r = t.calcRes(poses[k], c["new_exposure"], affs[k], c["cutoffTH"])
+        assert np.array_equal(batch[k], r), f"hypothesis {k}: {batch[k]} vs {r}"
+    assert len({tuple(b) for b in batch}) > 5, "the hypotheses must actually differ"
