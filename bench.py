@@ -518,6 +518,11 @@ def main():
             gpu_ref = time_gpu_reference(win, local)
             dd = gpu_ref.pop("depth_dense_gpu", None)
             if dd is not None:   # our output vs the comparator's on the same window (sanity of both arms)
+                # accuracy is compared on IDENTICAL inputs: the per-stage intrinsics the golden / comparator use (the timed legs go
+                # through CallAsync, whose stage intrinsics follow the C++ wrapper's derivation, dr_mvsnet.cpp:220-247)
+                m.CallAsyncStageK(win["H"], win["W"], win["V"], win["ref_index"], win["bgrs"], np.stack(win["Ks"]).astype(np.float32),
+                                  win["c2ws"], win["dmin"], win["dmax"], win["discard"])
+                out = m.GetResult()
                 msk = dd > 0
                 gpu_ref["abs_rel_ours_vs_gpu_reference"] = float(np.mean(np.abs(dd[msk] - out.depth_dense[msk]) / dd[msk]))
                 # how well do the reference's OWN two arithmetic paths agree?  (golden = its CPU fp32 model output)
