@@ -281,11 +281,12 @@ def test_argument_errors_and_two_handles():
     assert np.array_equal(ra.depth_dense, rb.depth_dense) and np.array_equal(ra.confidence, rb.confidence)
 
 
-def test_tma_staged_cost_volume_is_bit_identical(golden_full):
+@pytest.mark.parametrize("which", ["full", "small"])
+def test_tma_staged_cost_volume_is_bit_identical(golden_full, golden_small, which):
     """cv_variant 5 (A/B for north_star's "TMA staging of feature tiles"): the stage-3 cost volume with the
     source-view tile staged in shared memory by one tiled cp.async.bulk.tensor per (CTA, view) - zero-filled outside the map,
     global-gather fallback when the bounding box exceeds the staged box - must equal the L1-gather kernel bit for bit."""
-    g = golden_full
+    g = golden_full if which == "full" else golden_small     # 640x480 / 512x320 (the small one is the compute-sanitizer instance)
     V, H, W, bgrs, c2ws, Ks = _inputs(g)
     outs, vols = [], []
     for variant in (3, 5):
