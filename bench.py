@@ -131,7 +131,9 @@ def pick_cpu_threads(run=None):
     headline ratio - moved 2x between driver runs; a full forward per candidate costs ~10 s in total and is stable."""
     import torch
     ncpu = os.cpu_count() or 1
-    cands = sorted({c for c in (16, 32, 64, ncpu) if c <= ncpu}) or [ncpu]
+    # (all hardware threads is only a candidate up to 64: on the 128-thread host of the B200 boxes torch's CPU convolutions take
+    #  53 s per forward with 128 threads against 1.7 s with 16 - measured in round 2, profiles/r02_bench_reference.json)
+    cands = sorted({c for c in (16, 32, 64, ncpu if ncpu <= 64 else 64) if c <= ncpu}) or [ncpu]
     if run is None or len(cands) == 1:
         torch.set_num_threads(cands[-1])
         return cands[-1], {}

@@ -48,6 +48,7 @@ struct Geom {
   int S;                  // ring slots
   int oHp, oWp, opd;      // padded dims / D halo of the OUTPUT tensor (differs from the input in deconv mode)
   int iDp;                // padded plane count of the input: tensor-map dim 3 = channel_group * iDp + plane
+  int dbg_aligned;        // TIMING EXPERIMENT ONLY (TDM_DEBUG_ALIGNED_TAPS=1): every tap reads at kw = 0, i.e. 128-byte aligned A tiles (wrong results)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -542,8 +543,10 @@ inline Plan make_plan(int cin, int npad, int kd, int D, int H, int W, int pd, in
           const double clk_mma = mode == 4 ? 40.0 + 0.35 * 3 * npad : (mode == 1 ? 35.0 + 0.45 * npad : 45.0 + 0.35 * npad);
           const int planes_in = mode == 4 ? DR + 2 : DR;                       // instruction streams per tile
           const double per_plane = (double)nch * nblk * (mode == 4 ? 1.25 : (double)kd) * clk_mma;
-          const double tile_clk = 8500.0 + planes_in * per_plane;
-          const double cost = std::ceil(T / 148.0) * tile_clk * (1.0 + 0.25 * (amp - 1.0)) * (S == s_hi ? 1.0 : 1.05);
+          // mode 4 is persistent over tiles (conv_tc_is.cuh): the ~8.5 k clk of prologue / fill / drain are paid once per CTA,
+          // a tile boundary costs ~1.5 k clk (plane-ring turnover)
+          const double tile_clk = (mode == 4 ? 1500.0 : 8500.0) + planes_in * per_plane;
+          const double cost = (std::ceil(T / 148.0) * tile_clk + (mode == 4 ? 8500.0 : 0.0)) * (1.0 + 0.25 * (amp - 1.0)) * (S == s_hi ? 1.0 : 1.05);
           if (cost < best_cost - 1e-9) { best_cost = cost; bestR = R; bestTW = TW; bestS = S; bestDR = DR; }
           if (T > 4000) break;
         }

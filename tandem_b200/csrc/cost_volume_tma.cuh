@@ -19,7 +19,7 @@ constexpr int kCvBW = 48, kCvBH = 24;   // staged box in texels (18 KB of shared
 template <typename TV, bool ACC16>
 __global__ void __launch_bounds__(256)
 k_cost_volume_va16_tma(const __grid_constant__ CUtensorMap tmap /*feat3: {8, Wp, Hp, V}, box {8, kCvBW, kCvBH, 1}*/,
-                       P8<const __half> feats, const float* __restrict__ dmin_map, P8<TV> vol, int slot, int stage,
+                       P8<const __half> feats, const DminSrc dsrc, P8<TV> vol, int slot, int stage,
                        unsigned* __restrict__ stats /*[2]: views staged by TMA, views that fell back*/) {
   constexpr int C = 8, ND = 4;
   const CvParams& p = c_call_params[slot].cv[stage];
@@ -51,7 +51,7 @@ k_cost_volume_va16_tma(const __grid_constant__ CUtensorMap tmap /*feat3: {8, Wp,
   }
   float depth[ND];
   {
-    const float dmn = p.hyp.adaptive ? dmin_map[pix] : 0.f;
+    const float dmn = p.hyp.adaptive ? dmin_px(dsrc, pix, xc, yc, c_call_params[slot].half_range[stage]) : 0.f;
 #pragma unroll
     for (int k = 0; k < ND; ++k) depth[k] = hyp_value(p.hyp, dmn, min(d0 + k, p.D - 1));
   }

@@ -921,6 +921,8 @@ class FusionImpl final : public FusionIface {
     for (int half = 0; half < 2; ++half) {
       TDM_CUDA(cudaMallocHost(&h_bgr_out_[half], npx * 3 * ns));
       TDM_CUDA(cudaMallocHost(&h_depth_out_[half], npx * 4 * ns));
+      std::memset(h_bgr_out_[half], 0, npx * 3 * ns);     // "slab_exchange" mode never writes them: GetRenderResult then hands out
+      std::memset(h_depth_out_[half], 0, npx * 4 * ns);   // all-miss images rather than uninitialised memory
     }
     TDM_CUDA(cudaMalloc(&d_bgr_out_, npx * 3 * ns));
     TDM_CUDA(cudaMalloc(&d_depth_out_, npx * 4 * ns));

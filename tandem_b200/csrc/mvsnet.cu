@@ -168,6 +168,7 @@ class MvsnetEngine final : public MvsnetIface {
       cudaFree(d_cv_stats_);
     }
     if (select_state_) cudaFree(select_state_);
+    if (select2_) cudaFree(select2_);
     release_slot(slot_);
     if (d_bs3_) cudaFree(d_bs3_);
     if (h_params_) cudaFreeHost(h_params_);
@@ -212,6 +213,8 @@ class MvsnetEngine final : public MvsnetIface {
     else if (key == "fork_fpn") fork_fpn_ = value != 0;
     else if (key == "prob_direct") prob_direct_ = value != 0;
     else if (key == "direct_conv00") direct_conv00_ = value != 0;
+    else if (key == "fused_select") fused_select_ = value != 0;
+    else if (key == "inline_dmin") inline_dmin_ = value != 0;
     else throw Error("unknown option " + key);
   }
 
@@ -614,6 +617,8 @@ class MvsnetEngine final : public MvsnetIface {
       }
     }
     TDM_CUDA(cudaMalloc(&select_state_, sizeof(SelectState)));
+    TDM_CUDA(cudaMalloc(&select2_, sizeof(SelectState2)));
+    TDM_CUDA(cudaMemset(select2_, 0, sizeof(SelectState2)));
     TDM_CUDA(cudaMallocHost(&h_params_, sizeof(CallParams)));
     TDM_CUDA(cudaMalloc(&d_params_, sizeof(CallParams)));
   }
@@ -837,6 +842,7 @@ class MvsnetEngine final : public MvsnetIface {
       TcCache tcx;
       tcx.plan = tc::make_plan(CIN, HILO ? 2 * NPAD : NPAD, 3, in.D, in.H, in.W, in.pd, 4, (size_t)tc_smem_kb_ * 1024);
       tc::Geom& g = tcx.plan.g;
+      g.dbg_aligned = std::getenv("TDM_DEBUG_ALIGNED_TAPS") ? 1 : 0;
       g.oHp = out.H + 2; g.oWp = out.W + 2; g.opd = out.pd;
       g.iDp = in.D + 2 * in.pd;
       g.in_gs = p8<const TIn>(in).gs;
@@ -868,7 +874,11 @@ class MvsnetEngine final : public MvsnetIface {
       TDM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
       attr_set = true;
     }
-    launch_pdl(kern, dim3(pl.grid, 1), pl.smem, it->second.tmap, (const TIn*)c.bimg_is, (const float*)c.bias,
+    // persistent over tiles: every CTA takes ceil(tiles / SMs) tiles, the grid is what that needs (<= one CTA per SM)
+    static const bool persist = !(std::getenv("TDM_IS_PERSIST") && std::getenv("TDM_IS_PERSIST")[0] == '0');   // A/B: 0 = one tile per CTA
+    const int tpc = persist ? (pl.grid + kNumSm - 1) / kNumSm : 1;
+    const int gx = (pl.grid + tpc - 1) / tpc;
+    launch_pdl(kern, dim3(gx, 1), pl.smem, it->second.tmap, (const TIn*)c.bimg_is, (const float*)c.bias,
                (const TOut*)(PLAIN ? nullptr : (res ? res->p : nullptr)), (TOut*)(PLAIN ? nullptr : out.p),
                (float*)(PLAIN ? out.p : nullptr), pl.g);
   }
@@ -1140,7 +1150,7 @@ class MvsnetEngine final : public MvsnetIface {
     const long long n = (long long)vb.D * vb.H * vb.W;
     rec_begin(k + "cost_volume", (double)fb.alg_bytes + (double)vb.alg_bytes + (s > 1 ? 4.0 * vb.H * vb.W : 0.0),
               (double)n * nsrc * fb.C * 12.0);
-    const float* dm = s > 1 ? fbuf(k + "dmin") : nullptr;
+    const DminSrc dm = dmin_src(s);
     bool done = false;
     if constexpr (std::is_same<TA, __half>::value) {
       if (va_ && cv_variant_ == 5 && fb.C == 8 && vb.D == 8) {
@@ -1191,6 +1201,18 @@ class MvsnetEngine final : public MvsnetIface {
     rec_end();
   }
 
+  // where stage s takes the lower end of its hypothesis range from: computed in place from the previous stage's depth
+  // (inline_dmin_, default) or read from the map k_adaptive_dmin materialised
+  DminSrc dmin_src(int s) {
+    DminSrc d{nullptr, nullptr, 0, 0};
+    if (s <= 1) return d;
+    const std::string k = "s" + std::to_string(s) + ".";
+    if (!inline_dmin_) { d.map = fbuf(k + "dmin"); return d; }
+    const DevBuf& pd = bufs_.at("s" + std::to_string(s - 1) + ".depth_dense");
+    d.prev = (const float*)pd.p; d.ph = pd.H; d.pw = pd.W;
+    return d;
+  }
+
   HypSpec hyp_spec(int s) const {
     HypSpec h;
     const float base = (dmax_ - dmin_) / (float)(depth_num_[0] - 1);
@@ -1206,6 +1228,16 @@ class MvsnetEngine final : public MvsnetIface {
     const std::string k = "s" + std::to_string(s) + ".";
     const DevBuf& d = bufs_.at(k + "depth_dense");
     const int n = d.H * d.W;
+    if (fused_select_) {
+      rec_begin(k + "edge_metric+select0", 8.0 * n, 0);
+      k_edge_metric_select0<<<cdiv(n, 256), 256, 0, stream_>>>(fbuf(k + "depth_dense"), fbuf(k + "edge"), d.H, d.W, select2_, &d_params_->cutoff[s - 1]);
+      rec_end();
+      rec_begin(k + "percentile", 8.0 * n, 0);
+      for (int pass = 1; pass <= 2; ++pass)
+        k_select_pass<<<std::min(cdiv(n, 256 * 8), 296), 256, 0, stream_>>>(fbuf(k + "edge"), n, select2_, pass, fbuf("thr") + (s - 1));
+      launch_count_ += 1;
+      rec_end();
+    } else {
     rec_begin(k + "edge_metric", 8.0 * n, 0);
     k_edge_metric<<<cdiv(n, 128), 128, 0, stream_>>>(fbuf(k + "depth_dense"), fbuf(k + "edge"), d.H, d.W);
     rec_end();
@@ -1217,6 +1249,7 @@ class MvsnetEngine final : public MvsnetIface {
     }
     launch_count_ += 6;
     rec_end();
+    }
     rec_begin(k + "apply_mask", 20.0 * n, 0);
     k_apply_edge_mask<<<cdiv(n, 256), 256, 0, stream_>>>(fbuf(k + "edge"), fbuf("thr") + (s - 1), fbuf(k + "depth_dense"),
                                                        fbuf(k + "confidence_dense"), fbuf(k + "depth"),
@@ -1327,7 +1360,7 @@ class MvsnetEngine final : public MvsnetIface {
       const HypSpec hs = hyp_spec(s);
       const DevBuf& dd = bufs_.at(k + "depth_dense");
       if (s == 2 && fork) TDM_CUDA(cudaStreamWaitEvent(stream_, ev_join_, 0));
-      if (s > 1) {
+      if (s > 1 && !inline_dmin_) {
         const DevBuf& pd = bufs_.at("s" + std::to_string(s - 1) + ".depth_dense");
         rec_begin(k + "adaptive_dmin", 4.0 * (pd.H * pd.W + dd.H * dd.W), 0);
         k_adaptive_dmin<<<cdiv(dd.H * dd.W, 256), 256, 0, stream_>>>((const float*)pd.p, pd.H, pd.W, fbuf(k + "dmin"),
@@ -1352,10 +1385,11 @@ class MvsnetEngine final : public MvsnetIface {
       {
         const int HW = dd.H * dd.W;
         rec_begin(k + "regress", 4.0 * HW * (hs.D + 3), 0);
-        const float* dm = s > 1 ? fbuf(k + "dmin") : nullptr;
-        if (hs.D <= 8) k_regress<8><<<cdiv(HW, 128), 128, 0, stream_>>>(fbuf(k + "logits"), dm, fbuf(k + "depth_dense"), fbuf(k + "confidence_dense"), HW, &d_params_->hyp[s - 1]);
-        else if (hs.D <= 32) k_regress<32><<<cdiv(HW, 128), 128, 0, stream_>>>(fbuf(k + "logits"), dm, fbuf(k + "depth_dense"), fbuf(k + "confidence_dense"), HW, &d_params_->hyp[s - 1]);
-        else if (hs.D <= 64) k_regress<64><<<cdiv(HW, 128), 128, 0, stream_>>>(fbuf(k + "logits"), dm, fbuf(k + "depth_dense"), fbuf(k + "confidence_dense"), HW, &d_params_->hyp[s - 1]);
+        const DminSrc dm = dmin_src(s);
+        const float* hr = &d_params_->half_range[s - 1];
+        if (hs.D <= 8) k_regress<8><<<cdiv(HW, 128), 128, 0, stream_>>>(fbuf(k + "logits"), dm, fbuf(k + "depth_dense"), fbuf(k + "confidence_dense"), HW, dd.W, &d_params_->hyp[s - 1], hr);
+        else if (hs.D <= 32) k_regress<32><<<cdiv(HW, 128), 128, 0, stream_>>>(fbuf(k + "logits"), dm, fbuf(k + "depth_dense"), fbuf(k + "confidence_dense"), HW, dd.W, &d_params_->hyp[s - 1], hr);
+        else if (hs.D <= 64) k_regress<64><<<cdiv(HW, 128), 128, 0, stream_>>>(fbuf(k + "logits"), dm, fbuf(k + "depth_dense"), fbuf(k + "confidence_dense"), HW, dd.W, &d_params_->hyp[s - 1], hr);
         else throw Error("depth_num > 64 unsupported");
         TDM_CUDA(cudaGetLastError());
         rec_end();
@@ -1429,6 +1463,7 @@ class MvsnetEngine final : public MvsnetIface {
   // mixed16: the cost volume is fp16 too, stored x 2^-5 (values reach ~1e4 and fp16 ends at 65504; bf16 has the range but only 8
   // significant bits - the CPU study (profiles/r02_precision_study.md) attributes 1 % of mask IoU to that alone)
   static constexpr float kVolScale = (std::is_same<TA, __half>::value && std::is_same<TV, __half>::value) ? 0.03125f : 1.f;
+  static constexpr int kNumSm = 148;   // B200 (sm_100a only build)
   static constexpr bool kRawInput = sizeof(TA) == 2;   // 16-bit engines: exact u8/256 input, 256/255 folded into f.conv0.0
 
   int device_ = 0;
@@ -1440,6 +1475,9 @@ class MvsnetEngine final : public MvsnetIface {
   Gate gates_[3];
   std::map<std::string, DevBuf> bufs_;
   SelectState* select_state_ = nullptr;
+  SelectState2* select2_ = nullptr;
+  bool inline_dmin_ = true;    // adaptive range's d_min computed where it is consumed (dmin_px) instead of by k_adaptive_dmin (A/B: 0)
+  bool fused_select_ = true;   // edge metric + pass 0 in one kernel, passes 1 / 2 with the scan in their last CTA (A/B: set_option("fused_select", 0))
   int V_ = 0, H_ = 0, W_ = 0;
   unsigned char* h_bgr_ = nullptr;
   unsigned char* d_bgr_ = nullptr;

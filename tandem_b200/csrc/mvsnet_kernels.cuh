@@ -330,6 +330,29 @@ __device__ __forceinline__ float hyp_value(const HypSpec& h, float dmin_px, int 
   return dmin_px + (dmax - dmin_px) * lin;
 }
 
+// a4 without a kernel of its own (round 2): the lower end of a pixel's adaptive hypothesis range, d_min = max(up2(depth_prev) -
+// half_range, 1e-3) with up2 = bilinear x2, align_corners=False (cva_mvsnet.py:143-147, module.py:1503-1565), evaluated where it
+// is consumed - the cost-volume kernel's prologue and the regression - from the previous stage's depth map (4 L2-resident
+// loads).  Explicit fma / mul intrinsics: every consumer must see bit-identical hypotheses.  map != nullptr reads the
+// materialised map instead (k_adaptive_dmin, kept for the A/B and the fp32 parity engine's layer-wise tests).
+struct DminSrc {
+  const float* map;    // [H][W] or null
+  const float* prev;   // [ph][pw] depth of the previous stage
+  int ph, pw;
+};
+__device__ __forceinline__ float dmin_px(const DminSrc& s, int pix, int x, int y, float half_range) {
+  if (s.map) return s.map[pix];
+  const float sy = fmaxf(__fmaf_rn(0.5f, (float)y + 0.5f, -0.5f), 0.f), sx = fmaxf(__fmaf_rn(0.5f, (float)x + 0.5f, -0.5f), 0.f);
+  const int y0 = (int)sy, x0 = (int)sx;
+  const int y1 = min(y0 + 1, s.ph - 1), x1 = min(x0 + 1, s.pw - 1);
+  const float ly = sy - (float)y0, lx = sx - (float)x0;
+  const float hy = 1.f - ly, hx = 1.f - lx;
+  const float t0 = __fmaf_rn(lx, s.prev[y0 * s.pw + x1], __fmul_rn(hx, s.prev[y0 * s.pw + x0]));
+  const float t1 = __fmaf_rn(lx, s.prev[y1 * s.pw + x1], __fmul_rn(hx, s.prev[y1 * s.pw + x0]));
+  const float up = __fmaf_rn(ly, t1, __fmul_rn(hy, t0));
+  return fmaxf(up - half_range, 0.001f);
+}
+
 __global__ void k_adaptive_dmin(const float* __restrict__ prev /*[h][w]*/, int h, int w,
                                 float* __restrict__ dmin /*[2h][2w]*/, const float* __restrict__ half_range_p) {
   const float half_range = *half_range_p;
@@ -395,7 +418,7 @@ __constant__ CallParams c_call_params[kMaxEngines];
 
 template <typename T, typename TV, int C, int CSPLIT = 1>
 __global__ void __launch_bounds__(128)
-k_cost_volume(P8<const T> feats /*views on the D axis, ref first*/, const float* __restrict__ dmin_map,
+k_cost_volume(P8<const T> feats /*views on the D axis, ref first*/, const DminSrc dsrc,
               P8<TV> vol, int slot, int stage /*per-call parameters: c_call_params[slot].cv[stage] (graph-replayable)*/) {
   const CvParams& p = c_call_params[slot].cv[stage];
   const long long n = (long long)p.D * p.H * p.W;
@@ -409,7 +432,7 @@ k_cost_volume(P8<const T> feats /*views on the D axis, ref first*/, const float*
   const int x = (int)(i % p.W);
   const int y = (int)((i / p.W) % p.H);
   const int d = (int)(i / ((long long)p.W * p.H));
-  const float depth = hyp_value(p.hyp, p.hyp.adaptive ? dmin_map[y * p.W + x] : 0.f, d);
+  const float depth = hyp_value(p.hyp, p.hyp.adaptive ? dmin_px(dsrc, y * p.W + x, x, y, c_call_params[slot].half_range[stage]) : 0.f, d);
 
   float ref[C];
   {
@@ -598,7 +621,7 @@ __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
 
 template <typename TV, int C /*channels of one thread*/, int CSPLIT, int ND, bool ACC16>
 __global__ void __launch_bounds__(128)
-k_cost_volume_va16(P8<const __half> feats, const float* __restrict__ dmin_map, P8<TV> vol, int slot, int stage) {
+k_cost_volume_va16(P8<const __half> feats, const DminSrc dsrc, P8<TV> vol, int slot, int stage) {
   const CvParams& p = c_call_params[slot].cv[stage];
   constexpr float kS = 1.f / 64.f;
   const int HW = p.H * p.W;
@@ -631,7 +654,7 @@ k_cost_volume_va16(P8<const __half> feats, const float* __restrict__ dmin_map, P
   }
   float depth[ND];
   {
-    const float dmn = p.hyp.adaptive ? dmin_map[pix] : 0.f;
+    const float dmn = p.hyp.adaptive ? dmin_px(dsrc, pix, x, y, c_call_params[slot].half_range[stage]) : 0.f;
 #pragma unroll
     for (int k = 0; k < ND; ++k) depth[k] = hyp_value(p.hyp, dmn, min(d0 + k, p.D - 1));
   }
@@ -731,8 +754,9 @@ k_cost_volume_va16(P8<const __half> feats, const float* __restrict__ dmin_map, P
 // a8: softmax over D + soft-argmin depth + 4-neighbour confidence, one thread per pixel.
 // ------------------------------------------------------------------------------------------------
 template <int MAXD>
-__global__ void k_regress(const float* __restrict__ logits /*[D][H][W]*/, const float* __restrict__ dmin_map,
-                          float* __restrict__ depth, float* __restrict__ conf, int HW, const HypSpec* __restrict__ hyp_p) {
+__global__ void k_regress(const float* __restrict__ logits /*[D][H][W]*/, const DminSrc dsrc,
+                          float* __restrict__ depth, float* __restrict__ conf, int HW, int W, const HypSpec* __restrict__ hyp_p,
+                          const float* __restrict__ half_range_p) {
   const HypSpec hyp = *hyp_p;
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= HW) return;
@@ -746,7 +770,7 @@ __global__ void k_regress(const float* __restrict__ logits /*[D][H][W]*/, const 
 #pragma unroll
   for (int j = 0; j < MAXD; ++j)
     if (j < D) { l[j] = expf(l[j] - m); s += l[j]; }
-  const float dm = hyp.adaptive ? dmin_map[i] : 0.f;
+  const float dm = hyp.adaptive ? dmin_px(dsrc, i, i % W, i / W, *half_range_p) : 0.f;
   float dsum = 0.f, isum = 0.f;
 #pragma unroll
   for (int j = 0; j < MAXD; ++j)
@@ -857,6 +881,121 @@ __global__ void __launch_bounds__(1024) k_select_scan(SelectState* st, int pass,
     st->prefix = np;
     if (pass == 2) *thr_out = __uint_as_float(np);
   }
+}
+
+// ---- fused percentile select (round 2): 4 launches instead of 9 --------------------------------------------------------
+// The exact k-th order statistic of the edge map is still a 3-pass radix select over the float bit patterns (11 + 11 + 10
+// bits), but every pass is ONE launch: the CTAs histogram their share into shared memory, merge into the global histogram,
+// and the LAST CTA to finish (ticket) scans the 2048 bins, narrows (prefix, k) for the next pass and re-zeroes the histogram.
+// Pass 0 rides on the edge-metric kernel itself (the values are in registers there).  State between passes lives in SelectState;
+// its histogram and ticket are zero whenever no select is in flight (zeroed at allocation and by every pass' last CTA).
+struct SelectState2 {
+  unsigned prefix, k, ticket, pad;
+  unsigned hist[2048];
+};
+
+// blockDim.x == 256.  Called by every thread of the last CTA of pass `pass`.
+__device__ __forceinline__ void select_scan_last_cta(SelectState2* st, int pass, unsigned k_in, unsigned prefix_in, float* thr_out) {
+  __shared__ unsigned wsum[8];
+  const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+  const int shift = pass == 0 ? 21 : (pass == 1 ? 10 : 0);
+  unsigned c[8], tot = 0;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { c[j] = __ldcg(&st->hist[8 * t + j]); tot += c[j]; }
+  unsigned incl = tot;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned n = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += n;
+  }
+  if (lane == 31) wsum[w] = incl;
+  __syncthreads();
+  unsigned off = 0;
+  for (int i = 0; i < w; ++i) off += wsum[i];
+  unsigned excl = off + incl - tot;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) st->hist[8 * t + j] = 0;
+  if (k_in >= excl && k_in < excl + tot) {            // exactly one thread
+    unsigned kk = k_in - excl;
+    int bin = 8 * t;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (kk < c[j]) { bin = 8 * t + j; break; }
+      kk -= c[j];
+    }
+    const unsigned np = prefix_in | ((unsigned)bin << shift);
+    st->k = kk;
+    st->prefix = np;
+    if (pass == 2) *thr_out = __uint_as_float(np);
+  }
+  if (t == 0) st->ticket = 0;
+}
+
+// shared by the three passes: merge the CTA's shared-memory histogram, elect the last CTA, let it scan
+__device__ __forceinline__ void select_finish_pass(SelectState2* st, unsigned* h /*shared [2048]*/, int pass, unsigned k_in, unsigned prefix_in,
+                                                   float* thr_out) {
+  __shared__ bool is_last;
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2048; i += blockDim.x)
+    if (h[i]) atomicAdd(&st->hist[i], h[i]);
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) is_last = atomicAdd(&st->ticket, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (is_last) {
+    __threadfence();
+    select_scan_last_cta(st, pass, k_in, prefix_in, thr_out);
+  }
+}
+
+// a9 edge metric + pass 0 of the percentile select (bits 31..21)
+__global__ void __launch_bounds__(256) k_edge_metric_select0(const float* __restrict__ depth, float* __restrict__ edge, int H, int W,
+                                                             SelectState2* st, const unsigned* __restrict__ cutoff) {
+  __shared__ unsigned h[2048];
+  for (int i = threadIdx.x; i < 2048; i += blockDim.x) h[i] = 0;
+  __syncthreads();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < H * W) {
+    const int y = i / W, x = i - y * W;
+    const float c = depth[i];
+    float e[25];
+#pragma unroll
+    for (int dy = -2; dy <= 2; ++dy)
+#pragma unroll
+      for (int dx = -2; dx <= 2; ++dx) {
+        const int yy = y + dy, xx = x + dx;
+        const float v = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? depth[yy * W + xx] : 0.f;
+        e[(dy + 2) * 5 + dx + 2] = fabsf(v - c);
+      }
+#pragma unroll
+    for (int k = 0; k < 15; ++k) {
+#pragma unroll
+      for (int j = k + 1; j < 25; ++j) {
+        const float a = e[k], b = e[j];
+        e[k] = fminf(a, b);
+        e[j] = fmaxf(a, b);
+      }
+    }
+    edge[i] = e[14];
+    atomicAdd(&h[__float_as_uint(e[14]) >> 21], 1u);
+  }
+  select_finish_pass(st, h, 0, *cutoff, 0u, nullptr);
+}
+
+// passes 1 (bits 20..10) and 2 (bits 9..0)
+__global__ void __launch_bounds__(256) k_select_pass(const float* __restrict__ v, int n, SelectState2* st, int pass, float* thr_out) {
+  __shared__ unsigned h[2048];
+  for (int i = threadIdx.x; i < 2048; i += blockDim.x) h[i] = 0;
+  const unsigned prefix = st->prefix, k_in = st->k;      // written by the previous pass' last CTA (kernel boundary in between)
+  __syncthreads();
+  const int shift = pass == 1 ? 10 : 0;
+  const unsigned hi_mask = pass == 1 ? 0xFFE00000u : 0xFFFFFC00u;
+  const unsigned bmask = pass == 2 ? 0x3FFu : 0x7FFu;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const unsigned b = __float_as_uint(v[i]);
+    if ((b & hi_mask) == prefix) atomicAdd(&h[(b >> shift) & bmask], 1u);
+  }
+  select_finish_pass(st, h, pass, k_in, prefix, thr_out);
 }
 
 __global__ void k_apply_edge_mask(const float* __restrict__ edge, const float* __restrict__ thr,
