@@ -529,12 +529,10 @@ inline Plan make_plan(int cin, int npad, int kd, int D, int H, int W, int pd, in
         const int nch = (R * P + 127) / 128;
         const int slot_pos = (std::max((R + 2) * P, nch * 128 + 2 * P + 2) + 8 + 7) / 8 * 8;
         const size_t smem = bbytes + (size_t)S * cg * slot_pos * 16 + 256;
-        const int ring = mode == 4 ? (npad == 16 ? 8 : 4) : 2;   // TMEM accumulator slots per chunk (conv_tc_is.cuh: 8 for the 16-column outputs)
-        if (smem > smem_limit || ring * nch * npad > 512) break;
+        if (smem > smem_limit || (mode == 4 ? 4 : 2) * nch * npad > 512) break;
         const int th_n = (H + R - 1) / R;
         for (int dsplit = 1; dsplit <= D; ++dsplit) {
           const int DR = (D + dsplit - 1) / dsplit;
-          if (mode == 4 && npad == 16 && DR != std::min(D, 8)) continue;   // 8-slot ring: tiles of exactly 8 planes never wrap
           if (kd >= 2 && DR < 2 && D >= 2) break;
           const int td_n = (D + DR - 1) / DR;
           const double T = (double)tw_n * th_n * td_n;

@@ -35,12 +35,7 @@ k_conv_tc_is(const __grid_constant__ CUtensorMap tmap, const TIn* __restrict__ b
   constexpr int NMMA = HILO ? 2 * NPAD : NPAD;
   constexpr int NB3 = 3 * NMMA;                       // columns of one B block
   constexpr int B_BYTES = NBLK * NB3 * 32;
-  // TMEM ring slots per chunk.  NMMA == 16 (the <= 8-channel outputs): 8 slots, and the planner gives such layers tiles of
-  // exactly 8 output planes (or all D < 8), so a tile's plane od sits in slot od and the run (od-1, od, od+1) of an instruction
-  // NEVER wraps - no split instructions, no second read of the 4 KB A tile (which was 27 % of the kernel's shared-memory
-  // traffic with the ring of 4).  Wider outputs keep the ring of 4 (512 TMEM columns).
-  constexpr int RS = NMMA == 16 ? 8 : 4;
-  constexpr int RSH = NMMA == 16 ? 3 : 2;             // log2(RS)
+  constexpr int RS = 4;                               // TMEM ring slots per chunk
   constexpr uint32_t AFMT = std::is_same<TIn, __nv_bfloat16>::value ? 1u : 0u;
   constexpr uint32_t IDESC0 = (1u << 4) | (AFMT << 7) | (AFMT << 10) | ((128u >> 4) << 24);
 
@@ -53,9 +48,9 @@ k_conv_tc_is(const __grid_constant__ CUtensorMap tmap, const TIn* __restrict__ b
   uint64_t* full = bars;                 // [S]
   uint64_t* empty = bars + 4;            // [S]
   uint64_t* acc_full = bars + 8;         // [RS]
-  uint64_t* acc_empty = bars + 16;       // [RS]
-  uint64_t* b_full = bars + 24;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 25);
+  uint64_t* acc_empty = bars + 12;       // [RS]
+  uint64_t* b_full = bars + 16;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
@@ -141,7 +136,7 @@ k_conv_tc_is(const __grid_constant__ CUtensorMap tmap, const TIn* __restrict__ b
       for (int rp = 0; rp < nin; ++rp, ++gp) {
         const int q = rp - 1;                                  // this input plane is output plane q's centre (kd = 1)
         const int oa = max(q - 1, 0), ob = min(q + 1, ndo - 1);
-        if (q + 1 <= ndo - 1) mbar_wait(&acc_empty[(go + q + 1) & (RS - 1)], ((go + q + 1) >> RSH) & 1);   // newest plane's slot is drained + zeroed
+        if (q + 1 <= ndo - 1) mbar_wait(&acc_empty[(go + q + 1) & 3], ((go + q + 1) >> 2) & 1);   // newest plane's slot is drained + zeroed
         mbar_wait(&full[gp % g.S], (gp / g.S) & 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t slot16 = sA16 + (uint32_t)(gp % g.S) * (slot_bytes >> 4);
@@ -149,8 +144,8 @@ k_conv_tc_is(const __grid_constant__ CUtensorMap tmap, const TIn* __restrict__ b
           const uint32_t a16 = slot16 + (uint32_t)c * 128u;
           const uint32_t d_chunk = tmem_base + (uint32_t)c * chunk_cols;
           for (int od = oa; od <= ob;) {
-            const int gs = (go + od) & (RS - 1);                         // ring slot of output plane od
-            const int run_end = min(ob, od + (RS - 1 - gs));                  // stay inside the ring (no wrap within a run)
+            const int gs = (go + od) & 3;                                // ring slot of output plane od
+            const int run_end = min(ob, od + (3 - gs));                  // stay inside the ring (no wrap within a run)
             const int nrun = run_end - od + 1;
             const uint32_t d_tmem = d_chunk + (uint32_t)gs * NMMA;
             const uint32_t bcol16 = (uint32_t)((od - (q - 1)) * NMMA / 8) * 8u;     // column offset in 16-byte units (128 B per 8 cols)
@@ -166,7 +161,7 @@ k_conv_tc_is(const __grid_constant__ CUtensorMap tmap, const TIn* __restrict__ b
         }
         if (leader) {
           mma_commit(&empty[gp % g.S]);                              // the input plane is consumed exactly once
-          if (q - 1 >= 0 && q - 1 <= ndo - 1) mma_commit(&acc_full[(go + q - 1) & (RS - 1)]);   // output plane q-1 has seen kd = 0,1,2
+          if (q - 1 >= 0 && q - 1 <= ndo - 1) mma_commit(&acc_full[(go + q - 1) & 3]);   // output plane q-1 has seen kd = 0,1,2
         }
         __syncwarp();
       }
@@ -188,8 +183,8 @@ k_conv_tc_is(const __grid_constant__ CUtensorMap tmap, const TIn* __restrict__ b
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     TDM_IS_TILE(tile)
     for (int od = 0; od < ndo; ++od) {
-      const int r = (go + od) & (RS - 1);
-      mbar_wait(&acc_full[r], ((go + od) >> RSH) & 1);
+      const int r = (go + od) & 3;
+      mbar_wait(&acc_full[r], ((go + od) >> 2) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const int d = d0 + od;
       for (int c = egroup; c < g.nch; c += kEpiGroups) {
