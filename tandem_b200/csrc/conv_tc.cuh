@@ -33,6 +33,11 @@
 namespace tdm {
 namespace tc {
 
+#ifdef TDM_TIMING_EXPERIMENTS
+#define TDM_DBG_MODE(g) ((g).dbg_aligned)
+#else
+#define TDM_DBG_MODE(g) 0
+#endif
 struct Geom {
   int D, H, W;            // output == input dims (stride 1, pad 1)
   int Hp, Wp;             // H+2, W+2
@@ -48,7 +53,8 @@ struct Geom {
   int S;                  // ring slots
   int oHp, oWp, opd;      // padded dims / D halo of the OUTPUT tensor (differs from the input in deconv mode)
   int iDp;                // padded plane count of the input: tensor-map dim 3 = channel_group * iDp + plane
-  int dbg_aligned;        // TIMING EXPERIMENT ONLY (TDM_DEBUG_ALIGNED_TAPS=1): every tap reads at kw = 0, i.e. 128-byte aligned A tiles (wrong results)
+  int dbg_aligned;        // only read when built with -DTDM_TIMING_EXPERIMENTS (env TDM_DEBUG_ALIGNED_TAPS; WRONG RESULTS, timing only):
+                          // 1 = every tap reads a 128-byte aligned A tile, 2 = a third of the MMA instructions, 3 = no epilogue work, 4 = 2 + 3
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }

@@ -117,11 +117,11 @@ k_conv_tc_is(const __grid_constant__ CUtensorMap tmap, const TIn* __restrict__ b
     for (int b = 0; b < NBLK; ++b) {
       if constexpr (CIN >= 16) {
         const int t = b / (CIN / 16), j = b % (CIN / 16);
-        a_off[b] = (uint32_t)(2 * j) * (cg_bytes >> 4) + (uint32_t)((t / 3) * g.P + (g.dbg_aligned ? 0 : (t % 3)));
+        a_off[b] = (uint32_t)(2 * j) * (cg_bytes >> 4) + (uint32_t)((t / 3) * g.P + (TDM_DBG_MODE(g) ? 0 : (t % 3)));
         a_lbo[b] = cg_bytes >> 4;
       } else {
         const int t0 = b < 4 ? 2 * b : 7, t1 = b < 4 ? 2 * b + 1 : 8;   // (0,1)(2,3)(4,5)(6,7)(7*,8), see conv_tc.cuh
-        const int o0 = (t0 / 3) * g.P + (g.dbg_aligned ? 0 : (t0 % 3)), o1 = (t1 / 3) * g.P + (g.dbg_aligned ? 0 : (t1 % 3));
+        const int o0 = (t0 / 3) * g.P + (TDM_DBG_MODE(g) ? 0 : (t0 % 3)), o1 = (t1 / 3) * g.P + (TDM_DBG_MODE(g) ? 0 : (t1 % 3));
         a_off[b] = (uint32_t)o0;
         a_lbo[b] = (uint32_t)(o1 - o0);
       }
@@ -152,6 +152,7 @@ k_conv_tc_is(const __grid_constant__ CUtensorMap tmap, const TIn* __restrict__ b
             const uint32_t idesc = IDESC0 | ((uint32_t)((nrun * NMMA) >> 3) << 17);
 #pragma unroll
             for (int b = 0; b < NBLK; ++b) {
+              if ((TDM_DBG_MODE(g) == 2 || TDM_DBG_MODE(g) == 4) && b >= (NBLK + 2) / 3) continue;   // TIMING EXPERIMENT ONLY: a third of the instructions (kw folded into N)
               const uint64_t ad = ((uint64_t)desc_hi << 32) | (uint64_t)((a16 + a_off[b]) | (a_lbo[b] << 16));
               const uint64_t bd = ((uint64_t)desc_hi << 32) | (uint64_t)(b_lo_base + (uint32_t)(b * NB3 * 2) + bcol16);
               if (leader) mma_f16(d_tmem, ad, bd, idesc, 1u);
@@ -188,6 +189,7 @@ k_conv_tc_is(const __grid_constant__ CUtensorMap tmap, const TIn* __restrict__ b
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const int d = d0 + od;
       for (int c = egroup; c < g.nch; c += kEpiGroups) {
+        if (TDM_DBG_MODE(g) >= 3) continue;   // TIMING EXPERIMENT ONLY: no TMEM drain / zero / global stores (is the epilogue the limiter?)
         const int l = c * 128 + qd * 32 + lane;
         const int hh = l / g.P, ww = l - hh * g.P;
         const int h = h0 + hh, w = w0 + ww;

@@ -842,7 +842,11 @@ class MvsnetEngine final : public MvsnetIface {
       TcCache tcx;
       tcx.plan = tc::make_plan(CIN, HILO ? 2 * NPAD : NPAD, 3, in.D, in.H, in.W, in.pd, 4, (size_t)tc_smem_kb_ * 1024);
       tc::Geom& g = tcx.plan.g;
-      g.dbg_aligned = std::getenv("TDM_DEBUG_ALIGNED_TAPS") ? 1 : 0;
+#ifdef TDM_TIMING_EXPERIMENTS
+      g.dbg_aligned = std::getenv("TDM_DEBUG_ALIGNED_TAPS") ? std::atoi(std::getenv("TDM_DEBUG_ALIGNED_TAPS")) : 0;
+#else
+      g.dbg_aligned = 0;
+#endif
       g.oHp = out.H + 2; g.oWp = out.W + 2; g.opd = out.pd;
       g.iDp = in.D + 2 * in.pd;
       g.in_gs = p8<const TIn>(in).gs;
