@@ -508,7 +508,8 @@ struct Plan {
   size_t smem;
 };
 
-inline Plan make_plan(int cin, int npad, int kd, int D, int H, int W, int pd, int mode = 0, size_t smem_limit = 225 * 1024) {
+inline Plan make_plan(int cin, int npad, int kd, int D, int H, int W, int pd, int mode = 0, size_t smem_limit = 225 * 1024,
+                      bool full_depth = false /* tiles span all D planes (the prob layer's soft-argmin tail needs a pixel's D logits in one CTA) */) {
   Plan p{};
   Geom& g = p.g;
   g.D = D; g.H = H; g.W = W; g.Hp = H + 2; g.Wp = W + 2; g.pd = pd;
@@ -537,7 +538,7 @@ inline Plan make_plan(int cin, int npad, int kd, int D, int H, int W, int pd, in
         const size_t smem = bbytes + (size_t)S * cg * slot_pos * 16 + 256;
         if (smem > smem_limit || (mode == 4 ? 4 : 2) * nch * npad > 512) break;
         const int th_n = (H + R - 1) / R;
-        for (int dsplit = 1; dsplit <= D; ++dsplit) {
+        for (int dsplit = 1; dsplit <= (full_depth ? 1 : D); ++dsplit) {
           const int DR = (D + dsplit - 1) / dsplit;
           if (kd >= 2 && DR < 2 && D >= 2) break;
           const int td_n = (D + DR - 1) / DR;
@@ -560,7 +561,7 @@ inline Plan make_plan(int cin, int npad, int kd, int D, int H, int W, int pd, in
     }
     if (bestR > 0 && S == s_hi) break;
   }
-  if (bestR == 0 && smem_limit < 225 * 1024) return make_plan(cin, npad, kd, D, H, W, pd, mode, 225 * 1024);   // soft limit
+  if (bestR == 0 && smem_limit < 225 * 1024) return make_plan(cin, npad, kd, D, H, W, pd, mode, 225 * 1024, full_depth);   // soft limit
   TDM_CHECK(bestR > 0, "conv_tc: no tile fits shared memory");
   g.S = bestS; g.R = bestR; g.TW = bestTW; g.P = bestTW + 2; g.DR = bestDR;
   g.nch = (g.R * g.P + 127) / 128;

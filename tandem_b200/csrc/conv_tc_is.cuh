@@ -25,11 +25,20 @@ __device__ __forceinline__ void tmem_st16_zero(uint32_t taddr) {
 }
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
-template <typename TIn, typename TOut, int CIN, int NPAD, bool OUT_PLAIN, bool HILO>
+// Per-pixel tail of the OUT_PLAIN (prob) instantiation: with tiles that span all D planes (make_plan(full_depth)) the epilogue
+// thread that stored a pixel's D logits is the same for every plane, so once the tile's last plane is drained it can finish the
+// pixel (softmax / soft-argmin / confidence, module.py:1116-1133) without another launch.  NoTail = plain convolution.
+struct NoTail {
+  static constexpr bool enabled = false;
+  __device__ __forceinline__ void operator()(const float*, int, int, int, int) const {}
+};
+
+template <typename TIn, typename TOut, int CIN, int NPAD, bool OUT_PLAIN, bool HILO, typename Tail = NoTail>
 __global__ void __launch_bounds__(kThreads, 1)
 k_conv_tc_is(const __grid_constant__ CUtensorMap tmap, const TIn* __restrict__ bimg, const float* __restrict__ bias,
              const TOut* __restrict__ res, TOut* __restrict__ out, float* __restrict__ plain_out,
-             const __grid_constant__ Geom g) {
+             const __grid_constant__ Geom g, const __grid_constant__ Tail tail) {
+  static_assert(!Tail::enabled || OUT_PLAIN, "a per-pixel tail only exists for the single-channel fp32 output");
   constexpr int CG = CIN / 8;
   constexpr int NBLK = blocks_per_kd<CIN, 0>();
   constexpr int NMMA = HILO ? 2 * NPAD : NPAD;
@@ -257,6 +266,15 @@ k_conv_tc_is(const __grid_constant__ CUtensorMap tmap, const TIn* __restrict__ b
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[r]);
+    }
+    if constexpr (Tail::enabled) {
+      // ndo == D (host-checked): this thread wrote all D logits of its pixels itself (program order makes them visible to it)
+      for (int c = egroup; c < g.nch; c += kEpiGroups) {
+        const int l = c * 128 + qd * 32 + lane;
+        const int hh = l / g.P, ww = l - hh * g.P;
+        const int h = h0 + hh, w = w0 + ww;
+        if (hh < g.R && ww < g.TW && h < g.H && w < g.W) tail(plain_out, h * g.W + w, w, h, g.H * g.W);
+      }
     }
     go += ndo;
     }

@@ -214,6 +214,7 @@ class MvsnetEngine final : public MvsnetIface {
     else if (key == "prob_direct") prob_direct_ = value != 0;
     else if (key == "direct_conv00") direct_conv00_ = value != 0;
     else if (key == "fused_select") fused_select_ = value != 0;
+    else if (key == "fused_regress") fused_regress_ = value != 0;
     else if (key == "inline_dmin") inline_dmin_ = value != 0;
     else throw Error("unknown option " + key);
   }
@@ -834,14 +835,16 @@ class MvsnetEngine final : public MvsnetIface {
     launch_pdl(kern, dim3(pl.grid, c.nsplit), pl.smem, it->second.tmap, (const TIn*)c.bimg, (const float*)c.bias, rp, op, plain, pl.g);
   }
 
-  template <typename TIn, typename TOut, int CIN, int NPAD, bool PLAIN, bool HILO>
-  void tc_is_inst(const std::string& wkey, const DevBuf& in, const DevConv& c, const DevBuf* res, const DevBuf& out, bool relu) {
-    const std::string key = wkey + "#is";
+  template <typename TIn, typename TOut, int CIN, int NPAD, bool PLAIN, bool HILO, typename Tail = tc::NoTail>
+  void tc_is_inst(const std::string& wkey, const DevBuf& in, const DevConv& c, const DevBuf* res, const DevBuf& out, bool relu,
+                  const Tail& tail = Tail()) {
+    const std::string key = wkey + (Tail::enabled ? "#is+tail" : "#is");
     auto it = tc_cache_.find(key);
     if (it == tc_cache_.end()) {
       TcCache tcx;
-      tcx.plan = tc::make_plan(CIN, HILO ? 2 * NPAD : NPAD, 3, in.D, in.H, in.W, in.pd, 4, (size_t)tc_smem_kb_ * 1024);
+      tcx.plan = tc::make_plan(CIN, HILO ? 2 * NPAD : NPAD, 3, in.D, in.H, in.W, in.pd, 4, (size_t)tc_smem_kb_ * 1024, Tail::enabled);
       tc::Geom& g = tcx.plan.g;
+      TDM_CHECK(!Tail::enabled || g.tiles_d == 1, "the prob tail needs tiles that span all depth planes");
 #ifdef TDM_TIMING_EXPERIMENTS
       g.dbg_aligned = std::getenv("TDM_DEBUG_ALIGNED_TAPS") ? std::atoi(std::getenv("TDM_DEBUG_ALIGNED_TAPS")) : 0;
 #else
@@ -872,7 +875,7 @@ class MvsnetEngine final : public MvsnetIface {
       it = tc_cache_.emplace(key, tcx).first;
     }
     const tc::Plan& pl = it->second.plan;
-    auto kern = tc::k_conv_tc_is<TIn, TOut, CIN, NPAD, PLAIN, HILO>;
+    auto kern = tc::k_conv_tc_is<TIn, TOut, CIN, NPAD, PLAIN, HILO, Tail>;
     static bool attr_set = false;
     if (!attr_set) {
       TDM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -884,7 +887,7 @@ class MvsnetEngine final : public MvsnetIface {
     const int gx = (pl.grid + tpc - 1) / tpc;
     launch_pdl(kern, dim3(gx, 1), pl.smem, it->second.tmap, (const TIn*)c.bimg_is, (const float*)c.bias,
                (const TOut*)(PLAIN ? nullptr : (res ? res->p : nullptr)), (TOut*)(PLAIN ? nullptr : out.p),
-               (float*)(PLAIN ? out.p : nullptr), pl.g);
+               (float*)(PLAIN ? out.p : nullptr), pl.g, tail);
   }
 
   struct S2Cache { tc::PlanS2 plan; CUtensorMap tmap; };
@@ -961,7 +964,17 @@ class MvsnetEngine final : public MvsnetIface {
       if (use_is_ && c.bimg_is && c.kd == 3) {
         if (bo.f32) {
           if (c.cin == 8 && c.cout == 1 && bi.kind == 1 && c.hilo) {
-            if (c.npad_is == 8) tc_is_inst<TA, TA, 8, 8, true, true>(wkey, bi, c, nullptr, bo, false);
+            if (tail_req_.stage && c.npad_is == 8 && fused_regress_) {
+              // a8 inside the prob convolution's epilogue (round 2): the thread that stored a pixel's D logits finishes the pixel
+              const TailReq& t = tail_req_;
+#define TDM_TAIL(MAXD)                                                                                           \
+  tc_is_inst<TA, TA, 8, 8, true, true, RegressTail<MAXD>>(wkey, bi, c, nullptr, bo, false,                        \
+                                                          RegressTail<MAXD>{t.dsrc, t.depth, t.conf, t.hyp, t.half_range})
+              if (t.D <= 8) TDM_TAIL(8); else if (t.D <= 32) TDM_TAIL(32); else if (t.D <= 48) TDM_TAIL(48); else TDM_TAIL(64);
+#undef TDM_TAIL
+              tail_req_.done = true;
+            }
+            else if (c.npad_is == 8) tc_is_inst<TA, TA, 8, 8, true, true>(wkey, bi, c, nullptr, bo, false);
             else tc_is_inst<TA, TA, 8, 16, true, true>(wkey, bi, c, nullptr, bo, false);
             return true;
           }
@@ -1385,8 +1398,14 @@ class MvsnetEngine final : public MvsnetIface {
       conv(k + "conv7", k + "c6", k + "x7", s5, 2, 2, true, 1, k + "c4");
       conv(k + "conv9", k + "x7", k + "x9", 2, 2, 2, true, 1, k + "c2");
       conv(k + "conv11", k + "x9", k + "x11", 2, 2, 2, true, 1, k + "c0");
-      conv(k + "prob", k + "x11", k + "logits", 1, 1, 1, false);
       {
+        TDM_CHECK(hs.D <= 64, "depth_num > 64 unsupported");
+        tail_req_ = TailReq{s, hs.D, dmin_src(s), fbuf(k + "depth_dense"), fbuf(k + "confidence_dense"), &d_params_->hyp[s - 1],
+                            &d_params_->half_range[s - 1], false};
+        conv(k + "prob", k + "x11", k + "logits", 1, 1, 1, false);
+        tail_req_.stage = 0;
+      }
+      if (!tail_req_.done) {
         const int HW = dd.H * dd.W;
         rec_begin(k + "regress", 4.0 * HW * (hs.D + 3), 0);
         const DminSrc dm = dmin_src(s);
@@ -1481,6 +1500,13 @@ class MvsnetEngine final : public MvsnetIface {
   SelectState* select_state_ = nullptr;
   SelectState2* select2_ = nullptr;
   bool inline_dmin_ = true;    // adaptive range's d_min computed where it is consumed (dmin_px) instead of by k_adaptive_dmin (A/B: 0)
+  // softmax / soft-argmin / confidence in the epilogue of the tensor-core prob convolution (set_option("fused_regress", 1)):
+  // bit-identical to k_regress and three launches fewer, but measured SLOWER (forward 1.368 vs 1.337 ms, 875 vs 904 keyframes/s
+  // with eight windows in flight; profiles/r02_bench_ab.txt): the 256 epilogue threads of a CTA finish their pixels after the
+  // last plane with nothing left to overlap, where the stand-alone kernel spreads the same work over 2048 threads per SM. Off.
+  bool fused_regress_ = false;
+  struct TailReq { int stage; int D; DminSrc dsrc; float* depth; float* conf; const HypSpec* hyp; const float* half_range; bool done; };
+  TailReq tail_req_{};
   bool fused_select_ = true;   // edge metric + pass 0 in one kernel, passes 1 / 2 with the scan in their last CTA (A/B: set_option("fused_select", 0))
   int V_ = 0, H_ = 0, W_ = 0;
   unsigned char* h_bgr_ = nullptr;
@@ -1557,7 +1583,8 @@ void debug_homography(const float* K3x3, const float* c2w_ref, const float* c2w_
 // host-only view of the tcgen05 tile planner (no GPU involved; used by the CPU test-suite): out12 = {S, R, TW, P, DR, nch,
 // slot_pos, tiles_w, tiles_h, tiles_d, grid, smem_bytes}
 void debug_conv_plan(int cin, int npad, int kd, int D, int H, int W, int pd, int mode, int smem_kb, long long* out12) {
-  const tc::Plan p = tc::make_plan(cin, npad, kd, D, H, W, pd, mode, (size_t)smem_kb * 1024);
+  // mode + 100 = the same mode with tiles that span all D planes (the prob layer with the soft-argmin tail)
+  const tc::Plan p = tc::make_plan(cin, npad, kd, D, H, W, pd, mode % 100, (size_t)smem_kb * 1024, mode >= 100);
   const tc::Geom& g = p.g;
   const long long v[12] = {g.S, g.R, g.TW, g.P, g.DR, g.nch, g.slot_pos, g.tiles_w, g.tiles_h, g.tiles_d, p.grid, (long long)p.smem};
   for (int i = 0; i < 12; ++i) out12[i] = v[i];

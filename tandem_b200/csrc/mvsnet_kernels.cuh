@@ -753,24 +753,21 @@ k_cost_volume_va16(P8<const __half> feats, const DminSrc dsrc, P8<TV> vol, int s
 // ------------------------------------------------------------------------------------------------
 // a8: softmax over D + soft-argmin depth + 4-neighbour confidence, one thread per pixel.
 // ------------------------------------------------------------------------------------------------
-template <int MAXD>
-__global__ void k_regress(const float* __restrict__ logits /*[D][H][W]*/, const DminSrc dsrc,
-                          float* __restrict__ depth, float* __restrict__ conf, int HW, int W, const HypSpec* __restrict__ hyp_p,
-                          const float* __restrict__ half_range_p) {
-  const HypSpec hyp = *hyp_p;
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= HW) return;
+template <int MAXD, bool L2_LOADS>
+__device__ __forceinline__ void regress_px(const float* __restrict__ logits /*[D][H][W]*/, const DminSrc& dsrc,
+                                           float* __restrict__ depth, float* __restrict__ conf, int HW, int i, int x, int y,
+                                           const HypSpec& hyp, float half_range) {
   const int D = hyp.D;
   float l[MAXD];
   float m = -INFINITY;
 #pragma unroll
   for (int j = 0; j < MAXD; ++j)
-    if (j < D) { l[j] = logits[(long long)j * HW + i]; m = fmaxf(m, l[j]); }
+    if (j < D) { l[j] = L2_LOADS ? __ldcg(logits + (long long)j * HW + i) : logits[(long long)j * HW + i]; m = fmaxf(m, l[j]); }
   float s = 0.f;
 #pragma unroll
   for (int j = 0; j < MAXD; ++j)
     if (j < D) { l[j] = expf(l[j] - m); s += l[j]; }
-  const float dm = hyp.adaptive ? dmin_px(dsrc, i, i % W, i / W, *half_range_p) : 0.f;
+  const float dm = hyp.adaptive ? dmin_px(dsrc, i, x, y, half_range) : 0.f;
   float dsum = 0.f, isum = 0.f;
 #pragma unroll
   for (int j = 0; j < MAXD; ++j)
@@ -787,6 +784,30 @@ __global__ void k_regress(const float* __restrict__ logits /*[D][H][W]*/, const 
   depth[i] = dsum;
   conf[i] = c;
 }
+
+template <int MAXD>
+__global__ void k_regress(const float* __restrict__ logits /*[D][H][W]*/, const DminSrc dsrc,
+                          float* __restrict__ depth, float* __restrict__ conf, int HW, int W, const HypSpec* __restrict__ hyp_p,
+                          const float* __restrict__ half_range_p) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= HW) return;
+  regress_px<MAXD, false>(logits, dsrc, depth, conf, HW, i, i % W, i / W, *hyp_p, *half_range_p);
+}
+
+// the same arithmetic as the tail of the tensor-core prob convolution (conv_tc_is.cuh, Tail): the epilogue thread that stored
+// a pixel's D logits finishes the pixel, reading its own stores back from L2 (bit-identical to k_regress by construction)
+template <int MAXD>
+struct RegressTail {
+  static constexpr bool enabled = true;
+  DminSrc dsrc;
+  float* depth;
+  float* conf;
+  const HypSpec* hyp;
+  const float* half_range;
+  __device__ __forceinline__ void operator()(const float* logits, int i, int x, int y, int HW) const {
+    regress_px<MAXD, true>(logits, dsrc, depth, conf, HW, i, x, y, *hyp, *half_range);
+  }
+};
 
 // ------------------------------------------------------------------------------------------------
 // K4 (a9): edge filter.  (1) per-pixel 15-th smallest |window - centre| over a zero padded 5x5

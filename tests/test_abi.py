@@ -121,6 +121,7 @@ def test_tcgen05_tile_planner_invariants():
             c0 = (32, 16, 8)[s]
             shapes.append((c0, 48, 3, D, h, w, 1, 4))                       # conv0, input-stationary, hi/lo, 3 kd
             shapes.append((8, 48, 3, D, h, w, 1, 4))                        # prob
+            shapes.append((8, 16, 3, D, h, w, 1, 104))                      # prob with the soft-argmin tail: tiles span all D planes
             for lvl, (cin, npad) in enumerate([(16, 32), (32, 32), (64, 32)]):
                 d2, h2, w2 = max(D >> (lvl + 1), 1), h >> (lvl + 1), w >> (lvl + 1)
                 shapes.append((cin, npad, 3, d2, h2, w2, 1, 0))             # conv2 / conv4 / conv6
@@ -132,6 +133,9 @@ def test_tcgen05_tile_planner_invariants():
         rc = l.tdm_debug_conv_plan(cin, npad, kd, D, H, W, pd, mode, 225, out)
         assert rc == 0, (cin, npad, kd, D, H, W, mode, l.tdm_last_error())
         S, R, TW, P, DR, nch, slot_pos, tw, th, td, grid, smem = [int(x) for x in out]
+        if mode >= 100:
+            assert td == 1 and DR == D, (D, H, W, DR, td)
+            mode -= 100
         key = (cin, npad, kd, D, H, W, mode)
         assert P == TW + 2 and P <= 256 and R >= 1 and DR >= 1 and 2 <= S <= 4, key
         assert tw * TW >= W and (tw - 1) * TW < W and th * R >= H and (th - 1) * R < H and td * DR >= D and (td - 1) * DR < D, key

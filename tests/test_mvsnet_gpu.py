@@ -297,3 +297,25 @@ def test_tma_staged_cost_volume_is_bit_identical(golden_full, golden_small, whic
         vols.append(m.debug_tensor("s3.volume"))
     assert np.array_equal(vols[0], vols[1]), f"stage-3 volume differs on {np.mean(vols[0] != vols[1]):.6f} of the entries"
     assert np.array_equal(outs[0].depth_dense, outs[1].depth_dense) and np.array_equal(outs[0].depth, outs[1].depth)
+
+
+@pytest.mark.parametrize("weights,which", [("abl03_view_aggregation", "full"), ("abl03_view_aggregation", "small"),
+                                           ("abl04_fewer_depth_planes", "small")])
+def test_regress_in_prob_epilogue_is_bit_identical(golden_full, golden_small, weights, which):
+    """SURVEY 8a a8 / VERDICT r01 item 9: softmax + soft-argmin + confidence (module.py:1116-1133) run in the epilogue of the
+    tensor-core prob convolution (tiles span all D planes, so the thread that stored a pixel's D logits finishes the pixel) -
+    same arithmetic, same order as the stand-alone k_regress, so every output map must be bit-identical with
+    set_option("fused_regress", 0); three launches fewer per forward.  D = 48 / 32 / 8 (abl03) and 48 / 4 / 4 (abl04)."""
+    g = golden_full if which == "full" else golden_small
+    res, launches = [], []
+    for fused in (1, 0):
+        m, out = _run_opts(g, weights, "mixed16", fused_regress=fused)
+        res.append((out, [m.stage_output(s, "depth_dense") for s in (1, 2, 3)], [m.stage_output(s, "confidence_dense") for s in (1, 2, 3)]))
+        launches.append(m.run_resident(1)[1])
+    (oa, da, ca), (ob, db, cb) = res
+    for s in range(3):
+        assert np.array_equal(da[s], db[s]), f"stage {s + 1} depth differs on {np.mean(da[s] != db[s]):.6f} of the pixels"
+        assert np.array_equal(ca[s], cb[s]), f"stage {s + 1} confidence differs"
+    for k in ("depth", "confidence", "depth_dense", "confidence_dense"):
+        assert np.array_equal(getattr(oa, k), getattr(ob, k)), k
+    assert launches[0] == launches[1] - 3, launches
