@@ -200,7 +200,6 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmap /*P8 input: {8, Wp, Hp, group
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     mbar_expect_tx(b_full, B_BYTES);          // weights do not depend on the previous kernel: fetch them before pdl_wait
     bulk_g2s(sB, bimg, B_BYTES, b_full);
-    pdl_launch_dependents();
   }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(tmem_cols) : "memory");
@@ -211,6 +210,9 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmap /*P8 input: {8, Wp, Hp, group
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
   pdl_wait();   // from here on activations written by the previous kernel are read and our outputs are written
+  // trigger the dependents only now: a trigger BEFORE the wait lets the whole chain of later kernels become resident early (each
+  // one's prologue would trigger the next), and their idle CTAs then hold the shared memory the running kernel's tiles need
+  if (threadIdx.x == 0) pdl_launch_dependents();
 
   if (warp == 0) {
     // ===================== TMA producer =====================

@@ -194,6 +194,7 @@ class MvsnetEngine final : public MvsnetIface {
     if (key == "filter_all_stages") filter_all_ = value != 0;
     else if (key == "use_graph") use_graph_ = value != 0;
     else if (key == "use_pdl") use_pdl_ = value != 0;
+    else if (key == "pdl_min_smem_kb") { TDM_CHECK(value >= 0 && value <= 225, "pdl_min_smem_kb out of range"); pdl_min_smem_kb_ = value; }
     else if (key == "cv_variant") { TDM_CHECK(value >= 0 && value <= 5, "cv_variant out of range"); cv_variant_ = value; }
     else if (key == "tc_smem_kb") { TDM_CHECK(value >= 48 && value <= 225, "tc_smem_kb out of range"); tc_smem_kb_ = value; tc_cache_.clear(); s2_cache_.clear(); }
     else if (key.rfind("depth_num_stage", 0) == 0 && key.size() == 16 && key[15] >= '1' && key[15] <= '3') {
@@ -772,7 +773,9 @@ class MvsnetEngine final : public MvsnetIface {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = grid;
     cfg.blockDim = dim3(tc::kThreads);
-    cfg.dynamicSmemBytes = smem;
+    // with PDL an early-launched dependent must not stack several CTAs on the few SMs its predecessor left idle (they would
+    // serialise on the 512 TMEM columns): ask for enough shared memory that one CTA fills an SM
+    cfg.dynamicSmemBytes = use_pdl_ ? std::max(smem, (size_t)pdl_min_smem_kb_ * 1024) : smem;
     cfg.stream = stream_;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -1507,6 +1510,7 @@ class MvsnetEngine final : public MvsnetIface {
   bool fused_regress_ = false;
   struct TailReq { int stage; int D; DminSrc dsrc; float* depth; float* conf; const HypSpec* hyp; const float* half_range; bool done; };
   TailReq tail_req_{};
+  int pdl_min_smem_kb_ = 120;
   bool fused_select_ = true;   // edge metric + pass 0 in one kernel, passes 1 / 2 with the scan in their last CTA (A/B: set_option("fused_select", 0))
   int V_ = 0, H_ = 0, W_ = 0;
   unsigned char* h_bgr_ = nullptr;
@@ -1527,7 +1531,13 @@ class MvsnetEngine final : public MvsnetIface {
   bool cv_tmap_ok_ = false;
   unsigned* d_cv_stats_ = nullptr;
   int cv_variant_ = 3;   // 0: generic cost-volume kernel; 1-4: k_cost_volume_va16 (ND 2/2/4 | 4/4/4, fp32 | fp16 accumulate)
-  bool warmed_ = false, use_graph_ = true, use_pdl_ = false;   // PDL measured slower (1.86 vs 1.73 ms): dependents squat on SM resources while they wait
+  // Programmatic dependent launch of the tensor-core kernels (round 2: ON). Round 1 measured it slower (1.86 vs 1.73 ms) for two
+  // reasons found in round 2: (1) the trigger sat BEFORE griddepcontrol.wait, so every kernel's prologue triggered the next and the
+  // whole chain became resident early; (2) early CTAs of the small-footprint kernels stacked 2-5 deep on the few SMs the predecessor
+  // left idle and then serialised on the 512 TMEM columns. With the trigger after the wait and pdl_min_smem_kb_ = 120 (one
+  // tensor-core CTA per SM) it wins at every concurrency: 1.339 / 1.157 / 1.100 / 1.084 ms per window with 1 / 2 / 4 / 8 windows
+  // in flight against 1.352 / 1.204 / 1.128 / 1.117 without (tools/pdl_sweep.py, profiles/r02_bench_ab.txt).
+  bool warmed_ = false, use_graph_ = true, use_pdl_ = true;
   int slot_ = 0;           // index into c_call_params
   int tc_smem_kb_ = 225;   // shared-memory budget of the tile planner (<= 113 lets two CTAs share an SM)
   bool use_is_ = true;   // input-stationary kernel for the 3-D stride-1 convs
