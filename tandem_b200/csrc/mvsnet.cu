@@ -193,7 +193,7 @@ class MvsnetEngine final : public MvsnetIface {
     drop_graph();
     if (key == "filter_all_stages") filter_all_ = value != 0;
     else if (key == "use_graph") use_graph_ = value != 0;
-    else if (key == "use_pdl") use_pdl_ = value != 0;
+    else if (key == "use_pdl") { TDM_CHECK(value >= 0 && value <= 2, "use_pdl: 0 off, 1 tensor-core kernels, 2 every kernel of the forward"); use_pdl_ = value; }
     else if (key == "pdl_min_smem_kb") { TDM_CHECK(value >= 0 && value <= 225, "pdl_min_smem_kb out of range"); pdl_min_smem_kb_ = value; }
     else if (key == "cv_variant") { TDM_CHECK(value >= 0 && value <= 5, "cv_variant out of range"); cv_variant_ = value; }
     else if (key == "tc_smem_kb") { TDM_CHECK(value >= 48 && value <= 225, "tc_smem_kb out of range"); tc_smem_kb_ = value; tc_cache_.clear(); s2_cache_.clear(); }
@@ -752,18 +752,38 @@ class MvsnetEngine final : public MvsnetIface {
     if constexpr (COUT != 1) {
       if (out_b) {
         ob = p8<TOut>(*out_b);
-        k_conv_direct<TIn, TOut, CIN, COUT><<<cdiv(npos, 128), 128, 0, stream_>>>(p8<const TIn>(in), c.w, c.bias, r, o, plain, g, ob, bias_b);
+        launch_k(k_conv_direct<TIn, TOut, CIN, COUT>, dim3(cdiv(npos, 128)), dim3(128), p8<const TIn>(in), c.w, c.bias, r, o, plain, g, ob, bias_b);
         return;
       }
     }
     if constexpr (COUT >= 16) {
       if (npos < 128ll * 592) {  // too few positions to fill the chip: split the output channels over blockIdx.y
         dim3 grid(cdiv(npos, 128), COUT / 8);
-        k_conv_direct<TIn, TOut, CIN, COUT, 8><<<grid, 128, 0, stream_>>>(p8<const TIn>(in), c.w, c.bias, r, o, plain, g);
+        launch_k(k_conv_direct<TIn, TOut, CIN, COUT, 8>, grid, dim3(128), p8<const TIn>(in), c.w, c.bias, r, o, plain, g, P8<TOut>{}, (const float*)nullptr);
         return;
       }
     }
-    k_conv_direct<TIn, TOut, CIN, COUT><<<cdiv(npos, 128), 128, 0, stream_>>>(p8<const TIn>(in), c.w, c.bias, r, o, plain, g);
+    launch_k(k_conv_direct<TIn, TOut, CIN, COUT>, dim3(cdiv(npos, 128)), dim3(128), p8<const TIn>(in), c.w, c.bias, r, o, plain, g, P8<TOut>{}, (const float*)nullptr);
+  }
+
+  // the other kernels of the forward (all begin with grid_dep_sync()): with use_pdl = 2 they carry the attribute too
+  template <typename... KArgs, typename... Args>
+  void launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, Args&&... args) {
+    if (use_pdl_ < 2) {
+      kern<<<grid, block, 0, stream_>>>(static_cast<KArgs>(args)...);
+      return;
+    }
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = stream_;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    TDM_CUDA(cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...));
   }
 
   // tensor-core kernels are launched with programmatic stream serialization (PDL): their prologue and weight-image
@@ -1198,7 +1218,7 @@ class MvsnetEngine final : public MvsnetIface {
         const bool h16 = cv_variant_ >= 3;   // (variant 5 = variant 3 outside stage 3)
         const long long thr = (long long)cdiv(vb.D, nd) * vb.H * vb.W * (fb.C == 32 ? 2 : 1);
         const unsigned grid = (unsigned)cdiv(thr, 128);
-        auto go = [&](auto kern) { kern<<<grid, 128, 0, stream_>>>(p8<const __half>(fb), dm, p8<TV>(vb), slot_, s - 1); };
+        auto go = [&](auto kern) { launch_k(kern, dim3(grid), dim3(128), p8<const __half>(fb), dm, p8<TV>(vb), slot_, s - 1); };
         if (fb.C == 32) {
           if (nd == 2) { if (h16) go(k_cost_volume_va16<TV, 16, 2, 2, true>); else go(k_cost_volume_va16<TV, 16, 2, 2, false>); }
           else         { if (h16) go(k_cost_volume_va16<TV, 16, 2, 4, true>); else go(k_cost_volume_va16<TV, 16, 2, 4, false>); }
@@ -1250,11 +1270,11 @@ class MvsnetEngine final : public MvsnetIface {
     const int n = d.H * d.W;
     if (fused_select_) {
       rec_begin(k + "edge_metric+select0", 8.0 * n, 0);
-      k_edge_metric_select0<<<cdiv(n, 256), 256, 0, stream_>>>(fbuf(k + "depth_dense"), fbuf(k + "edge"), d.H, d.W, select2_, &d_params_->cutoff[s - 1]);
+      launch_k(k_edge_metric_select0, dim3(cdiv(n, 256)), dim3(256), fbuf(k + "depth_dense"), fbuf(k + "edge"), d.H, d.W, select2_, &d_params_->cutoff[s - 1]);
       rec_end();
       rec_begin(k + "percentile", 8.0 * n, 0);
       for (int pass = 1; pass <= 2; ++pass)
-        k_select_pass<<<std::min(cdiv(n, 256 * 8), 296), 256, 0, stream_>>>(fbuf(k + "edge"), n, select2_, pass, fbuf("thr") + (s - 1));
+        launch_k(k_select_pass, dim3(std::min(cdiv(n, 256 * 8), 296)), dim3(256), fbuf(k + "edge"), n, select2_, pass, fbuf("thr") + (s - 1));
       launch_count_ += 1;
       rec_end();
     } else {
@@ -1271,7 +1291,7 @@ class MvsnetEngine final : public MvsnetIface {
     rec_end();
     }
     rec_begin(k + "apply_mask", 20.0 * n, 0);
-    k_apply_edge_mask<<<cdiv(n, 256), 256, 0, stream_>>>(fbuf(k + "edge"), fbuf("thr") + (s - 1), fbuf(k + "depth_dense"),
+    launch_k(k_apply_edge_mask, dim3(cdiv(n, 256)), dim3(256), fbuf(k + "edge"), fbuf("thr") + (s - 1), fbuf(k + "depth_dense"),
                                                        fbuf(k + "confidence_dense"), fbuf(k + "depth"),
                                                        fbuf(k + "confidence"), n);
     TDM_CUDA(cudaGetLastError());
@@ -1320,7 +1340,7 @@ class MvsnetEngine final : public MvsnetIface {
         if (direct_conv00_) {
           fused = true;
           rec_begin("f.conv0.0[u8-direct]", 3.0 * n + 8.0 * n * sizeof(TA), 2.0 * 27 * 8 * (double)n);
-          k_conv00_u8<TA><<<dim3(cdiv(W, 32), cdiv(H, 8), V), 256, 0, stream_>>>(d_bgr_, p8<TA>(bufs_.at("f.c0_0")), H, W, slot_);
+          launch_k(k_conv00_u8<TA>, dim3(cdiv(W, 32), cdiv(H, 8), V), dim3(256), d_bgr_, p8<TA>(bufs_.at("f.c0_0")), H, W, slot_);
           TDM_CUDA(cudaGetLastError());
           rec_end();
         }
@@ -1413,9 +1433,9 @@ class MvsnetEngine final : public MvsnetIface {
         rec_begin(k + "regress", 4.0 * HW * (hs.D + 3), 0);
         const DminSrc dm = dmin_src(s);
         const float* hr = &d_params_->half_range[s - 1];
-        if (hs.D <= 8) k_regress<8><<<cdiv(HW, 128), 128, 0, stream_>>>(fbuf(k + "logits"), dm, fbuf(k + "depth_dense"), fbuf(k + "confidence_dense"), HW, dd.W, &d_params_->hyp[s - 1], hr);
-        else if (hs.D <= 32) k_regress<32><<<cdiv(HW, 128), 128, 0, stream_>>>(fbuf(k + "logits"), dm, fbuf(k + "depth_dense"), fbuf(k + "confidence_dense"), HW, dd.W, &d_params_->hyp[s - 1], hr);
-        else if (hs.D <= 64) k_regress<64><<<cdiv(HW, 128), 128, 0, stream_>>>(fbuf(k + "logits"), dm, fbuf(k + "depth_dense"), fbuf(k + "confidence_dense"), HW, dd.W, &d_params_->hyp[s - 1], hr);
+        if (hs.D <= 8) launch_k(k_regress<8>, dim3(cdiv(HW, 128)), dim3(128), fbuf(k + "logits"), dm, fbuf(k + "depth_dense"), fbuf(k + "confidence_dense"), HW, dd.W, &d_params_->hyp[s - 1], hr);
+        else if (hs.D <= 32) launch_k(k_regress<32>, dim3(cdiv(HW, 128)), dim3(128), fbuf(k + "logits"), dm, fbuf(k + "depth_dense"), fbuf(k + "confidence_dense"), HW, dd.W, &d_params_->hyp[s - 1], hr);
+        else if (hs.D <= 64) launch_k(k_regress<64>, dim3(cdiv(HW, 128)), dim3(128), fbuf(k + "logits"), dm, fbuf(k + "depth_dense"), fbuf(k + "confidence_dense"), HW, dd.W, &d_params_->hyp[s - 1], hr);
         else throw Error("depth_num > 64 unsupported");
         TDM_CUDA(cudaGetLastError());
         rec_end();
@@ -1537,7 +1557,8 @@ class MvsnetEngine final : public MvsnetIface {
   // left idle and then serialised on the 512 TMEM columns. With the trigger after the wait and pdl_min_smem_kb_ = 120 (one
   // tensor-core CTA per SM) it wins at every concurrency: 1.339 / 1.157 / 1.100 / 1.084 ms per window with 1 / 2 / 4 / 8 windows
   // in flight against 1.352 / 1.204 / 1.128 / 1.117 without (tools/pdl_sweep.py, profiles/r02_bench_ab.txt).
-  bool warmed_ = false, use_graph_ = true, use_pdl_ = true;
+  bool warmed_ = false, use_graph_ = true;
+  int use_pdl_ = 1;   // 2: the FMA-pipe kernels (cost volume, soft-argmin, edge filter ...) are launched with the attribute as well
   int slot_ = 0;           // index into c_call_params
   int tc_smem_kb_ = 225;   // shared-memory budget of the tile planner (<= 113 lets two CTAs share an SM)
   bool use_is_ = true;   // input-stationary kernel for the 3-D stride-1 convs

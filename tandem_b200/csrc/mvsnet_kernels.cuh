@@ -23,6 +23,17 @@
 
 namespace tdm {
 
+// Programmatic dependent launch (mvsnet.cu launch_pdl / launch_k): first statement of every kernel of the forward.  Launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization the grid may become resident while its predecessor still runs; it must not touch
+// memory before griddepcontrol.wait (= predecessor complete and visible).  The trigger right behind the wait lets the NEXT kernel's
+// launch latency / prologue overlap this grid (one kernel of look-ahead).  Launched normally, both instructions are no-ops apart from
+// the trigger, which still lets a tensor-core successor set up its barriers, TMEM and weight image early.
+__device__ __forceinline__ void grid_dep_sync() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
+
 template <typename T>
 struct P8 {
   T* p;
@@ -83,6 +94,7 @@ __constant__ Conv00Weights c_conv00[8 /* kMaxEngines */];
 
 template <typename T>
 __global__ void __launch_bounds__(256) k_conv00_u8(const unsigned char* __restrict__ bgr /*[V][H][W][3], reference view first*/, P8<T> out, int H, int W, int slot) {
+  grid_dep_sync();
   constexpr int TX = 32, TY = 8;
   __shared__ float tile[TY + 2][(TX + 2) * 3];   // x = u8 / 255 formed ONCE per input value (IEEE division, dr_mvsnet.cpp:203-210)
   const Conv00Weights& cw = c_conv00[slot];
@@ -144,6 +156,7 @@ k_conv_direct(const P8<const TIn> in, const float* __restrict__ wgt /*[taps][CIN
               const float* __restrict__ bias /*[COUT] or null*/, const P8<const TOut> res,
               const P8<TOut> out, float* __restrict__ plain_out /*COUT==1: fp32 [D][H][W]*/, ConvGeom g,
               const P8<TOut> out_b = P8<TOut>{}, const float* __restrict__ bias_b = nullptr /*optional 2nd output = out + bias_b*/) {
+  grid_dep_sync();
   constexpr int SLICE = CIN * COUT_T;
   constexpr int TAPS_PER_STAGE = (SLICE >= 4096) ? 1 : (4096 / SLICE);
   __shared__ __align__(16) float ws[TAPS_PER_STAGE * SLICE];
@@ -622,6 +635,7 @@ __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
 template <typename TV, int C /*channels of one thread*/, int CSPLIT, int ND, bool ACC16>
 __global__ void __launch_bounds__(128)
 k_cost_volume_va16(P8<const __half> feats, const DminSrc dsrc, P8<TV> vol, int slot, int stage) {
+  grid_dep_sync();
   const CvParams& p = c_call_params[slot].cv[stage];
   constexpr float kS = 1.f / 64.f;
   const int HW = p.H * p.W;
@@ -789,6 +803,7 @@ template <int MAXD>
 __global__ void k_regress(const float* __restrict__ logits /*[D][H][W]*/, const DminSrc dsrc,
                           float* __restrict__ depth, float* __restrict__ conf, int HW, int W, const HypSpec* __restrict__ hyp_p,
                           const float* __restrict__ half_range_p) {
+  grid_dep_sync();
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= HW) return;
   regress_px<MAXD, false>(logits, dsrc, depth, conf, HW, i, i % W, i / W, *hyp_p, *half_range_p);
@@ -972,6 +987,7 @@ __device__ __forceinline__ void select_finish_pass(SelectState2* st, unsigned* h
 // a9 edge metric + pass 0 of the percentile select (bits 31..21)
 __global__ void __launch_bounds__(256) k_edge_metric_select0(const float* __restrict__ depth, float* __restrict__ edge, int H, int W,
                                                              SelectState2* st, const unsigned* __restrict__ cutoff) {
+  grid_dep_sync();
   __shared__ unsigned h[2048];
   for (int i = threadIdx.x; i < 2048; i += blockDim.x) h[i] = 0;
   __syncthreads();
@@ -1005,6 +1021,7 @@ __global__ void __launch_bounds__(256) k_edge_metric_select0(const float* __rest
 
 // passes 1 (bits 20..10) and 2 (bits 9..0)
 __global__ void __launch_bounds__(256) k_select_pass(const float* __restrict__ v, int n, SelectState2* st, int pass, float* thr_out) {
+  grid_dep_sync();
   __shared__ unsigned h[2048];
   for (int i = threadIdx.x; i < 2048; i += blockDim.x) h[i] = 0;
   const unsigned prefix = st->prefix, k_in = st->k;      // written by the previous pass' last CTA (kernel boundary in between)
@@ -1022,6 +1039,7 @@ __global__ void __launch_bounds__(256) k_select_pass(const float* __restrict__ v
 __global__ void k_apply_edge_mask(const float* __restrict__ edge, const float* __restrict__ thr,
                                   const float* __restrict__ depth_dense, const float* __restrict__ conf_dense,
                                   float* __restrict__ depth, float* __restrict__ conf, int n) {
+  grid_dep_sync();
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const bool m = edge[i] > *thr;
