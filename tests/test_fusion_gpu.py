@@ -188,6 +188,61 @@ def test_config3_shape_matches_oracle():
     assert nblk > 20000 and exact > 0.9999
 
 
+def test_occupancy_shortcut_is_bit_identical():
+    """The ray-cast's empty-space shortcut (dilated block-occupancy bitmap in front of the sampler, option occ_skip) must not
+    move a single sample: two volumes fed the same scans, one rendered with and one without it, give renders that are equal bit
+    for bit - views from inside the map, views from outside looking in and looking away, a pose 100 m from the origin (block
+    coordinates alias modulo 128 in the bitmap), a Z-slab volume, and the config-3 shape."""
+    def pair(make, scans, views):
+        vols = []
+        for v in (0, 1):
+            f = make()
+            f.set_option("occ_skip", v)
+            vols.append(f)
+        cover = []
+        for k, q in enumerate(views):
+            bgr, depth, pose = scans[min(k, len(scans) - 1)]
+            out = []
+            for f in vols:
+                f.IntegrateScanAsync(bgr, depth, pose)
+                f.RenderAsync([q])
+                (rb,), (rd,) = f.GetRenderResult()
+                out.append((rd.copy(), rb.copy()))
+            (d0, b0), (d1, b1) = out
+            assert np.array_equal(d0.view(np.uint32), d1.view(np.uint32)) and np.array_equal(b0, b1), f"view {k}"
+            cover.append(float((d1 > 0).mean()))
+        return cover
+
+    poses, frames = _scene_frames(3)
+    for shift, slab in ((0.0, None), (100.0, None), (0.0, (-4, 3))):
+        ps = [p.copy() for p in poses]
+        for p in ps:
+            p[:3, 3] += np.float32(shift)
+        away = look_at_pose((3.0, 3.0, 3.0), (3.0, 8.0, 4.0)); away[:3, 3] += np.float32(shift)          # outside, looking away
+        outside = look_at_pose((3.0, 0.2, 0.1), (0.0, 0.0, 0.0)); outside[:3, 3] += np.float32(shift)    # outside, looking in
+
+        def make():
+            f = DrFusion(_opts())
+            if slab:
+                f.set_slab(*slab)
+            return f
+        scans = [(bgr, depth, pose) for (bgr, depth), pose in zip(frames, ps)]
+        cover = pair(make, scans, [ps[0], ps[1], ps[2], ps[0], outside, away])
+        assert slab or cover[3] > 0.5, cover
+        assert cover[5] == 0.0, cover
+    # config-3 shape: 640x480 into the initDr-sized map, camera inside the 5 m room
+    hh, ww = 480, 640
+    intr = dict(fx=320.0, fy=320.0, cx=319.5, cy=239.5)
+    scene = RoomScene()
+    ps = circle_trajectory(3, radius=1.0)
+    fr = [scene.render(p, hh, ww, **intr, noise_sigma=0.002, dropout=0.02, seed=k) for k, p in enumerate(ps)]
+    for p in ps:
+        p[:3, 3] += np.float32(5.12)
+    scans = [(bgr, depth, pose) for (bgr, depth), pose in zip(fr, ps)]
+    cover = pair(lambda: DrFusion(DrFusionOptions(height=hh, width=ww, **intr)), scans, [ps[0], ps[1], ps[2], ps[0]])
+    assert min(cover) > 0.9, cover
+
+
 def test_z_slab_partition_matches_single_volume():
     """two Z-slabs (each + 1 halo block) integrated from the same scans reproduce the single-volume map on
     their owned blocks bit-for-bit, and the per-pixel nearest-hit reduction of the two slab renders reproduces the
