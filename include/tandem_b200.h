@@ -194,6 +194,10 @@ long long tdm_fusion_get_mesh(tdm_fusion* h, float* vert, float* cols, size_t ma
  * the voxel indices {gMA, gMB, gPA, gPB, gC} (ints5), {wM, wP, cM, cP} (floats4), and per voxel block {first cell, #cells}
  * (ranges2, bmin_nb = {first block, #blocks}). Returns the number of cells (mesh_extractor.cu:248-261 arithmetic). */
 int tdm_debug_mesh_axis_table(float lower, float upper, float voxel_size, int* ints5, float* floats4, int* ranges2, int* bmin_nb, int capacity);
+/* Host-only introspection (no GPU needed): the bucket the voxel-hashing kernels compute for block (x, y, z) - a division-free
+ * remainder (precomputed ceil(2^64 / num_buckets)) - and, in *reference_expression when non-NULL, the reference's expression
+ * ((x * 73856093) ^ (y * 19349669) ^ (z * 83492791)) % num_buckets, + num_buckets when negative (hash_table.cu:157-168). */
+int tdm_debug_hash_slot(int x, int y, int z, int num_buckets, int* reference_expression);
 /* Device time (CUDA events) of the last extraction: classify + scan + emit. */
 int tdm_fusion_last_mesh_ms(tdm_fusion* h, float* ms);
 /* Introspection for parity tests and the roofline: counters of the last integrate / render. */

@@ -132,6 +132,12 @@ int tdm_debug_mesh_axis_table(float lower, float upper, float voxel_size, int* i
   return tdm::mesh_axis_table(lower, upper, voxel_size, ints5, floats4, ranges2, bmin_nb, capacity);
   TDM_API_END
 }
+int tdm_debug_hash_slot(int x, int y, int z, int num_buckets, int* reference_expression) {
+  TDM_API_BEGIN
+  TDM_CHECK(num_buckets > 0, "num_buckets must be positive");
+  return tdm::hash_slot_host(x, y, z, num_buckets, reference_expression);
+  TDM_API_END
+}
 int tdm_fusion_set_option(tdm_fusion* h, const char* name, int value) {
   TDM_API_BEGIN
   TDM_CHECK(h && name, "null argument");

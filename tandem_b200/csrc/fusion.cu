@@ -49,6 +49,8 @@ struct FusionDev {
   int* counters;             // [0] #blocks allocated, [1] dropped, [2] visible (last scan), [3] new this scan
   int slab_lo, slab_hi;      // Z-slab partition (block z in [slab_lo, slab_hi) is kept), default: everything
   float r_vs, r_fx, r_fy;    // RN(1 / voxel_size), RN(1 / fx), RN(1 / fy) for cdiv_ (ray-cast only)
+  unsigned long long mod_magic;   // ceil(2^64 / num_buckets): exact 32-bit remainder without a division (fast_umod)
+  unsigned mod_c32;               // 2^32 mod num_buckets
   unsigned* occ;             // [128*128*4] dilated block-occupancy bitmap of the blocks THIS volume stores (occ_mark below)
   // Interleaved Z-slab partition (il_k > 0): block z belongs to rank ((z - il_z0) div il_k) mod il_world; a rank STORES its own
   // blocks plus one halo block on either side of each of its slabs.  Thin interleaved slabs keep the per-frame work of every
@@ -127,6 +129,15 @@ __device__ __forceinline__ float3 get_point3d_c(const FusionDev& d, int i, float
   p.y = cdiv_<FAST>(mul_(sub_((float)v, o.cy), p.z), o.fy, d.r_fy);
   return p;
 }
+// the same with the pixel terms (u - cx), (v - cy) - loop invariants of a ray - computed once by the caller (same operations)
+template <bool FAST>
+__device__ __forceinline__ float3 get_point3d_px(const FusionDev& d, float ucx /* sub_(u, cx) */, float vcy /* sub_(v, cy) */, float depth) {
+  float3 p;
+  p.z = depth;
+  p.x = cdiv_<FAST>(mul_(ucx, p.z), d.o.fx, d.r_fx);
+  p.y = cdiv_<FAST>(mul_(vcy, p.z), d.o.fy, d.r_fy);
+  return p;
+}
 __device__ __forceinline__ int2 project(const tdm_fusion_options& o, float3 p) {  // utils.h:103-108
   const float x = add_(div_(mul_(o.fx, p.x), p.z), o.cx);
   const float y = add_(div_(mul_(o.fy, p.y), p.z), o.cy);
@@ -138,11 +149,28 @@ __device__ __forceinline__ unsigned long long pack_key(int x, int y, int z) {
   return (unsigned long long)(unsigned)(x + kKeyBias) | ((unsigned long long)(unsigned)(y + kKeyBias) << 21) |
          ((unsigned long long)(unsigned)(z + kKeyBias) << 42);
 }
-__device__ __forceinline__ long long hash_bucket(const tdm_fusion_options& o, int x, int y, int z) {  // hash_table.cu:157-168
-  const int a = (int)((unsigned)x * 73856093u), b = (int)((unsigned)y * 19349669u), c = (int)((unsigned)z * 83492791u);
-  int r = (a ^ b ^ c) % o.num_buckets;
-  if (r < 0) r += o.num_buckets;
-  return (long long)r * o.bucket_size;
+// u mod n for any 32-bit u and n from the precomputed M = ceil(2^64 / n) (Lemire, Kaser, Kurz, "Faster remainder by direct
+// computation", 2019: exact whenever M has at least 64 fractional bits for 32-bit operands): fraction = M * u mod 2^64,
+// remainder = floor(fraction * n / 2^64).  ~8 integer instructions instead of the ~25 of the runtime `%` expansion.
+__host__ __device__ __forceinline__ unsigned fast_umod(unsigned u, unsigned n, unsigned long long M) {
+  const unsigned long long frac = M * (unsigned long long)u;
+#ifdef __CUDA_ARCH__
+  return (unsigned)__umul64hi(frac, (unsigned long long)n);
+#else
+  return (unsigned)(((unsigned __int128)frac * n) >> 64);
+#endif
+}
+// hash_table.cu:157-168: ((x * 73856093) ^ (y * 19349669) ^ (z * 83492791)) % num_buckets on ints, + num_buckets if negative -
+// i.e. the mathematical (floor) modulus of the SIGNED 32-bit hash h.  With u = (unsigned)h: h = u - 2^32 [h < 0], so
+// h mod n = (u mod n - [h < 0] * (2^32 mod n)) mod n.  tests/test_abi.py pins it against Python's % on ints.
+__host__ __device__ __forceinline__ int hash_slot(int x, int y, int z, int num_buckets, unsigned long long magic, unsigned c32) {
+  const int h = (int)((unsigned)x * 73856093u) ^ (int)((unsigned)y * 19349669u) ^ (int)((unsigned)z * 83492791u);
+  int r = (int)fast_umod((unsigned)h, (unsigned)num_buckets, magic);
+  if (h < 0) { r -= (int)c32; if (r < 0) r += num_buckets; }
+  return r;
+}
+__device__ __forceinline__ long long hash_bucket(const FusionDev& d, int x, int y, int z) {
+  return (long long)hash_slot(x, y, z, d.o.num_buckets, d.mod_magic, d.mod_c32) * d.o.bucket_size;
 }
 
 // Dilated block-occupancy bitmap (the ray-cast's empty-space test).  One bit per block coordinate modulo 128 per axis
@@ -175,7 +203,7 @@ __device__ bool insert_block(const FusionDev& d, int x, int y, int z) {
   if (x <= -kKeyBias || x >= kKeyBias || y <= -kKeyBias || y >= kKeyBias || z <= -kKeyBias || z >= kKeyBias) return false;
   if (!slab_stores(d, z)) return false;   // another rank's Z-slab
   const unsigned long long key = pack_key(x, y, z);
-  const long long b = hash_bucket(d.o, x, y, z);
+  const long long b = hash_bucket(d, x, y, z);
   for (int i = 0; i < d.o.bucket_size; ++i) {
     unsigned long long cur = d.keys[b + i];
     if (cur == key) return true;
@@ -216,19 +244,19 @@ __device__ __forceinline__ void insert_filtered(const FusionDev& d, unsigned lon
   if (insert_block(d, x, y, z)) sfilter[slot] = key;
 }
 
-__device__ __forceinline__ int find_in(const unsigned long long* __restrict__ keys, const int* __restrict__ ptrs, const tdm_fusion_options& o,
+__device__ __forceinline__ int find_in(const unsigned long long* __restrict__ keys, const int* __restrict__ ptrs, const FusionDev& d,
                                        int x, int y, int z) {  // hash_table.cu:141-155
   if (x <= -kKeyBias || x >= kKeyBias || y <= -kKeyBias || y >= kKeyBias || z <= -kKeyBias || z >= kKeyBias) return -1;
   const unsigned long long key = pack_key(x, y, z);
-  const long long b = hash_bucket(o, x, y, z);
-  for (int i = 0; i < o.bucket_size; ++i) {
+  const long long b = hash_bucket(d, x, y, z);
+  for (int i = 0; i < d.o.bucket_size; ++i) {
     const unsigned long long k = keys[b + i];
     if (k == key) return ptrs[b + i];
     if (k == kEmptyKey) return -1;   // inserts fill a bucket front to back and nothing is ever removed: a free slot ends the search
   }
   return -1;
 }
-__device__ __forceinline__ int find_block(const FusionDev& d, int x, int y, int z) { return find_in(d.keys, d.ptrs, d.o, x, y, z); }
+__device__ __forceinline__ int find_block(const FusionDev& d, int x, int y, int z) { return find_in(d.keys, d.ptrs, d, x, y, z); }
 
 // ---------------------------------------------------------------------------------------------- K5
 template <bool FILTER>
@@ -442,6 +470,8 @@ struct Cache1 {
     const int p = find(d, bx, by, bz);
     return p < 0 ? nullptr : d.voxels + (size_t)p * 512;
   }
+  __device__ __forceinline__ bool holds(int bx, int by, int bz) const { return bx == x && by == y && bz == z; }
+  __device__ __forceinline__ const uint2* held(const FusionDev& d) const { return ptr < 0 ? nullptr : d.voxels + (size_t)ptr * 512; }
 };
 // Last-block cache over the PEER view: the block is looked up in the table of the rank that owns its z row and its voxels are
 // read from that rank's pool - local HBM for this rank's own rows, NVLink P2P loads for the others.
@@ -456,12 +486,14 @@ struct CachePeer {
       int r = 0;
       while (r < d.pr_world - 1 && bz >= d.pr_hi[r]) ++r;     // contiguous slabs in rank order
       if (bz >= d.pr_lo[r] && bz < d.pr_hi[r]) {
-        const int p = find_in(d.pr_keys[r], d.pr_ptrs[r], d.o, bx, by, bz);
+        const int p = find_in(d.pr_keys[r], d.pr_ptrs[r], d, bx, by, bz);
         if (p >= 0) base = d.pr_voxels[r] + (size_t)p * 512;
       }
     }
     return base;
   }
+  __device__ __forceinline__ bool holds(int bx, int by, int bz) const { return bx == x && by == y && bz == z; }
+  __device__ __forceinline__ const uint2* held(const FusionDev&) const { return base; }
 };
 struct Cache8 {
   unsigned long long* keys;   // [8][256] in shared memory, this thread's column
@@ -527,7 +559,10 @@ __device__ uint2 get_interpolated(const FusionDev& d, float3 p, Cache& bc) {  //
 // corners are index-adjacent and sit inside one voxel block (two thirds of all samples) they are read from ONE block lookup at
 // constant offsets.  ncu on the one-lookup-per-voxel form: 502 M warp instructions per 640x480 render, 18 % of them FP32.
 __device__ __forceinline__ int w2g_axis(float q /* = x / s */, float x) {   // tsdf_volume.cu:109-113, division hoisted
-  return (int)add_(q, mul_((float)sgn(x), 0.5f));
+  // sgn(x) * 0.5f is exactly +-0.5f, or +0.f for x == 0 and NaN: two selects instead of two set-compares, a subtraction, an
+  // int -> float conversion and a multiplication (ncu: this line and sgn() were 10 % of the ray-cast's instructions)
+  const float h = x > 0.f ? 0.5f : (x < 0.f ? -0.5f : 0.f);
+  return (int)add_(q, h);
 }
 template <class Cache>
 __device__ __forceinline__ uint2 voxel_at(const FusionDev& d, int gx, int gy, int gz, Cache& bc) {
@@ -537,7 +572,7 @@ __device__ __forceinline__ uint2 voxel_at(const FusionDev& d, int gx, int gy, in
 }
 // COLOR = false: the marching steps only consume the interpolated sdf and the centre voxel's weight; the colour blend (8 corners
 // x 3 channels of unpack / convert / multiply-add: a fifth of the sample's instructions) is only evaluated for the final hit.
-template <class Cache, bool COLOR = true, bool FAST = false>
+template <class Cache, bool COLOR = true, bool FAST = false, bool DEDUP = true>
 __device__ uint2 get_interpolated_shared(const FusionDev& d, float3 p, Cache& bc) {
   const float s = d.o.voxel_size, rs = d.r_vs;
   const float3 vp = make_float3(cdiv_<FAST>(p.x, s, rs), cdiv_<FAST>(p.y, s, rs), cdiv_<FAST>(p.z, s, rs));
@@ -564,6 +599,34 @@ __device__ uint2 get_interpolated_shared(const FusionDev& d, float3 p, Cache& bc
       c[0] = __ldg(b); c[1] = __ldg(b + 64); c[2] = __ldg(b + 8); c[3] = __ldg(b + 1);
       c[4] = __ldg(b + 72); c[5] = __ldg(b + 9); c[6] = __ldg(b + 65); c[7] = __ldg(b + 73);
     }
+  } else if constexpr (DEDUP) {
+    // The eight corners span at most two block rows per axis.  Reading them corner by corner through the one-entry cache
+    // ping-pongs between the blocks (order 000,100,010,001,...: up to seven hash probes per sample, and - SIMT - every warp
+    // has lanes on this path at every step: ncu counted ~600 warp instructions per marching step, two thirds of them probes).
+    // Here every DISTINCT block is looked up once: P_ijk = block (bx_i, by_j, bz_k), and a combination that does not cross
+    // a block face on some axis re-uses the pointer of its neighbour (typical sample: one axis crosses -> one new probe).
+    // Pure memoisation of find_block on a volume that is constant during the render -> bit-identical.
+    const int bx0 = gx0 >> 3, bx1 = gx1 >> 3, by0 = gy0 >> 3, by1 = gy1 >> 3, bz0 = gz0 >> 3, bz1 = gz1 >> 3;
+    const bool cx = bx1 != bx0, cy = by1 != by0, cz = bz1 != bz0;
+    const int ox0 = (gx0 & 7) * 64, ox1 = (gx1 & 7) * 64, oy0 = (gy0 & 7) * 8, oy1 = (gy1 & 7) * 8, oz0 = gz0 & 7, oz1 = gz1 & 7;
+    auto rd = [](const uint2* blk, int off) { return blk ? __ldg(blk + off) : make_uint2(0u, 0u); };
+    // A = block of the 0-side corner, Z = block of the 1-side corner.  With ONE crossing axis (87 % of these samples) every
+    // corner lies in A or Z; only samples that cross two or three faces need more probes.  (Each bc.block call site is
+    // executed by the warp whenever ANY lane needs it - the ordering below keeps the rarely needed sites rarely executed.)
+    // (the one-entry cache holds the centre voxel's block, which is A or Z: when it is Z, keep it before A's lookup evicts it)
+    const bool any = cx || cy || cz, zheld = any && bc.holds(bx1, by1, bz1);
+    const uint2* pZh = zheld ? bc.held(d) : nullptr;
+    const uint2* pA = bc.block(d, bx0, by0, bz0);
+    const uint2* pZ = !any ? pA : (zheld ? pZh : bc.block(d, bx1, by1, bz1));
+    const uint2* p100 = !cx ? pA : ((!cy && !cz) ? pZ : bc.block(d, bx1, by0, bz0));
+    const uint2* p010 = !cy ? pA : ((!cx && !cz) ? pZ : bc.block(d, bx0, by1, bz0));
+    const uint2* p001 = !cz ? pA : ((!cx && !cy) ? pZ : bc.block(d, bx0, by0, bz1));
+    const uint2* p110 = !cz ? pZ : (!cx ? p010 : (!cy ? p100 : bc.block(d, bx1, by1, bz0)));
+    const uint2* p101 = !cy ? pZ : (!cx ? p001 : (!cz ? p100 : bc.block(d, bx1, by0, bz1)));
+    const uint2* p011 = !cx ? pZ : (!cy ? p001 : (!cz ? p010 : bc.block(d, bx0, by1, bz1)));
+    c[0] = rd(pA, ox0 + oy0 + oz0);   c[1] = rd(p100, ox1 + oy0 + oz0); c[2] = rd(p010, ox0 + oy1 + oz0);
+    c[3] = rd(p001, ox0 + oy0 + oz1); c[4] = rd(p110, ox1 + oy1 + oz0); c[5] = rd(p011, ox0 + oy1 + oz1);
+    c[6] = rd(p101, ox1 + oy0 + oz1); c[7] = rd(pZ, ox1 + oy1 + oz1);
   } else {
     c[0] = voxel_at(d, gx0, gy0, gz0, bc); c[1] = voxel_at(d, gx1, gy0, gz0, bc); c[2] = voxel_at(d, gx0, gy1, gz0, bc);
     c[3] = voxel_at(d, gx0, gy0, gz1, bc); c[4] = voxel_at(d, gx1, gy1, gz0, bc); c[5] = voxel_at(d, gx0, gy1, gz1, bc);
@@ -614,7 +677,7 @@ __device__ __forceinline__ long long pack_hit_key(float depth, unsigned bgr24) {
 // lies in a block this volume does not store, i.e. the sample would return weight 0 and the ray would step by exactly tau - so
 // only `cur += tau` is executed (3 FMA + 3 floor + one L1-resident load instead of the pixel -> world transform, three
 // divisions, the hash probe and its dependent L2 miss).  Every sample that IS evaluated sits where the un-shortcut march puts it.
-template <int TW, int TH, int MINB, bool SLAB, bool FAST, bool PEER = false, bool OCC = false>
+template <int TW, int TH, int MINB, bool SLAB, bool FAST, bool PEER = false, bool OCC = false, bool DEDUP = true>
 __global__ void __launch_bounds__(TW * TH, MINB)
 k_raycast_shared(FusionDev d, Mat4 T, unsigned char* __restrict__ bgr_out, float* __restrict__ depth_out, long long* __restrict__ keys) {
   const tdm_fusion_options& o = d.o;
@@ -622,6 +685,7 @@ k_raycast_shared(FusionDev d, Mat4 T, unsigned char* __restrict__ bgr_out, float
   const int y = blockIdx.y * TH + (threadIdx.x / TW);
   if (x >= o.width || y >= o.height) return;
   const int i = y * o.width + x;
+  const float ucx = sub_((float)x, o.cx), vcy = sub_((float)y, o.cy);   // get_point3d's pixel terms (utils.h:93-101)
   if constexpr (PEER) {
     if ((int)((blockIdx.y * gridDim.x + blockIdx.x) % (unsigned)d.pr_world) != d.pr_rank) {   // another rank's tile
       bgr_out[3 * i] = bgr_out[3 * i + 1] = bgr_out[3 * i + 2] = 0;
@@ -702,7 +766,7 @@ k_raycast_shared(FusionDev d, Mat4 T, unsigned char* __restrict__ bgr_out, float
       const int bz = __float2int_rd(fmaf(occ_d[2], cur, occ_o[2]));
       if (!((__ldg(d.occ + occ_word(bx, by, bz)) >> (bz & 31)) & 1u)) { cur = add_(cur, o.truncation_distance); continue; }
     }
-    const uint2 v = get_interpolated_shared<decltype(bc), false, FAST>(d, xform(T, get_point3d_c<FAST>(d, i, cur)), bc);
+    const uint2 v = get_interpolated_shared<decltype(bc), false, FAST, DEDUP>(d, xform(T, get_point3d_px<FAST>(d, ucx, vcy, cur)), bc);
     const unsigned w = v.y >> 24;
     const float sdf = __uint_as_float(v.x);
     cur = add_(cur, w == 0 ? o.truncation_distance : sdf);
@@ -710,7 +774,7 @@ k_raycast_shared(FusionDev d, Mat4 T, unsigned char* __restrict__ bgr_out, float
   }
   // (un-clipped march: a ray that runs out of range ends with cur >= max_sensor_depth; the slab march may also stop behind the slab)
   if (hit && cur < o.max_sensor_depth) {
-    const uint2 v = get_interpolated_shared<decltype(bc), true, FAST>(d, xform(T, get_point3d_c<FAST>(d, i, cur)), bc);
+    const uint2 v = get_interpolated_shared<decltype(bc), true, FAST, DEDUP>(d, xform(T, get_point3d_px<FAST>(d, ucx, vcy, cur)), bc);
     bgr_out[3 * i] = v.y & 0xFF; bgr_out[3 * i + 1] = (v.y >> 8) & 0xFF; bgr_out[3 * i + 2] = (v.y >> 16) & 0xFF;
     depth_out[i] = cur;
     if (keys) keys[i] = pack_hit_key(cur, v.y);
@@ -927,6 +991,8 @@ class FusionImpl final : public FusionIface {
       fast_div_ = fast_div_ok_ && e && e[0] == '1';
     }
     n_entries_ = (long long)o.num_buckets * o.bucket_size;
+    d_.mod_magic = 0xFFFFFFFFFFFFFFFFull / (unsigned long long)o.num_buckets + 1ull;
+    d_.mod_c32 = (unsigned)((1ull << 32) % (unsigned long long)o.num_buckets);
     int lo, hi;
     TDM_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
     TDM_CUDA(cudaStreamCreateWithPriority(&stream_, cudaStreamNonBlocking, lo));  // low priority as tsdf_volume.cu:64-75
@@ -1201,6 +1267,7 @@ class FusionImpl final : public FusionIface {
     else if (n == "fast_div") fast_div_ = value != 0 && fast_div_ok_;
     else if (n == "slab_exchange") slab_exchange_ = value != 0;
     else if (n == "occ_skip") occ_skip_ = value != 0;
+    else if (n == "raycast_dedup") raycast_dedup_ = value != 0;
     else throw Error("unknown fusion option " + n);
   }
   bool mesh_pending() override { return mesh_kind_ != kMeshNone; }
@@ -1301,23 +1368,26 @@ class FusionImpl final : public FusionIface {
           if (!d_hit_keys_) TDM_CUDA(cudaMalloc(&d_hit_keys_, npx * sizeof(long long)));
           keys = d_hit_keys_;
         }
-#define TDM_RAY2(TW_, TH_, MB_, GRID_, THREADS_, OCC_)                                                           \
+#define TDM_RAY2(TW_, TH_, MB_, GRID_, THREADS_, OCC_, DD_)                                                       \
   do {                                                                                                             \
-    if (slab && fast_div_) k_raycast_shared<TW_, TH_, MB_, true, true, false, OCC_><<<GRID_, THREADS_, 0, stream_>>>(d_, render_poses_[i], bo, dout_i, keys);   \
-    else if (slab) k_raycast_shared<TW_, TH_, MB_, true, false, false, OCC_><<<GRID_, THREADS_, 0, stream_>>>(d_, render_poses_[i], bo, dout_i, keys);   \
-    else if (fast_div_) k_raycast_shared<TW_, TH_, MB_, false, true, false, OCC_><<<GRID_, THREADS_, 0, stream_>>>(d_, render_poses_[i], bo, dout_i, keys);   \
-    else k_raycast_shared<TW_, TH_, MB_, false, false, false, OCC_><<<GRID_, THREADS_, 0, stream_>>>(d_, render_poses_[i], bo, dout_i, keys);       \
+    if (slab && fast_div_) k_raycast_shared<TW_, TH_, MB_, true, true, false, OCC_, DD_><<<GRID_, THREADS_, 0, stream_>>>(d_, render_poses_[i], bo, dout_i, keys);   \
+    else if (slab) k_raycast_shared<TW_, TH_, MB_, true, false, false, OCC_, DD_><<<GRID_, THREADS_, 0, stream_>>>(d_, render_poses_[i], bo, dout_i, keys);   \
+    else if (fast_div_) k_raycast_shared<TW_, TH_, MB_, false, true, false, OCC_, DD_><<<GRID_, THREADS_, 0, stream_>>>(d_, render_poses_[i], bo, dout_i, keys);   \
+    else k_raycast_shared<TW_, TH_, MB_, false, false, false, OCC_, DD_><<<GRID_, THREADS_, 0, stream_>>>(d_, render_poses_[i], bo, dout_i, keys);       \
   } while (0)
-#define TDM_RAY(TW_, TH_, MB_, MBO_, GRID_, THREADS_)   /* MBO_: residency asked for with OCC (6 more live registers) */ \
+  /* MB_: residency asked for by the corner-by-corner sampler (round-2 tuning), MBD_: by the block-deduplicating sampler, */ \
+  /* MBO_: with the occupancy shortcut on top (6 more live registers) */                                           \
+#define TDM_RAY(TW_, TH_, MB_, MBD_, MBO_, GRID_, THREADS_)                                                       \
   do {                                                                                                             \
-    if (occ) TDM_RAY2(TW_, TH_, MBO_, GRID_, THREADS_, true);                                                      \
-    else TDM_RAY2(TW_, TH_, MB_, GRID_, THREADS_, false);                                                          \
+    if (occ) TDM_RAY2(TW_, TH_, MBO_, GRID_, THREADS_, true, true);                                                \
+    else if (raycast_dedup_) TDM_RAY2(TW_, TH_, MBD_, GRID_, THREADS_, false, true);                               \
+    else TDM_RAY2(TW_, TH_, MB_, GRID_, THREADS_, false, false);                                                   \
   } while (0)
-        if (peer) k_raycast_shared<8, 8, 24, false, false, true><<<dim3(cdiv(d_.o.width, 8), cdiv(d_.o.height, 8)), 64, 0, stream_>>>(d_, render_poses_[i], bo, dout_i, keys);
-        else if (raycast_tile_ == 0) TDM_RAY(16, 16, 5, 5, grid, 256);
-        else if (raycast_tile_ == 1) TDM_RAY(8, 8, 24, 20, dim3(cdiv(d_.o.width, 8), cdiv(d_.o.height, 8)), 64);
-        else if (raycast_tile_ == 2) TDM_RAY(8, 4, 48, 40, dim3(cdiv(d_.o.width, 8), cdiv(d_.o.height, 4)), 32);
-        else TDM_RAY(16, 8, 12, 10, dim3(cdiv(d_.o.width, 16), cdiv(d_.o.height, 8)), 128);
+        if (peer) k_raycast_shared<8, 8, 20, false, false, true><<<dim3(cdiv(d_.o.width, 8), cdiv(d_.o.height, 8)), 64, 0, stream_>>>(d_, render_poses_[i], bo, dout_i, keys);
+        else if (raycast_tile_ == 0) TDM_RAY(16, 16, 5, 5, 5, grid, 256);
+        else if (raycast_tile_ == 1) TDM_RAY(8, 8, 24, 20, 20, dim3(cdiv(d_.o.width, 8), cdiv(d_.o.height, 8)), 64);
+        else if (raycast_tile_ == 2) TDM_RAY(8, 4, 48, 40, 40, dim3(cdiv(d_.o.width, 8), cdiv(d_.o.height, 4)), 32);
+        else TDM_RAY(16, 8, 12, 10, 10, dim3(cdiv(d_.o.width, 16), cdiv(d_.o.height, 8)), 128);
 #undef TDM_RAY2
 #undef TDM_RAY
       } else if (raycast_persistent_) {
@@ -1496,7 +1566,13 @@ class FusionImpl final : public FusionIface {
   bool fast_div_ok_ = false, fast_div_ = false;   // constant-divisor division in the ray-cast (cdiv_): bit-identical, 3 instructions per division
   std::vector<void*> ipc_opened_;   // peers' allocations mapped with cudaIpcOpenMemHandle (closed in the destructor)
   bool slab_clip_ = true;        // Z-slab volumes: rays are only sampled inside the slab's z range (bit-identical, see k_raycast_shared)
-  bool occ_skip_ = true;         // ray-cast: dilated occupancy bitmap in front of the sampler (bit-identical, see k_raycast_shared OCC)
+  bool raycast_dedup_ = true;    // ray-cast: samples whose corners straddle block faces look every distinct block up once
+  bool occ_skip_ = false;        // ray-cast: dilated occupancy bitmap in front of the sampler (bit-identical, see k_raycast_shared OCC).
+                                 // Measured on the B200 (profiles/r02_fusion_tracker.txt): 0.445 ms with, 0.422 ms without - the
+                                 // reference's allocation DDA walks every ray from the CAMERA to the surface (tsdf_volume.cu:317-434),
+                                 // so the free space a later ray crosses is itself allocated (sdf ~ tau, weight > 0) and every
+                                 // sample there must be interpolated; the bitmap only ever skips what the bounding-box clip
+                                 // already skips.  Kept as an A/B option, off by default.
   bool slab_exchange_ = false;   // Z-slab volumes: the ray-cast emits packed nearest-hit keys for the exchange step, the per-slab
                                  // render is not copied back and GetRenderResult does not wait (tandem_b200.parallel)
   int* d_vis_list_ = nullptr;
@@ -1523,6 +1599,20 @@ class FusionImpl final : public FusionIface {
 };
 
 FusionIface* make_fusion(const tdm_fusion_options& o, int device) { return new FusionImpl(o, device); }
+
+// host-only view of the hash function the kernels use (division-free remainder) beside the reference's expression
+int hash_slot_host(int x, int y, int z, int num_buckets, int* reference_expression) {
+  if (num_buckets <= 0) return -1;
+  const unsigned long long magic = 0xFFFFFFFFFFFFFFFFull / (unsigned long long)num_buckets + 1ull;
+  const unsigned c32 = (unsigned)((1ull << 32) % (unsigned long long)num_buckets);
+  if (reference_expression) {   // hash_table.cu:157-168 as written
+    const int a = (int)((unsigned)x * 73856093u), b = (int)((unsigned)y * 19349669u), c = (int)((unsigned)z * 83492791u);
+    int r = (a ^ b ^ c) % num_buckets;
+    if (r < 0) r += num_buckets;
+    *reference_expression = r;
+  }
+  return hash_slot(x, y, z, num_buckets, magic, c32);
+}
 
 // host-only view of the mesh extractor's per-axis table (no GPU involved; used by the CPU test-suite)
 int mesh_axis_table(float lower, float upper, float voxel_size, int* ints5, float* floats4, int* ranges2, int* bmin, int cap) {

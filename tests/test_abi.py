@@ -163,3 +163,24 @@ def test_constant_division_is_correctly_rounded(tmp_path):
     for fx in (320.0, 80.0, 300.0, 525.0, 481.2):
         assert l.cdiv_check_exhaustive(fx, 1e-3, 16384.0) == 0
     assert l.cdiv_check_random(1, 200_000_000) == 0
+
+
+def test_division_free_hash_equals_the_reference_expression():
+    """Host logic (no GPU): the bucket the voxel-hashing kernels compute with a precomputed reciprocal (fast_umod, fusion.cu)
+    equals ((x * 73856093) ^ (y * 19349669) ^ (z * 83492791)) % num_buckets on 32-bit ints with the +num_buckets fix-up
+    (hash_table.cu:157-168) - against the C expression compiled beside it and against Python's integers."""
+    import random
+    l = lib()
+    ref = ctypes.c_int(0)
+    rnd = random.Random(7)
+    edge = [0, 1, -1, 2, -2, (1 << 20) - 1, -(1 << 20) + 1, 12345, -54321]
+    for n in (1, 2, 3, 7, 10, 1000, 200003, 999983, 1000000, 1000003, 1 << 20, (1 << 31) - 1):
+        pts = [(x, y, z) for x in edge for y in edge[:4] for z in edge[:4]]
+        pts += [tuple(rnd.randint(-(1 << 20), 1 << 20) for _ in range(3)) for _ in range(4000)]
+        for x, y, z in pts:
+            got = l.tdm_debug_hash_slot(x, y, z, n, ctypes.byref(ref))
+            h = ((x * 73856093) & 0xFFFFFFFF) ^ ((y * 19349669) & 0xFFFFFFFF) ^ ((z * 83492791) & 0xFFFFFFFF)
+            h -= (h >> 31) << 32
+            assert got == ref.value == h % n, (n, x, y, z, got, ref.value, h % n)
+    assert l.tdm_debug_hash_slot(1, 2, 3, 0, None) < 0          # rejected, not a division by zero
+

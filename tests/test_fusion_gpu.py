@@ -243,6 +243,54 @@ def test_occupancy_shortcut_is_bit_identical():
     assert min(cover) > 0.9, cover
 
 
+def test_raycast_variants_are_bit_identical():
+    """Every ray-cast variant must put every sample where the reference's GetInterpolatedVoxel march puts it: the kernel
+    that mirrors the reference sampler voxel by voxel (raycast_shared=0: one hash lookup per voxel, IEEE divisions, sgn()) and
+    the production kernel (shared per-axis index arithmetic, one lookup per DISTINCT block of a sample, division-free hash,
+    select-form rounding) with its switches - block de-duplication off, constant-divisor division on, the other tile shapes -
+    render the same volume bit for bit, depth and colour, at 160x120 and at the config-3 shape."""
+    variants = [{"raycast_shared": 0}, {}, {"raycast_dedup": 0}, {"fast_div": 1}, {"raycast_tile": 0}, {"raycast_tile": 2, "fast_div": 1},
+                {"raycast_tile": 3, "raycast_dedup": 0}, {"occ_skip": 1, "fast_div": 1}]
+
+    def run(make, scans, views):
+        vols = []
+        for opts in variants:
+            f = make()
+            for k, v in opts.items():
+                f.set_option(k, v)
+            vols.append(f)
+        for k, q in enumerate(views):
+            bgr, depth, pose = scans[min(k, len(scans) - 1)]
+            ref = None
+            for opts, f in zip(variants, vols):
+                f.IntegrateScanAsync(bgr, depth, pose)
+                f.RenderAsync([q])
+                (rb,), (rd,) = f.GetRenderResult()
+                if ref is None:
+                    ref = (rd.copy(), rb.copy())
+                    assert (rd > 0).mean() > 0.3
+                else:
+                    assert np.array_equal(ref[0].view(np.uint32), rd.view(np.uint32)) and np.array_equal(ref[1], rb), (k, opts)
+
+    poses, frames = _scene_frames(3)
+    for shift in (0.0, -7.3):
+        ps = [p.copy() for p in poses]
+        for p in ps:
+            p[:3, 3] += np.float32(shift)
+        scans = [(bgr, depth, pose) for (bgr, depth), pose in zip(frames, ps)]
+        run(lambda: DrFusion(_opts()), scans, [ps[0], ps[1], ps[2], ps[0]])
+    hh, ww = 480, 640
+    intr = dict(fx=320.0, fy=320.0, cx=319.5, cy=239.5)
+    scene = RoomScene()
+    ps = circle_trajectory(2, radius=1.0)
+    fr = [scene.render(p, hh, ww, **intr, noise_sigma=0.002, dropout=0.02, seed=k) for k, p in enumerate(ps)]
+    for p in ps:
+        p[:3, 3] += np.float32(5.12)
+    scans = [(bgr, depth, pose) for (bgr, depth), pose in zip(fr, ps)]
+    variants = variants[:4]
+    run(lambda: DrFusion(DrFusionOptions(height=hh, width=ww, num_buckets=200003, num_blocks=150000, **intr)), scans, [ps[0], ps[1], ps[0]])
+
+
 def test_z_slab_partition_matches_single_volume():
     """two Z-slabs (each + 1 halo block) integrated from the same scans reproduce the single-volume map on
     their owned blocks bit-for-bit, and the per-pixel nearest-hit reduction of the two slab renders reproduces the
