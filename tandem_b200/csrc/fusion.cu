@@ -49,6 +49,7 @@ struct FusionDev {
   int* counters;             // [0] #blocks allocated, [1] dropped, [2] visible (last scan), [3] new this scan
   int slab_lo, slab_hi;      // Z-slab partition (block z in [slab_lo, slab_hi) is kept), default: everything
   float r_vs, r_fx, r_fy;    // RN(1 / voxel_size), RN(1 / fx), RN(1 / fy) for cdiv_ (ray-cast only)
+  float half_vs;             // RN(voxel_size / 2.0f): the sampler's half-voxel shift (tsdf_volume.cu:166), a per-volume constant
   unsigned long long mod_magic;   // ceil(2^64 / num_buckets): exact 32-bit remainder without a division (fast_umod)
   unsigned mod_c32;               // 2^32 mod num_buckets
   unsigned* occ;             // [128*128*4] dilated block-occupancy bitmap of the blocks THIS volume stores (occ_mark below)
@@ -473,6 +474,23 @@ struct Cache1 {
   __device__ __forceinline__ bool holds(int bx, int by, int bz) const { return bx == x && by == y && bz == z; }
   __device__ __forceinline__ const uint2* held(const FusionDev& d) const { return ptr < 0 ? nullptr : d.voxels + (size_t)ptr * 512; }
 };
+// Cache1 holding the block's BASE POINTER: a hit costs the three compares only (ncu: re-deriving voxels + ptr * 512 on every
+// hit was 4.5 % of the ray-cast's instructions).  Used by the production ray-cast; Cache1 stays with the reference-shaped kernels.
+struct Cache1P {
+  int x, y, z;
+  const uint2* base;
+  __device__ __forceinline__ void init() { x = y = z = INT_MIN; base = nullptr; }
+  __device__ __forceinline__ const uint2* block(const FusionDev& d, int bx, int by, int bz) {
+    if (bx != x || by != y || bz != z) {
+      x = bx; y = by; z = bz;
+      const int p = find_block(d, bx, by, bz);
+      base = p < 0 ? nullptr : d.voxels + (size_t)p * 512;
+    }
+    return base;
+  }
+  __device__ __forceinline__ bool holds(int bx, int by, int bz) const { return bx == x && by == y && bz == z; }
+  __device__ __forceinline__ const uint2* held(const FusionDev&) const { return base; }
+};
 // Last-block cache over the PEER view: the block is looked up in the table of the rank that owns its z row and its voxels are
 // read from that rank's pool - local HBM for this rank's own rows, NVLink P2P loads for the others.
 struct CachePeer {
@@ -578,7 +596,7 @@ __device__ uint2 get_interpolated_shared(const FusionDev& d, float3 p, Cache& bc
   const float3 vp = make_float3(cdiv_<FAST>(p.x, s, rs), cdiv_<FAST>(p.y, s, rs), cdiv_<FAST>(p.z, s, rs));
   const uint2 v0 = voxel_at(d, w2g_axis(vp.x, p.x), w2g_axis(vp.y, p.y), w2g_axis(vp.z, p.z), bc);
   if ((v0.y >> 24) == 0) return v0;
-  const float hs = div_(s, 2.0f);
+  const float hs = d.half_vs;   // = div_(s, 2.0f), hoisted to the host (IEEE division there too)
   const float3 pd = make_float3(sub_(p.x, hs), sub_(p.y, hs), sub_(p.z, hs));
   const float wx = sub_(vp.x, floorf(vp.x)), wy = sub_(vp.y, floorf(vp.y)), wz = sub_(vp.z, floorf(vp.z));
   const float ux = sub_(1.f, wx), uy = sub_(1.f, wy), uz = sub_(1.f, wz);
@@ -694,7 +712,7 @@ k_raycast_shared(FusionDev d, Mat4 T, unsigned char* __restrict__ bgr_out, float
       return;
     }
   }
-  typename std::conditional<PEER, CachePeer, Cache1>::type bc;
+  typename std::conditional<PEER, CachePeer, Cache1P>::type bc;
   bc.init();
   float cur = 0.f;
   float t_exit = FLT_MAX;
@@ -978,6 +996,8 @@ class FusionImpl final : public FusionIface {
       // reciprocals for cdiv_: host IEEE division = correctly rounded (the file is built with -ffp-contract=off, no fast-math)
       volatile float one = 1.0f;
       d_.r_vs = one / o.voxel_size; d_.r_fx = one / o.fx; d_.r_fy = one / o.fy;
+      volatile float two = 2.0f;
+      d_.half_vs = o.voxel_size / two;
       auto ok = [](float d) {
         unsigned u;
         std::memcpy(&u, &d, 4);
