@@ -220,7 +220,12 @@ int tdm_fusion_last_alloc_ms(tdm_fusion* h, float* ms);
  * on B200 they do not pay (the table probes are L2 hits behind other latency); "raycast_persistent" (warps pull rays from a
  * counter and refill finished lanes; default 0 = one ray per thread, which measured faster: 0.82 vs 0.875 ms), "raycast_shared" (index arithmetic shared between the nine voxel reads of a sample, one block lookup when they sit in one
  * block; default 1), "integrate_compact" (visibility pass + update of the
- * visible blocks only, default 1; 0 = every CTA scans the whole block list). */
+ * visible blocks only, default 1; 0 = every CTA scans the whole block list); "raycast_tile" (0: 16x16-pixel CTAs, 1: 8x8
+ * (default), 2: 8x4, 3: 16x8); "raycast_dedup" (a sample whose eight corners straddle voxel-block faces looks every distinct
+ * block up once instead of corner by corner; default 1: 0.31 vs 0.38 ms); "fast_div" (constant-divisor FMA division in the
+ * ray-cast, exhaustively checked correctly rounded; default 0: 0.316 vs 0.311 ms); "occ_skip" (dilated block-occupancy bitmap
+ * in front of the sampler; default 0: 0.330 vs 0.311 ms, a frustum-allocated map has no unallocated space on a ray's way);
+ * "slab_clip" / "slab_exchange" (Z-slab volumes, see above). */
 int tdm_fusion_set_option(tdm_fusion* h, const char* name, int value);
 
 /* ------------------------------------------------------------------------------------------------
