@@ -8,11 +8,13 @@
 //   K5 allocate : one thread per depth PIXEL (the reference sizes its grid by the 10 M hash entries), lock-free
 //                 insert with a single 64-bit CAS on the packed block key (no lock state, no duplicate blocks),
 //                 every new block appended to a compact block list.
-//   K6 integrate: persistent CTAs stride over the compact block list (the reference scans all 10 M entries,
-//                 free ones included), 256 threads x 2 voxels, one 128-bit load + store per thread, no
-//                 per-voxel re-hash.
-//   K7 ray-cast : one thread per pixel in 16x16 tiles, sphere tracing with a per-thread last-block cache so the
-//                 9 lookups of a trilinear sample mostly skip the hash probe.
+//   K6 integrate: a visibility pass compacts the blocks in view, persistent CTAs stride over that list (the reference
+//                 scans all 10 M entries, free ones included), 256 threads x 2 voxels, one 128-bit load + store per
+//                 thread, no per-voxel re-hash.
+//   K7 ray-cast : one thread per pixel in 8x8 tiles, sphere tracing clipped to the bounding box of everything ever
+//                 allocated; per-axis index arithmetic shared by the nine voxel reads of a sample, ONE hash probe per
+//                 distinct voxel block of a sample (one-entry pointer cache in front), division-free bucket index,
+//                 colour blend only for the final hit.  Every sample sits where the reference's march puts it.
 // The hash function, bucket structure (full bucket -> block dropped), voxel record (8 B) and all geometry are
 // the reference's; geometry that decides integers uses __f*_rn intrinsics so it is bit-identical to the CPU
 // oracle (oracle/tsdf_oracle.c) which evaluates the same expressions without FMA contraction.
